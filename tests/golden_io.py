@@ -1,0 +1,86 @@
+"""Helpers shared by the parity tests: load a committed golden case (tests/golden/*.npz, produced by
+tests/golden/make_golden.py from the unmodified reference) into tensors."""
+import argparse
+import ast
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["satnerf_h64", "satnerf_h64_snerfloss_depth", "satnerf_sc_h64", "satnerf_fine_h64", "snerf_sc_h64",
+         "nerf_fine_h64", "satnerf_h512", "satnerf_h256_s96"]
+
+
+def pcg_params(shapes, seed):
+    """Same procedure as tests/golden/make_golden.py::pcg_params (numpy PCG64 stream)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out, fan = {}, {}
+    for name, shape in shapes.items():
+        u = rng.random(int(np.prod(shape)), dtype=np.float32).reshape(shape) * 2 - 1
+        if name.endswith(".weight"):
+            fan[name[:-7]] = shape[1]
+            bound = 1.0 / shape[1] if name in ("fc_net.0.weight", "sun_v_net.0.weight") else np.sqrt(6.0 / shape[1])
+        else:
+            bound = 1.0 / np.sqrt(fan[name[:-5]])
+        out[name] = (u * np.float32(bound)).astype(np.float32)
+    return out
+
+
+def field_shapes(model, h, layers=8, tau=4, skips=(4,)):
+    """Parameter shapes in the reference's state_dict order (models/satnerf.py:104-153, snerf.py, nerf.py)."""
+    in0, in1 = (60, 24) if model == "nerf" else (3, 0)
+    sh = {}
+    for i in range(layers):
+        k = in0 if i == 0 else (h + in0 if i in skips else h)
+        sh[f"fc_net.{2 * i}.weight"] = (h, k); sh[f"fc_net.{2 * i}.bias"] = (h,)
+    sh["sigma_from_xyz.0.weight"] = (1, h); sh["sigma_from_xyz.0.bias"] = (1,)
+    sh["feats_from_xyz.weight"] = (h, h); sh["feats_from_xyz.bias"] = (h,)
+    sh["rgb_from_xyzdir.0.weight"] = (h // 2, h + in1); sh["rgb_from_xyzdir.0.bias"] = (h // 2,)
+    sh["rgb_from_xyzdir.2.weight"] = (3, h // 2); sh["rgb_from_xyzdir.2.bias"] = (3,)
+    if model != "nerf":
+        sh["sun_v_net.0.weight"] = (h // 2, h + 3); sh["sun_v_net.0.bias"] = (h // 2,)
+        for j in (2, 4):
+            sh[f"sun_v_net.{j}.weight"] = (h // 2, h // 2); sh[f"sun_v_net.{j}.bias"] = (h // 2,)
+        sh["sun_v_net.6.weight"] = (1, h // 2); sh["sun_v_net.6.bias"] = (1,)
+        sh["sky_color.0.weight"] = (h // 2, 3); sh["sky_color.0.bias"] = (h // 2,)
+        sh["sky_color.2.weight"] = (3, h // 2); sh["sky_color.2.bias"] = (3,)
+    if model == "sat-nerf":
+        sh["beta_from_xyz.0.weight"] = (h // 2, h + tau); sh["beta_from_xyz.0.bias"] = (h // 2,)
+        sh["beta_from_xyz.2.weight"] = (1, h // 2); sh["beta_from_xyz.2.bias"] = (1,)
+    return sh
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+        self.name = name
+        self.cfg = argparse.Namespace(**ast.literal_eval(str(z["cfg"])), chunk=5120)
+        self.rays = torch.from_numpy(z["rays"])
+        self.ts = torch.from_numpy(z["ts"]) if "ts" in z else None
+        self.draws = [torch.from_numpy(z[f"draw{i}"]) for i in range(int(z["n_draws"]))]
+        self.out = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("out.")}
+        self.params = {}
+        levels = ["coarse"] + (["fine"] if self.cfg.n_importance > 0 else [])
+        if "pcg_seed" in z:
+            sh = field_shapes(self.cfg.model, self.cfg.fc_units, self.cfg.fc_layers, self.cfg.t_embbeding_tau)
+            for i, lvl in enumerate(levels):
+                self.params[lvl] = {k: torch.from_numpy(v) for k, v in pcg_params(sh, int(z["pcg_seed"]) + i).items()}
+        else:
+            for lvl in levels:
+                pre = f"param.{lvl}."
+                self.params[lvl] = {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+        if "param.t" in z:
+            self.params["t"] = torch.from_numpy(z["param.t"])
+        self.grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad.")}
+        self.loss_kind = str(z["loss_kind"]) if "loss_kind" in z else None
+        self.target = torch.from_numpy(z["target"]) if "target" in z else None
+        self.loss = float(z["loss"]) if "loss" in z else None
+        self.depth_target = torch.from_numpy(z["depth_target"]) if "depth_target" in z else None
+        self.depth_weights = torch.from_numpy(z["depth_weights"]) if "depth_weights" in z else None
+
+
+def rel_err(a, b, floor=1e-6):
+    """max |a-b| / max(max|b|, floor): the 'max-abs over max-ref' measure SURVEY.md §7 uses for the 1e-3 target."""
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))
