@@ -1,0 +1,156 @@
+/*
+ * satnerf_b200 — C-ABI of the B200-native Sat-NeRF volumetric-rendering hot path.
+ *
+ * The reference (centreborelli/satnerf @ 700a5919) is pure Python and has no FFI layer; its
+ * boundary for this path is two Python callables:
+ *     rendering.render_rays(models, args, rays, ts)            rendering.py:52
+ *     models.<variant>.inference(model, args, xyz, z_vals, …)  models/satnerf.py:4, snerf.py:4, nerf.py:71
+ *     <Field>.forward(input_xyz, input_dir, input_sun_dir, input_t)   satnerf.py:156, snerf.py:148, nerf.py:184
+ * The entry points below are what a ctypes binding for those callables binds (the binding itself is
+ * satnerf_b200/capi.py; INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (int64 where stated), row-major, contiguous;
+ *     NULL means "absent" (input) or "not wanted" (output);
+ *   - no allocation and no hidden streams inside the library: the caller passes a workspace
+ *     (size from snb_render_workspace) and the cudaStream_t (as void*) to launch on;
+ *   - every function returns 0 on success; otherwise a negative code, and snb_last_error()
+ *     (thread-local) describes it.  Nothing falls back to the CPU.
+ *   - parameters live in ONE flat fp32 buffer in the reference's state_dict() order, each
+ *     nn.Linear as weight[out][in] followed by bias[out] (snb_param_layout lists the offsets).
+ */
+#ifndef SATNERF_B200_H
+#define SATNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SNB_API __attribute__((visibility("default")))
+#else
+#define SNB_API
+#endif
+
+/* args.model (opt.py:34): which field / inference() variant */
+enum { SNB_NERF = 0, SNB_SNERF = 1, SNB_SATNERF = 2 };
+/* arithmetic of the MLP contractions */
+enum { SNB_FP32_SIMT = 0,   /* fp32 FFMA on CUDA cores: the exactness path                        */
+       SNB_FP16_TC = 1 };   /* fp16 operands / fp32 accumulate on tcgen05 tensor cores (sm_100a);
+                               first trunk layer and all head outputs stay fp32                    */
+
+/* Field architecture = constructor arguments of models.load_model (models/__init__.py:6-15). */
+typedef struct snb_field_desc {
+    int32_t variant;     /* SNB_NERF | SNB_SNERF | SNB_SATNERF                                  */
+    int32_t n_layers;    /* args.fc_layers (8)                                                  */
+    int32_t width;       /* args.fc_units  (512)                                                */
+    int32_t skip_layer;  /* trunk layer whose input is cat([x, h]) (skips=[4]); -1 = none       */
+    int32_t t_dims;      /* args.t_embbeding_tau (sat-nerf), else 0                             */
+    int32_t pe_xyz;      /* Mapping frequencies for xyz (nerf: 10), 0 = identity                */
+    int32_t pe_dir;      /* Mapping frequencies for the view direction (nerf: 4)                */
+} snb_field_desc;
+
+/* One inference() pass (models/satnerf.py:4-79) over R rays x S samples. */
+typedef struct snb_pass_desc {
+    int32_t n_rays;          /* R                                                               */
+    int32_t n_samples;       /* S (coarse: args.n_samples; fine: n_samples + n_importance)      */
+    int32_t ray_cols;        /* 8 (nerf) or 11: o(3) d(3) near far [sun(3)]  (rendering.py:62)  */
+    int32_t march_along_sun; /* 1 = solar-correction pass, points = o + sun_d*z (rendering.py:104) */
+    int32_t precision;       /* SNB_FP32_SIMT | SNB_FP16_TC                                     */
+    float   noise_std;       /* args.noise_std; multiplies `noise` (satnerf.py:57-58)           */
+} snb_pass_desc;
+
+typedef struct snb_render_io {
+    /* inputs */
+    const float* params;        /* flat parameter buffer of the field                           */
+    const float* rays;          /* (R, ray_cols); may be NULL when xyz and aux_dir are given    */
+    const float* z_vals;        /* (R, S) sample depths                                         */
+    const float* t_emb;         /* (R, t_dims) = models['t'](ts)  (rendering.py:100); sat-nerf  */
+    const float* noise;         /* (R, S) standard-normal draws, or NULL for none               */
+    const float* xyz;           /* (R,S,3) optional explicit sample positions — the `rays_xyz`
+                                   argument of inference() (satnerf.py:4); NULL: o + dir*z      */
+    const float* aux_dir;       /* (R,3) optional `sun_d` / `rays_d` argument of inference();
+                                   NULL: taken from rays[:, 8:11] / rays[:, 3:6]                */
+    /* outputs = the dict returned by inference(); any may be NULL                              */
+    float* rgb;                 /* (R,3)                                                        */
+    float* depth;               /* (R)                                                          */
+    float* weights;             /* (R,S)                                                        */
+    float* transparency;        /* (R,S)                                                        */
+    float* albedo;              /* (R,S,3)  (nerf: unused)                                      */
+    float* sun;                 /* (R,S,1)                                                      */
+    float* sky;                 /* (R,S,3)                                                      */
+    float* beta;                /* (R,S,1)  sat-nerf only                                       */
+    float* sigma;               /* (R,S) densities; stash needed by snb_render_backward         */
+    float* nerf_rgb;            /* (R,S,3) per-sample colour of the nerf variant (stash)        */
+} snb_render_io;
+
+typedef struct snb_render_grads {
+    /* upstream gradients w.r.t. the outputs above; NULL = zero */
+    const float* g_rgb;  const float* g_depth;  const float* g_weights;  const float* g_transparency;
+    const float* g_albedo;  const float* g_sun;  const float* g_sky;  const float* g_beta;
+    /* results */
+    float* g_params;            /* flat, same layout as params; ACCUMULATED into (+=)           */
+    float* g_t_emb;             /* (R, t_dims), overwritten; NULL if not wanted                 */
+} snb_render_grads;
+
+SNB_API int         snb_abi_version(void);
+SNB_API const char* snb_last_error(void);
+/* number of CUDA kernels this library has launched since the last reset (bench accounting) */
+SNB_API int64_t     snb_launch_count(int reset);
+/* 1 when the device of the current context can run the tcgen05 path (compute capability 10.x). */
+SNB_API int         snb_device_supports_tc(void);
+
+/* Flat parameter layout: returns the number of nn.Linear layers L (or <0); fills up to `cap`
+ * entries: weight offset, bias offset (in floats), rows (=out) and cols (=in).
+ * Order = state_dict() order of models/satnerf.py:104-153 / snerf.py / nerf.py:157-177. */
+SNB_API int     snb_param_layout(const snb_field_desc* f, int64_t* w_off, int64_t* b_off,
+                         int32_t* n_out, int32_t* n_in, int cap);
+SNB_API int64_t snb_param_count(const snb_field_desc* f);
+
+/* rendering.py:65-78: z = lower + (upper-lower)*u over the stratified bins of [near, far].
+ * steps = torch.linspace(0,1,S) (S floats, device); u (R,S) uniform draws; z (R,S) out.        */
+SNB_API int snb_stratified_depths(const float* rays, int ray_cols, const float* steps, const float* u,
+                          float* z, int n_rays, int n_samples, void* stream);
+
+/* rendering.py:121-125 + sample_pdf (:10-49): importance-sample n_imp depths from the coarse
+ * weights and merge them (sorted) with the coarse depths.  u (R,n_imp) uniform draws.
+ * z_out (R, S+n_imp).  Optional debug outputs: inds (R,n_imp) int64 = searchsorted result (:36),
+ * z_new (R,n_imp) unsorted samples, cdf (R,S-1).                                               */
+SNB_API int snb_importance_depths(const float* z_coarse, const float* weights_coarse, const float* u,
+                          float* z_out, int64_t* inds, float* z_new, float* cdf,
+                          int n_rays, int n_samples, int n_imp, void* stream);
+
+/* searchsorted(cdf, u, right=True) alone (rendering.py:36) — pure comparisons, bit-exact.      */
+SNB_API int snb_searchsorted_right(const float* cdf, const float* u, int64_t* inds,
+                           int n_rays, int n_cdf, int n_u, void* stream);
+
+/* Workspace (bytes) needed by forward / backward of a pass. */
+SNB_API int snb_render_workspace(const snb_field_desc* f, const snb_pass_desc* p, int backward, size_t* bytes);
+
+/* inference(): field at every sample + alpha compositing (satnerf.py:4-79, snerf.py:4-75, nerf.py:71-133) */
+SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient of the same pass w.r.t. the flat parameters and t_emb (what autograd derives for the
+ * reference).  `io` must carry the forward's inputs and saved outputs
+ * (weights, transparency, albedo, sun, sky, beta, sigma; nerf: nerf_rgb).                      */
+SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
+                        const snb_render_grads* g, void* workspace, size_t workspace_bytes, void* stream);
+
+/* <Field>.forward on B independent points (satnerf.py:156-208): xyz (B,3); aux_dir (B,3) = sun
+ * direction (sat-nerf / s-nerf) or view direction (nerf); t_emb (B,t_dims); out (B,C) with
+ * C = 9 / 8 / 4 = [rgb3, sigma, sun, sky3, beta]; sigma_only -> out (B,1) (satnerf.py:184-185). */
+SNB_API int snb_field_workspace(const snb_field_desc* f, int n_points, size_t* bytes);
+SNB_API int snb_field_forward(const snb_field_desc* f, const float* params, const float* xyz,
+                      const float* aux_dir, const float* t_emb, float* out, int n_points,
+                      int sigma_only, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATNERF_B200_H */

@@ -1,0 +1,233 @@
+"""ctypes binding of libsatnerf_b200.so (C ABI declared in include/satnerf_b200.h).
+
+PyTorch is used for device memory and streams only: every call passes raw device pointers
+(`tensor.data_ptr()`) and the current CUDA stream handle.  There is no CPU or eager fallback:
+a missing library, a CPU tensor or a non-zero return code raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsatnerf_b200.so")
+
+NERF, SNERF, SATNERF = 0, 1, 2
+FP32_SIMT, FP16_TC = 0, 1
+VARIANTS = {"nerf": NERF, "s-nerf": SNERF, "sat-nerf": SATNERF}
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("n_layers", C.c_int32), ("width", C.c_int32), ("skip_layer", C.c_int32),
+                ("t_dims", C.c_int32), ("pe_xyz", C.c_int32), ("pe_dir", C.c_int32)]
+
+
+class PassDesc(C.Structure):
+    _fields_ = [("n_rays", C.c_int32), ("n_samples", C.c_int32), ("ray_cols", C.c_int32),
+                ("march_along_sun", C.c_int32), ("precision", C.c_int32), ("noise_std", C.c_float)]
+
+
+_IO_FIELDS = ["params", "rays", "z_vals", "t_emb", "noise", "xyz", "aux_dir", "rgb", "depth", "weights", "transparency",
+              "albedo", "sun", "sky", "beta", "sigma", "nerf_rgb"]
+_GRAD_FIELDS = ["g_rgb", "g_depth", "g_weights", "g_transparency", "g_albedo", "g_sun", "g_sky", "g_beta",
+                "g_params", "g_t_emb"]
+
+
+class RenderIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _IO_FIELDS]
+
+
+class RenderGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _GRAD_FIELDS]
+
+
+_SIGNATURES = {
+    "snb_abi_version": (C.c_int, []),
+    "snb_last_error": (C.c_char_p, []),
+    "snb_device_supports_tc": (C.c_int, []),
+    "snb_launch_count": (C.c_int64, [C.c_int]),
+    "snb_param_layout": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
+    "snb_param_count": (C.c_int64, [C.POINTER(FieldDesc)]),
+    "snb_stratified_depths": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "snb_importance_depths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "snb_searchsorted_right": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "snb_render_workspace": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.c_int, C.POINTER(C.c_size_t)]),
+    "snb_render_forward": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.POINTER(RenderIO), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_render_backward": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(RenderGrads),
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_field_workspace": (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.POINTER(C.c_size_t)]),
+    "snb_field_forward": (C.c_int, [C.POINTER(FieldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library once; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: build it with `python -m satnerf_b200.build` "
+                "(satnerf_b200 has no CPU or eager fallback)")
+        handle = C.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if handle.snb_abi_version() != 1:
+            raise RuntimeError("libsatnerf_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def _check(code: int, what: str):
+    if code != 0:
+        raise RuntimeError(f"{what} failed ({code}): {lib().snb_last_error().decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("satnerf_b200 runs on CUDA tensors only (no CPU fallback)")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise RuntimeError(f"expected contiguous {dtype} tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def field_desc(variant: str, n_layers: int, width: int, skips, t_dims: int = 0, mapping_sizes=(10, 4), mapping=None) -> FieldDesc:
+    if variant not in VARIANTS:
+        raise ValueError(f"model {variant} is not valid")      # same error as models/__init__.py:14
+    skips = list(skips)
+    if len(skips) > 1:
+        raise ValueError("only a single skip connection is supported")
+    if mapping is None:
+        mapping = variant == "nerf"
+    return FieldDesc(VARIANTS[variant], n_layers, width, skips[0] if skips else -1, t_dims if variant == "sat-nerf" else 0,
+                     mapping_sizes[0] if mapping else 0, mapping_sizes[1] if mapping else 0)
+
+
+def param_layout(desc: FieldDesc):
+    """[(w_off, b_off, n_out, n_in)] in state_dict order — host arithmetic only, usable without a GPU."""
+    cap = 64
+    w, b = (C.c_int64 * cap)(), (C.c_int64 * cap)()
+    no, ni = (C.c_int32 * cap)(), (C.c_int32 * cap)()
+    n = lib().snb_param_layout(C.byref(desc), w, b, no, ni, cap)
+    if n < 0:
+        _check(n, "snb_param_layout")
+    return [(w[i], b[i], no[i], ni[i]) for i in range(n)]
+
+
+def param_count(desc: FieldDesc) -> int:
+    n = lib().snb_param_count(C.byref(desc))
+    if n < 0:
+        _check(int(n), "snb_param_count")
+    return int(n)
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().snb_launch_count(int(reset)))
+
+
+def device_supports_tc() -> bool:
+    return bool(lib().snb_device_supports_tc())
+
+
+# ---- workspace cache (one growing buffer per device; calls are ordered on the current stream) ----
+_workspaces: Dict[int, torch.Tensor] = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _workspaces.get(idx)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces[idx] = ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+    return ws
+
+
+def stratified_depths(rays, steps, u):
+    R, S = u.shape
+    z = torch.empty_like(u)
+    with torch.cuda.device(rays.device):
+        _check(lib().snb_stratified_depths(_ptr(rays), rays.shape[1], _ptr(steps), _ptr(u), _ptr(z), R, S, _stream(rays.device)),
+               "snb_stratified_depths")
+    return z
+
+
+def importance_depths(z_coarse, weights_coarse, u, debug=False):
+    R, S = z_coarse.shape
+    N = u.shape[1]
+    z_out = torch.empty(R, S + N, device=u.device, dtype=torch.float32)
+    inds = torch.empty(R, N, device=u.device, dtype=torch.int64) if debug else None
+    z_new = torch.empty(R, N, device=u.device, dtype=torch.float32) if debug else None
+    cdf = torch.empty(R, S - 1, device=u.device, dtype=torch.float32) if debug else None
+    with torch.cuda.device(u.device):
+        _check(lib().snb_importance_depths(_ptr(z_coarse), _ptr(weights_coarse), _ptr(u), _ptr(z_out), _ptr(inds, torch.int64),
+                                           _ptr(z_new), _ptr(cdf), R, S, N, _stream(u.device)), "snb_importance_depths")
+    return (z_out, inds, z_new, cdf) if debug else z_out
+
+
+def searchsorted_right(cdf, u):
+    R, n = cdf.shape
+    inds = torch.empty(u.shape, device=u.device, dtype=torch.int64)
+    with torch.cuda.device(u.device):
+        _check(lib().snb_searchsorted_right(_ptr(cdf), _ptr(u), _ptr(inds, torch.int64), R, n, u.shape[1], _stream(u.device)),
+               "snb_searchsorted_right")
+    return inds
+
+
+def _fill(struct, names, tensors: Dict[str, Optional[torch.Tensor]]):
+    for n in names:
+        setattr(struct, n, _ptr(tensors.get(n)))
+    return struct
+
+
+def render_forward(desc: FieldDesc, pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]]):
+    dev = tensors["rays"].device if tensors.get("rays") is not None else tensors["xyz"].device
+    io = _fill(RenderIO(), _IO_FIELDS, tensors)
+    n = C.c_size_t(0)
+    with torch.cuda.device(dev):
+        _check(lib().snb_render_workspace(C.byref(desc), C.byref(pd), 0, C.byref(n)), "snb_render_workspace")
+        ws = _workspace(dev, n.value)
+        _check(lib().snb_render_forward(C.byref(desc), C.byref(pd), C.byref(io), C.c_void_p(ws.data_ptr()), ws.numel(), _stream(dev)),
+               "snb_render_forward")
+
+
+def render_backward(desc: FieldDesc, pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]], grads: Dict[str, Optional[torch.Tensor]]):
+    dev = tensors["params"].device
+    io = _fill(RenderIO(), _IO_FIELDS, tensors)
+    g = _fill(RenderGrads(), _GRAD_FIELDS, grads)
+    n = C.c_size_t(0)
+    with torch.cuda.device(dev):
+        _check(lib().snb_render_workspace(C.byref(desc), C.byref(pd), 1, C.byref(n)), "snb_render_workspace")
+        ws = _workspace(dev, n.value)
+        _check(lib().snb_render_backward(C.byref(desc), C.byref(pd), C.byref(io), C.byref(g), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                         _stream(dev)), "snb_render_backward")
+
+
+def field_forward(desc: FieldDesc, params, xyz, aux_dir, t_emb, sigma_only: bool, n_channels: int, precision=FP32_SIMT):
+    B = xyz.shape[0]
+    out = torch.empty(B, 1 if sigma_only else n_channels, device=xyz.device, dtype=torch.float32)
+    n = C.c_size_t(0)
+    with torch.cuda.device(xyz.device):
+        _check(lib().snb_field_workspace(C.byref(desc), B, C.byref(n)), "snb_field_workspace")
+        ws = _workspace(xyz.device, n.value)
+        _check(lib().snb_field_forward(C.byref(desc), _ptr(params), _ptr(xyz), _ptr(aux_dir), _ptr(t_emb), _ptr(out), B,
+                                       int(sigma_only), precision, C.c_void_p(ws.data_ptr()), ws.numel(), _stream(xyz.device)),
+               "snb_field_forward")
+    return out

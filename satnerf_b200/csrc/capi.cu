@@ -1,0 +1,169 @@
+// extern "C" SNB_API entry points of the render pass (declared in include/satnerf_b200.h) and the
+// orchestration of the fp32 SIMT path: rays are processed in chunks of whole rays so that the
+// per-layer activations of a chunk fit the caller's workspace (the reference bounds memory the same
+// way with args.chunk, models/satnerf.py:30-40).
+#include "common.cuh"
+#include "composite.cuh"
+#include "simt_field.cuh"
+#include "tc_field.cuh"
+
+using namespace snb;
+
+namespace {
+
+constexpr int kChunkPoints = 8192;
+
+struct PassPlan {
+    int rays_per_chunk;
+    float *raw, *d_head, *xyz, *raw_chunk;
+    FieldChunk chunk;
+};
+
+int check_pass(const FieldLayout& L, const snb_pass_desc* p) {
+    if (!p) SNB_FAIL(-1, "null pass descriptor");
+    if (p->n_rays < 0 || p->n_samples < 1) SNB_FAIL(-1, "bad pass shape R=%d S=%d", p->n_rays, p->n_samples);
+    int need = L.variant == SNB_NERF ? 8 : 11;
+    if (p->ray_cols != 0 && p->ray_cols < need) SNB_FAIL(-1, "rays need %d columns for this variant, got %d", need, p->ray_cols);
+    if (p->march_along_sun && L.variant == SNB_NERF) SNB_FAIL(-1, "solar-correction pass is undefined for nerf");
+    if (p->precision != SNB_FP32_SIMT && p->precision != SNB_FP16_TC) SNB_FAIL(-1, "unknown precision %d", p->precision);
+    if ((int64_t)p->n_rays * p->n_samples > (int64_t)1 << 30) SNB_FAIL(-1, "too many points in one pass");
+    return 0;
+}
+
+void plan_pass(Arena& ar, const FieldLayout& L, const snb_pass_desc* p, bool backward, PassPlan* pl) {
+    const int S = p->n_samples, C = L.n_channels;
+    int rc = kChunkPoints / S; if (rc < 1) rc = 1; if (rc > p->n_rays) rc = p->n_rays > 0 ? p->n_rays : 1;
+    pl->rays_per_chunk = rc;
+    const size_t P = (size_t)p->n_rays * S, Pc = (size_t)rc * S;
+    pl->raw = backward ? nullptr : ar.take<float>(P * C);
+    pl->d_head = backward ? ar.take<float>(P * C) : nullptr;
+    pl->raw_chunk = backward ? ar.take<float>(Pc * C) : nullptr;
+    pl->xyz = ar.take<float>(Pc * 3);
+    pl->chunk.plan(ar, L, (int)Pc, rc, backward);
+}
+
+FieldInputs chunk_inputs(const FieldLayout& L, const snb_pass_desc* p, const snb_render_io* io, const float* xyz, int r0, int rc) {
+    const int S = p->n_samples;
+    FieldInputs in;
+    in.n_points = rc * S;
+    in.xyz = io->xyz ? Src{io->xyz + (size_t)r0 * S * 3, 3, 3, 1} : Src{xyz, 3, 3, 1};
+    // sat-nerf / s-nerf: sun direction rays[:, 8:11] (rendering.py:87/:99); nerf: view direction rays[:, 3:6] (:112)
+    int aux_col = L.variant == SNB_NERF ? 3 : 8;
+    if (io->aux_dir) in.aux = Src{io->aux_dir + (size_t)r0 * 3, 3, 3, S};
+    else in.aux = Src{io->rays + (size_t)r0 * p->ray_cols + aux_col, p->ray_cols, 3, S};
+    in.temb = L.t_dims ? Src{io->t_emb + (size_t)r0 * L.t_dims, L.t_dims, L.t_dims, S} : Src{nullptr, 0, 0, 1};
+    return in;
+}
+
+}  // namespace
+
+extern "C" SNB_API int snb_render_workspace(const snb_field_desc* f, const snb_pass_desc* p, int backward, size_t* bytes) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L)); SNB_TRY(check_pass(L, p));
+    if (!bytes) SNB_FAIL(-1, "null output pointer");
+    size_t simt = 0, tc = 0;
+    { Arena ar(nullptr, 0); PassPlan pl; plan_pass(ar, L, p, backward != 0, &pl); simt = ar.off; }
+    if (p->precision == SNB_FP16_TC) SNB_TRY(tc_workspace(L, p, backward != 0, &tc));
+    *bytes = (simt > tc ? simt : tc) + 256;
+    return 0;
+}
+
+extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L)); SNB_TRY(check_pass(L, p));
+    if (!io || !io->params || !io->z_vals) SNB_FAIL(-1, "snb_render_forward: params and z_vals are required");
+    if (!io->rays && !(io->xyz && io->aux_dir)) SNB_FAIL(-1, "snb_render_forward: rays (or xyz + aux_dir) are required");
+    if (L.t_dims && !io->t_emb) SNB_FAIL(-1, "snb_render_forward: sat-nerf needs t_emb (the reference raises on ts=None, satnerf.py:204)");
+    if (p->n_rays == 0) return 0;
+    if (!workspace) SNB_FAIL(-1, "snb_render_forward: null workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->precision == SNB_FP16_TC) return tc_render_forward(L, p, io, workspace, workspace_bytes, st);
+
+    Arena ar(workspace, workspace_bytes); PassPlan pl; plan_pass(ar, L, p, false, &pl);
+    if (ar.overflow) SNB_FAIL(-4, "snb_render_forward: workspace too small (%zu bytes given)", workspace_bytes);
+    const int S = p->n_samples, C = L.n_channels;
+    const int dir_col = p->march_along_sun ? 8 : 3;
+    for (int r0 = 0; r0 < p->n_rays; r0 += pl.rays_per_chunk) {
+        int rc = p->n_rays - r0 < pl.rays_per_chunk ? p->n_rays - r0 : pl.rays_per_chunk;
+        if (!io->xyz) SNB_TRY(launch_points(io->rays, p->ray_cols, dir_col, io->z_vals, pl.xyz, r0, rc, S, st));
+        FieldInputs in = chunk_inputs(L, p, io, pl.xyz, r0, rc);
+        SNB_TRY(field_forward_chunk(L, io->params, pl.chunk, in, pl.raw + (size_t)r0 * S * C, false, st));
+    }
+    CompositeArgs a{};
+    a.R = p->n_rays; a.S = S; a.C = C; a.raw = pl.raw; a.z = io->z_vals; a.noise = io->noise; a.noise_std = p->noise_std;
+    a.rgb = io->rgb; a.depth = io->depth; a.weights = io->weights; a.transparency = io->transparency;
+    a.albedo = io->albedo; a.sun = io->sun; a.sky = io->sky; a.beta = io->beta; a.sigma = io->sigma; a.nerf_rgb = io->nerf_rgb;
+    return launch_composite_fwd(a, st);
+}
+
+extern "C" SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
+                                   const snb_render_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L)); SNB_TRY(check_pass(L, p));
+    if (!io || !g || !io->params || !io->z_vals || !g->g_params) SNB_FAIL(-1, "snb_render_backward: missing required pointer");
+    if (!io->rays && !(io->xyz && io->aux_dir)) SNB_FAIL(-1, "snb_render_backward: rays (or xyz + aux_dir) are required");
+    if (!io->weights || !io->transparency || !io->sigma) SNB_FAIL(-1, "snb_render_backward: forward stash (weights, transparency, sigma) missing");
+    if (L.variant != SNB_NERF && (!io->albedo || !io->sun || !io->sky)) SNB_FAIL(-1, "snb_render_backward: saved albedo/sun/sky missing");
+    if (L.variant == SNB_SATNERF && (!io->beta || !io->t_emb)) SNB_FAIL(-1, "snb_render_backward: saved beta / t_emb missing");
+    if (L.variant == SNB_NERF && !io->nerf_rgb) SNB_FAIL(-1, "snb_render_backward: saved per-sample rgb missing");
+    if (p->n_rays == 0) return 0;
+    if (!workspace) SNB_FAIL(-1, "snb_render_backward: null workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->precision == SNB_FP16_TC) {
+        int r = tc_render_backward(L, p, io, g, workspace, workspace_bytes, st);
+        if (r != 1) return r;      // 1 = "not available for this shape": use the fp32 chain below
+    }
+    Arena ar(workspace, workspace_bytes); PassPlan pl; plan_pass(ar, L, p, true, &pl);
+    if (ar.overflow) SNB_FAIL(-4, "snb_render_backward: workspace too small (%zu bytes given)", workspace_bytes);
+    const int S = p->n_samples, C = L.n_channels;
+    CompositeBwdArgs b{};
+    b.R = p->n_rays; b.S = S; b.C = C; b.z = io->z_vals; b.noise = io->noise; b.noise_std = p->noise_std;
+    b.weights = io->weights; b.transparency = io->transparency; b.sigma = io->sigma; b.albedo = io->albedo; b.sun = io->sun;
+    b.sky = io->sky; b.beta = io->beta; b.nerf_rgb = io->nerf_rgb;
+    b.g_rgb = g->g_rgb; b.g_depth = g->g_depth; b.g_weights = g->g_weights; b.g_transparency = g->g_transparency;
+    b.g_albedo = g->g_albedo; b.g_sun = g->g_sun; b.g_sky = g->g_sky; b.g_beta = g->g_beta; b.d_head = pl.d_head;
+    SNB_TRY(launch_composite_bwd(b, st));
+    const int dir_col = p->march_along_sun ? 8 : 3;
+    for (int r0 = 0; r0 < p->n_rays; r0 += pl.rays_per_chunk) {
+        int rc = p->n_rays - r0 < pl.rays_per_chunk ? p->n_rays - r0 : pl.rays_per_chunk;
+        if (!io->xyz) SNB_TRY(launch_points(io->rays, p->ray_cols, dir_col, io->z_vals, pl.xyz, r0, rc, S, st));
+        FieldInputs in = chunk_inputs(L, p, io, pl.xyz, r0, rc);
+        SNB_TRY(field_forward_chunk(L, io->params, pl.chunk, in, pl.raw_chunk, false, st));
+        float* gt = (g->g_t_emb && L.t_dims) ? g->g_t_emb + (size_t)r0 * L.t_dims : nullptr;
+        SNB_TRY(field_backward_chunk(L, io->params, g->g_params, pl.chunk, in, pl.d_head + (size_t)r0 * S * C, gt, S, st));
+    }
+    return 0;
+}
+
+extern "C" SNB_API int snb_field_workspace(const snb_field_desc* f, int n_points, size_t* bytes) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L));
+    if (!bytes || n_points < 0) SNB_FAIL(-1, "snb_field_workspace: bad arguments");
+    int pc = n_points < kChunkPoints ? (n_points > 0 ? n_points : 1) : kChunkPoints;
+    Arena ar(nullptr, 0); FieldChunk c; c.plan(ar, L, pc, pc, false);
+    *bytes = ar.off + 256;
+    return 0;
+}
+
+extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* params, const float* xyz, const float* aux_dir,
+                                 const float* t_emb, float* out, int n_points, int sigma_only, int precision,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L));
+    if (!params || !xyz || !out || n_points < 0) SNB_FAIL(-1, "snb_field_forward: bad arguments");
+    if (!sigma_only && L.variant != SNB_NERF && !aux_dir) SNB_FAIL(-1, "snb_field_forward: input_sun_dir is required");
+    if (!sigma_only && L.variant == SNB_NERF && !aux_dir) SNB_FAIL(-1, "snb_field_forward: input_dir is required");
+    if (!sigma_only && L.t_dims && !t_emb) SNB_FAIL(-1, "snb_field_forward: input_t is required (satnerf.py:204)");
+    if (precision != SNB_FP32_SIMT) SNB_FAIL(-1, "snb_field_forward: only SNB_FP32_SIMT is provided for the per-point API");
+    if (n_points == 0) return 0;
+    if (!workspace) SNB_FAIL(-1, "snb_field_forward: null workspace");
+    int pc = n_points < kChunkPoints ? n_points : kChunkPoints;
+    Arena ar(workspace, workspace_bytes); FieldChunk c; c.plan(ar, L, pc, pc, false);
+    if (ar.overflow) SNB_FAIL(-4, "snb_field_forward: workspace too small");
+    const int C = sigma_only ? 1 : L.n_channels;
+    for (int p0 = 0; p0 < n_points; p0 += pc) {
+        int n = n_points - p0 < pc ? n_points - p0 : pc;
+        FieldInputs in; in.n_points = n;
+        in.xyz = Src{xyz + (size_t)p0 * 3, 3, 3, 1};
+        in.aux = aux_dir ? Src{aux_dir + (size_t)p0 * 3, 3, 3, 1} : Src{nullptr, 0, 0, 1};
+        in.temb = (L.t_dims && t_emb) ? Src{t_emb + (size_t)p0 * L.t_dims, L.t_dims, L.t_dims, 1} : Src{nullptr, 0, 0, 1};
+        SNB_TRY(field_forward_chunk(L, params, c, in, out + (size_t)p0 * C, sigma_only != 0, (cudaStream_t)stream));
+    }
+    return 0;
+}

@@ -1,0 +1,133 @@
+// Alpha compositing of one inference() pass and its gradient.
+// Forward restates models/satnerf.py:43-78 (snerf.py:43-74, nerf.py:108-132); backward is the closed
+// form autograd derives for those lines.  One thread per ray walks the samples in
+// order, so the transmittance product has the same association order as torch.cumprod.
+#include "composite.cuh"
+
+namespace snb {
+
+// raw: (R*S, C) field outputs [rgb3, sigma, sun, sky3, beta]; writes every non-null result array.
+__global__ void composite_fwd_kernel(CompositeArgs a) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const int S = a.S, C = a.C;
+    const float* z = a.z + (size_t)r * S;
+    const float* raw = a.raw + (size_t)r * S * C;
+    float T = 1.0f, depth = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int i = 0; i < S; ++i) {
+        const float* o = raw + (size_t)i * C;
+        float sg = o[3];
+        float nz = a.noise ? a.noise[(size_t)r * S + i] * a.noise_std : 0.f;                 // :57-58
+        float delta = i < S - 1 ? __fsub_rn(z[i + 1], z[i]) : 1e10f;                          // :52-54
+        float alpha = 1.0f - expf(-delta * fmaxf(sg + nz, 0.f));                              // :59
+        float w = alpha * T;                                                                  // :63
+        size_t p = (size_t)r * S + i;
+        if (a.weights) a.weights[p] = w;
+        if (a.transparency) a.transparency[p] = T;
+        if (a.sigma) a.sigma[p] = sg;
+        depth += w * z[i];                                                                    // :67
+        float r0 = o[0], r1 = o[1], r2 = o[2];
+        if (C >= 8) {
+            float s = o[4], k0 = o[5], k1 = o[6], k2 = o[7];
+            c0 += w * r0 * (s + (1.f - s) * k0);                                              // :68-69
+            c1 += w * r1 * (s + (1.f - s) * k1);
+            c2 += w * r2 * (s + (1.f - s) * k2);
+            if (a.albedo) { a.albedo[p * 3] = r0; a.albedo[p * 3 + 1] = r1; a.albedo[p * 3 + 2] = r2; }
+            if (a.sun) a.sun[p] = s;
+            if (a.sky) { a.sky[p * 3] = k0; a.sky[p * 3 + 1] = k1; a.sky[p * 3 + 2] = k2; }
+            if (C == 9 && a.beta) a.beta[p] = o[8];
+        } else {
+            c0 += w * r0; c1 += w * r1; c2 += w * r2;                                         // nerf.py:128
+            if (a.nerf_rgb) { a.nerf_rgb[p * 3] = r0; a.nerf_rgb[p * 3 + 1] = r1; a.nerf_rgb[p * 3 + 2] = r2; }
+        }
+        T = T * ((1.0f - alpha) + 1e-10f);                                                    // :60-62
+    }
+    if (a.depth) a.depth[r] = depth;
+    if (a.rgb) {
+        if (C >= 8) { c0 = fminf(fmaxf(c0, 0.f), 1.f); c1 = fminf(fmaxf(c1, 0.f), 1.f); c2 = fminf(fmaxf(c2, 0.f), 1.f); }   // :70
+        a.rgb[r * 3] = c0; a.rgb[r * 3 + 1] = c1; a.rgb[r * 3 + 2] = c2;
+    }
+}
+
+// Writes d_head (R*S, C): gradient w.r.t. the PRE-activation outputs of the field heads.
+__global__ void composite_bwd_kernel(CompositeBwdArgs a) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const int S = a.S, C = a.C;
+    const size_t base = (size_t)r * S;
+    const float* z = a.z + base;
+    const bool sat = C >= 8;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (a.g_rgb) { g0 = a.g_rgb[r * 3]; g1 = a.g_rgb[r * 3 + 1]; g2 = a.g_rgb[r * 3 + 2]; }
+    const float gd = a.g_depth ? a.g_depth[r] : 0.f;
+    const float* col = sat ? a.albedo : a.nerf_rgb;
+    if (sat && a.g_rgb) {
+        // clamp mask needs the un-clamped colour: re-accumulate it in the forward order
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        for (int i = 0; i < S; ++i) {
+            size_t p = base + i; float w = a.weights[p], s = a.sun[p];
+            c0 += w * col[p * 3] * (s + (1.f - s) * a.sky[p * 3]);
+            c1 += w * col[p * 3 + 1] * (s + (1.f - s) * a.sky[p * 3 + 1]);
+            c2 += w * col[p * 3 + 2] * (s + (1.f - s) * a.sky[p * 3 + 2]);
+        }
+        if (!(c0 >= 0.f && c0 <= 1.f)) g0 = 0.f;
+        if (!(c1 >= 0.f && c1 <= 1.f)) g1 = 0.f;
+        if (!(c2 >= 0.f && c2 <= 1.f)) g2 = 0.f;
+    }
+    float suffix = 0.f;   // sum_{k>i} (G_k alpha_k + gT_k) T_k
+    for (int i = S - 1; i >= 0; --i) {
+        size_t p = base + i;
+        float w = a.weights[p], T = a.transparency[p], sg = a.sigma[p];
+        float nz = a.noise ? a.noise[p] * a.noise_std : 0.f;
+        float delta = i < S - 1 ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+        float act = sg + nz;
+        float e = expf(-delta * fmaxf(act, 0.f));
+        float alpha = 1.0f - e;
+        float q = (1.0f - alpha) + 1e-10f;
+        float c_r = col[p * 3], c_g = col[p * 3 + 1], c_b = col[p * 3 + 2];
+        float s = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, i0 = 1.f, i1 = 1.f, i2 = 1.f;
+        if (sat) {
+            s = a.sun[p]; k0 = a.sky[p * 3]; k1 = a.sky[p * 3 + 1]; k2 = a.sky[p * 3 + 2];
+            i0 = s + (1.f - s) * k0; i1 = s + (1.f - s) * k1; i2 = s + (1.f - s) * k2;
+        }
+        float G = (a.g_weights ? a.g_weights[p] : 0.f) + gd * z[i] + g0 * c_r * i0 + g1 * c_g * i1 + g2 * c_b * i2;
+        float gT = a.g_transparency ? a.g_transparency[p] : 0.f;
+        float d_alpha = G * T - suffix / q;
+        suffix += (G * alpha + gT) * T;
+        float d_sigma = act > 0.f ? d_alpha * (delta * e) : 0.f;
+        float* out = a.d_head + p * C;
+        // colour head: alb = sigmoid(y)*1.002 - 0.001                                    (satnerf.py:193-195)
+        float dc0 = g0 * w * i0, dc1 = g1 * w * i1, dc2 = g2 * w * i2;
+        if (sat && a.g_albedo) { dc0 += a.g_albedo[p * 3]; dc1 += a.g_albedo[p * 3 + 1]; dc2 += a.g_albedo[p * 3 + 2]; }
+        float s0 = (c_r + 0.001f) / 1.002f, s1 = (c_g + 0.001f) / 1.002f, s2 = (c_b + 0.001f) / 1.002f;
+        out[0] = dc0 * 1.002f * s0 * (1.f - s0);
+        out[1] = dc1 * 1.002f * s1 * (1.f - s1);
+        out[2] = dc2 * 1.002f * s2 * (1.f - s2);
+        out[3] = d_sigma * (-expm1f(-sg));              // softplus' = sigmoid(y) = 1 - exp(-softplus(y))
+        if (sat) {
+            float ds = g0 * w * c_r * (1.f - k0) + g1 * w * c_g * (1.f - k1) + g2 * w * c_b * (1.f - k2);
+            if (a.g_sun) ds += a.g_sun[p];
+            out[4] = ds * s * (1.f - s);
+            float dk0 = g0 * w * c_r * (1.f - s), dk1 = g1 * w * c_g * (1.f - s), dk2 = g2 * w * c_b * (1.f - s);
+            if (a.g_sky) { dk0 += a.g_sky[p * 3]; dk1 += a.g_sky[p * 3 + 1]; dk2 += a.g_sky[p * 3 + 2]; }
+            out[5] = dk0 * k0 * (1.f - k0); out[6] = dk1 * k1 * (1.f - k1); out[7] = dk2 * k2 * (1.f - k2);
+            if (C == 9) { float b = a.beta[p]; out[8] = (a.g_beta ? a.g_beta[p] : 0.f) * (-expm1f(-b)); }
+        }
+    }
+}
+
+int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st) {
+    if (a.R == 0) return 0;
+    composite_fwd_kernel<<<ceil_div(a.R, 128), 128, 0, st>>>(a);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_composite_bwd(const CompositeBwdArgs& a, cudaStream_t st) {
+    if (a.R == 0) return 0;
+    composite_bwd_kernel<<<ceil_div(a.R, 128), 128, 0, st>>>(a);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace snb

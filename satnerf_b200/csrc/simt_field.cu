@@ -1,0 +1,444 @@
+// fp32 CUDA-core ("SIMT") evaluation of the three fields and of their parameter gradients.
+// This is the exactness path (SNB_FP32_SIMT): every contraction is an fp32 FFMA chain, every
+// activation the full-precision libdevice function, so results track the reference's fp32 torch ops
+// to rounding level.  It also serves as the on-device cross-check of the tcgen05 path at full size.
+//
+// Restates SatNeRF.forward (models/satnerf.py:156-208), ShadowNeRF.forward (models/snerf.py:148-196),
+// NeRF.forward + Mapping (models/nerf.py:184-227, :36-69); the backward is what autograd derives.
+#include "simt_field.cuh"
+
+namespace snb {
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ------------------------------------------------------------------------------------------------
+// xyz = o + dir*z, products and sums rounded separately like the eager torch ops (rendering.py:81/:104)
+__global__ void points_kernel(const float* __restrict__ rays, int ray_cols, int dir_col, const float* __restrict__ z,
+                              float* __restrict__ xyz, int r0, int n_rays, int S) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rays * S) return;
+    int r = r0 + idx / S;
+    const float* ray = rays + (size_t)r * ray_cols;
+    float zz = z[(size_t)r0 * S + idx];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xyz[(size_t)idx * 3 + c] = __fadd_rn(ray[c], __fmul_rn(ray[dir_col + c], zz));
+}
+
+// Mapping.forward (models/nerf.py:53-69): out = [sin(2^k x), cos(2^k x)]_k, x itself excluded.
+__global__ void pe_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int n_rows, int n_freqs) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int per = 6 * n_freqs;
+    if (idx >= n_rows * per) return;
+    int row = idx / per, j = idx - row * per;
+    int k = j / 6, rem = j - k * 6, c = rem % 3;
+    float v = __fmul_rn((float)(1 << k), x[(size_t)row * ldx + c]);
+    out[idx] = rem < 3 ? sinf(v) : cosf(v);
+}
+
+__global__ void ray_sum_kernel(const float* __restrict__ per_point, float* __restrict__ per_ray, int n_rays, int S, int D) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rays * D) return;
+    int r = idx / D, d = idx - r * D;
+    float acc = 0.f;
+    for (int i = 0; i < S; ++i) acc += per_point[((size_t)r * S + i) * D + d];
+    per_ray[idx] = acc;
+}
+
+__global__ void reduce_partials_kernel(float* __restrict__ dst, const float* __restrict__ part, int Z, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int z = 0; z < Z; ++z) acc += part[(int64_t)z * n + i];
+    dst[i] += acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// activations
+// ------------------------------------------------------------------------------------------------
+template <int ACT> __device__ __forceinline__ float act_fwd(float x) {
+    if (ACT == ACT_SIN) return sinf(x);
+    if (ACT == ACT_SIN30) return sinf(__fmul_rn(30.0f, x));                 // Siren(w0=30), nerf.py:33
+    if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
+    if (ACT == ACT_SOFTPLUS) return x > 20.f ? x : log1pf(expf(x));         // torch Softplus(beta=1, threshold=20)
+    if (ACT == ACT_SIGMOID_PAD) return __fsub_rn(__fmul_rn(1.0f / (1.0f + expf(-x)), 1.002f), 0.001f);   // satnerf.py:195
+    return x;
+}
+template <int ACT> __device__ __forceinline__ float act_bwd(float pre) {   // d act / d pre
+    if (ACT == ACT_SIN) return cosf(pre);
+    if (ACT == ACT_SIN30) return 30.0f * cosf(__fmul_rn(30.0f, pre));
+    if (ACT == ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
+
+__device__ __forceinline__ float src_at(const Src& a0, const Src& a1, int m, int k) {
+    if (k < a0.k) return a0.p[(size_t)(m / a0.div) * a0.ld + k];
+    return a1.p[(size_t)(m / a1.div) * a1.ld + (k - a0.k)];
+}
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+// ------------------------------------------------------------------------------------------------
+// Y = act(cat(A0,A1) W^T + b)        A: (M,K) virtual, W: (N,K) row-major with leading dim ldw
+// ------------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(NT) linear_fwd_kernel(LinFwd p) {
+    __shared__ float As[BK][BM + 4], Ws[BK][BN + 4];
+    const int K = p.a0.k + p.a1.k;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int idx = t + e * NT, row = idx / BK, kk = idx % BK;
+            int m = m0 + row, k = k0 + kk;
+            As[kk][row] = (m < p.M && k < K) ? src_at(p.a0, p.a1, m, k) : 0.f;
+            int n = n0 + row;
+            Ws[kk][row] = (n < p.N && k < K) ? p.W[(size_t)n * p.ldw + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; w[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= p.N) continue;
+            float y = acc[i][j] + p.b[n];
+            if (p.pre) p.pre[(size_t)m * p.N + n] = y;
+            p.out[(size_t)m * p.ldo + n] = act_fwd<ACT>(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dX[m,k] = (sum_n dY[m,n] W[n,k_off+k] (+ dX_old)) * act'(pre[m,k])
+// ------------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(NT) linear_bwd_in_kernel(LinBwdIn p) {
+    __shared__ float Ys[BK][BM + 4], Ws[BK][BN + 4];
+    const int m0 = blockIdx.x * BM, c0 = blockIdx.y * BN;
+    const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+    float acc[4][4] = {};
+    for (int n0 = 0; n0 < p.N; n0 += BK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int idx = t + e * NT;
+            { int row = idx / BK, nn = idx % BK; int m = m0 + row, n = n0 + nn;
+              Ys[nn][row] = (m < p.M && n < p.N) ? p.dY[(size_t)m * p.ldy + n] : 0.f; }
+            { int nn = idx / BN, col = idx % BN; int n = n0 + nn, k = c0 + col;
+              Ws[nn][col] = (n < p.N && k < p.K) ? p.W[(size_t)n * p.ldw + p.k_off + k] : 0.f; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int nn = 0; nn < BK; ++nn) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = Ys[nn][ty * 4 + i]; w[i] = Ws[nn][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = c0 + tx * 4 + j;
+            if (k >= p.K) continue;
+            float v = acc[i][j];
+            size_t o = (size_t)m * p.ldx + k;
+            if (p.accumulate) v += p.dX[o];
+            if (ACT != ACT_NONE) v *= act_bwd<ACT>(p.pre[(size_t)m * p.K + k]);
+            p.dX[o] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// partial[z][n][k] = sum_{m in slice z} dY[m,n] X[m,k];  partial bias appended after the N*K block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) linear_bwd_w_kernel(LinBwdW p) {
+    __shared__ float Ys[BK][BM + 4], Xs[BK][BN + 4];
+    const int K = p.a0.k + p.a1.k;
+    const int k0 = blockIdx.x * BN, n0 = blockIdx.y * BM, z = blockIdx.z;
+    const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+    const int m_beg = z * p.m_per_z, m_end = min(p.M, m_beg + p.m_per_z);
+    float acc[4][4] = {}; float bacc[4] = {};
+    for (int mb = m_beg; mb < m_end; mb += BK) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int idx = t + e * NT, mm = idx / BM, col = idx % BM;
+            int m = mb + mm;
+            int n = n0 + col, k = k0 + col;
+            Ys[mm][col] = (m < m_end && n < p.N) ? p.dY[(size_t)m * p.ldy + n] : 0.f;
+            Xs[mm][col] = (m < m_end && k < K) ? src_at(p.a0, p.a1, m, k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < BK; ++mm) {
+            float a[4], x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = Ys[mm][ty * 4 + i]; x[i] = Xs[mm][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (tx == 0) bacc[i] += a[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], x[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    float* part = p.partial + (size_t)z * ((size_t)p.N * K + p.N);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int n = n0 + ty * 4 + i;
+        if (n >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { int k = k0 + tx * 4 + j; if (k < K) part[(size_t)n * K + k] = acc[i][j]; }
+        if (tx == 0 && blockIdx.x == 0) part[(size_t)p.N * K + n] = bacc[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static int run_fwd(int act, const LinFwd& p, cudaStream_t st) {
+    if (p.M == 0) return 0;
+    dim3 g(ceil_div(p.M, BM), ceil_div(p.N, BN));
+    switch (act) {
+        case ACT_NONE: linear_fwd_kernel<ACT_NONE><<<g, NT, 0, st>>>(p); break;
+        case ACT_SIN: linear_fwd_kernel<ACT_SIN><<<g, NT, 0, st>>>(p); break;
+        case ACT_SIN30: linear_fwd_kernel<ACT_SIN30><<<g, NT, 0, st>>>(p); break;
+        case ACT_RELU: linear_fwd_kernel<ACT_RELU><<<g, NT, 0, st>>>(p); break;
+        case ACT_SIGMOID: linear_fwd_kernel<ACT_SIGMOID><<<g, NT, 0, st>>>(p); break;
+        case ACT_SOFTPLUS: linear_fwd_kernel<ACT_SOFTPLUS><<<g, NT, 0, st>>>(p); break;
+        case ACT_SIGMOID_PAD: linear_fwd_kernel<ACT_SIGMOID_PAD><<<g, NT, 0, st>>>(p); break;
+        default: SNB_FAIL(-3, "bad activation %d", act);
+    }
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+static int run_bwd_in(int act, const LinBwdIn& p, cudaStream_t st) {
+    if (p.M == 0) return 0;
+    dim3 g(ceil_div(p.M, BM), ceil_div(p.K, BN));
+    switch (act) {
+        case ACT_NONE: linear_bwd_in_kernel<ACT_NONE><<<g, NT, 0, st>>>(p); break;
+        case ACT_SIN: linear_bwd_in_kernel<ACT_SIN><<<g, NT, 0, st>>>(p); break;
+        case ACT_SIN30: linear_bwd_in_kernel<ACT_SIN30><<<g, NT, 0, st>>>(p); break;
+        case ACT_RELU: linear_bwd_in_kernel<ACT_RELU><<<g, NT, 0, st>>>(p); break;
+        default: SNB_FAIL(-3, "bad backward activation %d", act);
+    }
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+constexpr int kMaxZ = 16;
+static int run_bwd_w(LinBwdW p, float* g_params, const Lin& l, float* partial, cudaStream_t st) {
+    if (p.M == 0) return 0;
+    const int K = p.a0.k + p.a1.k;
+    int Z = ceil_div(p.M, 2048); if (Z > kMaxZ) Z = kMaxZ; if (Z < 1) Z = 1;
+    p.m_per_z = ceil_div(ceil_div(p.M, Z), BK) * BK;
+    Z = ceil_div(p.M, p.m_per_z);
+    p.partial = partial; p.N = l.n_out;
+    if (K != l.n_in) SNB_FAIL(-3, "internal: weight-gradient K mismatch (%d vs %d)", K, l.n_in);
+    dim3 g(ceil_div(K, BN), ceil_div(p.N, BM), Z);
+    linear_bwd_w_kernel<<<g, NT, 0, st>>>(p);
+    SNB_CHECK_LAUNCH();
+    int64_t n = (int64_t)l.n_out * l.n_in + l.n_out;      // weight block and bias are adjacent in the flat layout
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g_params + l.w, partial, Z, n);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+static inline Src S_(const float* p, int ld, int k, int div = 1) { Src s; s.p = p; s.ld = ld; s.k = k; s.div = div; return s; }
+static inline Src none() { return S_(nullptr, 0, 0, 1); }
+
+// ------------------------------------------------------------------------------------------------
+// chunk buffers
+// ------------------------------------------------------------------------------------------------
+size_t FieldChunk::plan(Arena& ar, const FieldLayout& L, int Pc, int Rc, bool keep) {
+    const int h = L.width, h2 = h / 2, nl = L.n_layers;
+    size_t before = ar.off;
+    enc = L.in_xyz != 3 ? ar.take<float>((size_t)Pc * L.in_xyz) : nullptr;
+    enc_dir = L.in_dir ? ar.take<float>((size_t)Rc * L.in_dir) : nullptr;
+    float* ping[2] = {nullptr, nullptr};
+    if (!keep) { ping[0] = ar.take<float>((size_t)Pc * h); ping[1] = ar.take<float>((size_t)Pc * h); }
+    for (int i = 0; i < nl; ++i) {
+        pre[i] = keep ? ar.take<float>((size_t)Pc * h) : nullptr;
+        act[i] = keep ? ar.take<float>((size_t)Pc * h) : ping[i & 1];
+    }
+    feat = keep ? ar.take<float>((size_t)Pc * h) : ping[nl & 1];
+    auto head = [&](float*& pr, float*& ac) { pr = keep ? ar.take<float>((size_t)Pc * h2) : nullptr; ac = ar.take<float>((size_t)Pc * h2); };
+    head(rgb1_pre, rgb1);
+    if (L.variant != SNB_NERF) {
+        if (keep) { for (int j = 0; j < 3; ++j) head(sun_pre[j], sun_act[j]); }
+        else { head(sun_pre[0], sun_act[0]); sun_act[1] = rgb1; sun_pre[1] = nullptr; sun_act[2] = sun_act[0]; sun_pre[2] = nullptr; }
+        head(sky1_pre, sky1);
+    }
+    if (L.variant == SNB_SATNERF) { if (keep) head(beta1_pre, beta1); else { beta1 = rgb1; beta1_pre = nullptr; } }
+    if (keep) {
+        d_feat = ar.take<float>((size_t)Pc * h); d_a = ar.take<float>((size_t)Pc * h); d_b = ar.take<float>((size_t)Pc * h);
+        d_t = L.t_dims ? ar.take<float>((size_t)Pc * L.t_dims) : nullptr;
+        int kmax = h + (L.in_xyz > L.in_dir ? L.in_xyz : L.in_dir) + 8 + L.t_dims;
+        partial = ar.take<float>((size_t)kMaxZ * ((size_t)h * kmax + h));
+    }
+    return ar.off - before;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward of one chunk of Pc points.  raw: (Pc, C) chunk slice.
+// ------------------------------------------------------------------------------------------------
+int field_forward_chunk(const FieldLayout& L, const float* P, const FieldChunk& c, const FieldInputs& in,
+                        float* raw, bool sigma_only, cudaStream_t st) {
+    const int h = L.width, h2 = h / 2, nl = L.n_layers, Pc = in.n_points, C = sigma_only ? 1 : L.n_channels;
+    const bool siren = L.variant != SNB_NERF;
+    Src x = in.xyz;
+    if (L.in_xyz != 3) {
+        pe_kernel<<<ceil_div(Pc * L.in_xyz, 256), 256, 0, st>>>(in.xyz.p, in.xyz.ld, c.enc, Pc, L.in_xyz / 6);
+        SNB_CHECK_LAUNCH();
+        x = S_(c.enc, L.in_xyz, L.in_xyz);
+    }
+    auto fwd = [&](const Lin& l, Src a0, Src a1, int act, float* pre, float* out, int ldo) {
+        LinFwd p; p.a0 = a0; p.a1 = a1; p.W = P + l.w; p.ldw = l.n_in; p.b = P + l.b; p.pre = pre; p.out = out; p.ldo = ldo; p.M = Pc; p.N = l.n_out;
+        if (a0.k + a1.k != l.n_in) { set_error("internal: layer K mismatch (%d+%d vs %d)", a0.k, a1.k, l.n_in); return -3; }
+        return run_fwd(act, p, st);
+    };
+    for (int i = 0; i < nl; ++i) {
+        Src a0 = i == 0 ? x : (i == L.skip ? x : S_(c.act[i - 1], h, h));
+        Src a1 = i == L.skip ? S_(c.act[i - 1], h, h) : none();
+        int act = siren ? (i == 0 ? ACT_SIN30 : ACT_SIN) : ACT_RELU;
+        SNB_TRY(fwd(L.trunk[i], a0, a1, act, c.pre[i], c.act[i], h));
+    }
+    Src top = S_(c.act[nl - 1], h, h);
+    SNB_TRY(fwd(L.sigma, top, none(), ACT_SOFTPLUS, nullptr, raw + (sigma_only ? 0 : 3), C));
+    if (sigma_only) return 0;
+    SNB_TRY(fwd(L.feats, top, none(), ACT_NONE, nullptr, c.feat, h));
+    Src f = S_(c.feat, h, h);
+    Src dir = none();
+    if (L.in_dir) {
+        if (L.in_dir != 3) {
+            int rows = ceil_div(Pc, in.aux.div);
+            pe_kernel<<<ceil_div(rows * L.in_dir, 256), 256, 0, st>>>(in.aux.p, in.aux.ld, c.enc_dir, rows, L.in_dir / 6);
+            SNB_CHECK_LAUNCH();
+            dir = S_(c.enc_dir, L.in_dir, L.in_dir, in.aux.div);
+        } else dir = in.aux;
+    }
+    SNB_TRY(fwd(L.rgb0, f, dir, siren ? ACT_SIN : ACT_RELU, c.rgb1_pre, c.rgb1, h2));
+    SNB_TRY(fwd(L.rgb2, S_(c.rgb1, h2, h2), none(), ACT_SIGMOID_PAD, nullptr, raw + 0, C));
+    if (L.variant != SNB_NERF) {
+        SNB_TRY(fwd(L.sun[0], f, in.aux, ACT_SIN, c.sun_pre[0], c.sun_act[0], h2));
+        SNB_TRY(fwd(L.sun[1], S_(c.sun_act[0], h2, h2), none(), ACT_SIN, c.sun_pre[1], c.sun_act[1], h2));
+        SNB_TRY(fwd(L.sun[2], S_(c.sun_act[1], h2, h2), none(), ACT_SIN, c.sun_pre[2], c.sun_act[2], h2));
+        SNB_TRY(fwd(L.sun[3], S_(c.sun_act[2], h2, h2), none(), ACT_SIGMOID, nullptr, raw + 4, C));
+        SNB_TRY(fwd(L.sky0, in.aux, none(), ACT_RELU, c.sky1_pre, c.sky1, h2));
+        SNB_TRY(fwd(L.sky2, S_(c.sky1, h2, h2), none(), ACT_SIGMOID, nullptr, raw + 5, C));
+    }
+    if (L.variant == SNB_SATNERF) {
+        SNB_TRY(fwd(L.beta0, f, in.temb, ACT_SIN, c.beta1_pre, c.beta1, h2));
+        SNB_TRY(fwd(L.beta2, S_(c.beta1, h2, h2), none(), ACT_SOFTPLUS, nullptr, raw + 8, C));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of one chunk; requires field_forward_chunk(keep buffers) on the same chunk just before.
+// d_head: (Pc, C) gradient w.r.t. pre-activation head outputs.  g_t_ray: (Rc, tau) or null.
+// ------------------------------------------------------------------------------------------------
+int field_backward_chunk(const FieldLayout& L, const float* P, float* G, const FieldChunk& c, const FieldInputs& in,
+                         const float* d_head, float* g_t_ray, int S, cudaStream_t st) {
+    const int h = L.width, h2 = h / 2, nl = L.n_layers, Pc = in.n_points, C = L.n_channels;
+    const bool siren = L.variant != SNB_NERF;
+    const int hact = siren ? ACT_SIN : ACT_RELU;
+    Src x = L.in_xyz != 3 ? S_(c.enc, L.in_xyz, L.in_xyz) : in.xyz;
+    Src f = S_(c.feat, h, h);
+    auto bw = [&](const Lin& l, const float* dY, int ldy, Src a0, Src a1) {
+        LinBwdW p; p.dY = dY; p.ldy = ldy; p.a0 = a0; p.a1 = a1; p.M = Pc;
+        return run_bwd_w(p, G, l, c.partial, st);
+    };
+    auto bi = [&](const Lin& l, const float* dY, int ldy, int k_off, int K, int act, const float* pre, float* dX, int ldx, int accumulate) {
+        LinBwdIn p; p.dY = dY; p.ldy = ldy; p.N = l.n_out; p.W = P + l.w; p.ldw = l.n_in; p.k_off = k_off; p.K = K;
+        p.pre = pre; p.dX = dX; p.ldx = ldx; p.accumulate = accumulate; p.M = Pc;
+        return run_bwd_in(act, p, st);
+    };
+    bool feat_started = false;
+    float* d1 = c.d_a; float* d2 = c.d_b;      // (Pc, <=h) scratch, used with leading dim h2 in the heads
+    if (L.variant == SNB_SATNERF) {
+        SNB_TRY(bw(L.beta2, d_head + 8, C, S_(c.beta1, h2, h2), none()));
+        SNB_TRY(bi(L.beta2, d_head + 8, C, 0, h2, ACT_SIN, c.beta1_pre, d1, h2, 0));
+        SNB_TRY(bw(L.beta0, d1, h2, f, in.temb));
+        SNB_TRY(bi(L.beta0, d1, h2, 0, h, ACT_NONE, nullptr, c.d_feat, h, 0)); feat_started = true;
+        if (g_t_ray) {
+            SNB_TRY(bi(L.beta0, d1, h2, h, L.t_dims, ACT_NONE, nullptr, c.d_t, L.t_dims, 0));
+            int rc = Pc / S;
+            ray_sum_kernel<<<ceil_div(rc * L.t_dims, 128), 128, 0, st>>>(c.d_t, g_t_ray, rc, S, L.t_dims);
+            SNB_CHECK_LAUNCH();
+        }
+    }
+    if (L.variant != SNB_NERF) {
+        SNB_TRY(bw(L.sun[3], d_head + 4, C, S_(c.sun_act[2], h2, h2), none()));
+        SNB_TRY(bi(L.sun[3], d_head + 4, C, 0, h2, ACT_SIN, c.sun_pre[2], d1, h2, 0));
+        SNB_TRY(bw(L.sun[2], d1, h2, S_(c.sun_act[1], h2, h2), none()));
+        SNB_TRY(bi(L.sun[2], d1, h2, 0, h2, ACT_SIN, c.sun_pre[1], d2, h2, 0));
+        SNB_TRY(bw(L.sun[1], d2, h2, S_(c.sun_act[0], h2, h2), none()));
+        SNB_TRY(bi(L.sun[1], d2, h2, 0, h2, ACT_SIN, c.sun_pre[0], d1, h2, 0));
+        SNB_TRY(bw(L.sun[0], d1, h2, f, in.aux));
+        SNB_TRY(bi(L.sun[0], d1, h2, 0, h, ACT_NONE, nullptr, c.d_feat, h, feat_started ? 1 : 0)); feat_started = true;
+        SNB_TRY(bw(L.sky2, d_head + 5, C, S_(c.sky1, h2, h2), none()));
+        SNB_TRY(bi(L.sky2, d_head + 5, C, 0, h2, ACT_RELU, c.sky1_pre, d1, h2, 0));
+        SNB_TRY(bw(L.sky0, d1, h2, in.aux, none()));
+    }
+    Src dir = none();
+    if (L.in_dir) dir = L.in_dir != 3 ? S_(c.enc_dir, L.in_dir, L.in_dir, in.aux.div) : in.aux;
+    SNB_TRY(bw(L.rgb2, d_head + 0, C, S_(c.rgb1, h2, h2), none()));
+    SNB_TRY(bi(L.rgb2, d_head + 0, C, 0, h2, hact, c.rgb1_pre, d1, h2, 0));
+    SNB_TRY(bw(L.rgb0, d1, h2, f, dir));
+    SNB_TRY(bi(L.rgb0, d1, h2, 0, h, ACT_NONE, nullptr, c.d_feat, h, feat_started ? 1 : 0));
+    // feats + sigma -> top of the trunk
+    Src top = S_(c.act[nl - 1], h, h);
+    SNB_TRY(bw(L.feats, c.d_feat, h, top, none()));
+    SNB_TRY(bw(L.sigma, d_head + 3, C, top, none()));
+    int top_act = siren ? (nl - 1 == 0 ? ACT_SIN30 : ACT_SIN) : ACT_RELU;
+    SNB_TRY(bi(L.sigma, d_head + 3, C, 0, h, ACT_NONE, nullptr, d1, h, 0));
+    SNB_TRY(bi(L.feats, c.d_feat, h, 0, h, top_act, c.pre[nl - 1], d1, h, 1));
+    // trunk
+    float* cur = d1; float* nxt = d2;
+    for (int i = nl - 1; i >= 1; --i) {
+        Src a0 = i == L.skip ? x : S_(c.act[i - 1], h, h);
+        Src a1 = i == L.skip ? S_(c.act[i - 1], h, h) : none();
+        SNB_TRY(bw(L.trunk[i], cur, h, a0, a1));
+        int act = siren ? (i - 1 == 0 ? ACT_SIN30 : ACT_SIN) : ACT_RELU;
+        SNB_TRY(bi(L.trunk[i], cur, h, i == L.skip ? L.in_xyz : 0, h, act, c.pre[i - 1], nxt, h, 0));
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    SNB_TRY(bw(L.trunk[0], cur, h, x, none()));
+    return 0;
+}
+
+int launch_points(const float* rays, int ray_cols, int dir_col, const float* z, float* xyz, int r0, int n_rays, int S, cudaStream_t st) {
+    if (n_rays == 0) return 0;
+    points_kernel<<<ceil_div(n_rays * S, 256), 256, 0, st>>>(rays, ray_cols, dir_col, z, xyz, r0, n_rays, S);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace snb

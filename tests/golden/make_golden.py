@@ -173,7 +173,7 @@ def sample_pdf_case():
     ww = w + 1e-5
     cdf = torch.cat([torch.zeros(r, 1), torch.cumsum(ww / ww.sum(-1, keepdim=True), -1)], -1)
     inds = torch.searchsorted(cdf, u.contiguous(), right=True)
-    np.savez_compressed(os.path.join(HERE, "sample_pdf.npz"), bins=bins.numpy(), weights=w.numpy(), u=u.numpy(),
+    np.savez_compressed(os.path.join(HERE, "sample_pdf.npz"), z=z.numpy(), bins=bins.numpy(), weights=w.numpy(), u=u.numpy(),
                         cdf=cdf.numpy(), inds=inds.numpy(), samples=out.numpy())
     print("sample_pdf: ok")
 

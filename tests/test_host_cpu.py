@@ -1,0 +1,103 @@
+"""CPU tests of the host logic: the C-ABI library loads and exports every declared symbol, the flat
+parameter layout matches the modules, parameter names/shapes/init match the reference, and the product
+refuses to run without CUDA (no fallback)."""
+import argparse
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(**kw):
+    base = dict(model="sat-nerf", fc_layers=8, fc_units=64, t_embbeding_tau=4, t_embbeding_vocab=30, n_samples=8,
+                n_importance=0, noise_std=0.0, sc_lambda=0.0, chunk=5120)
+    base.update(kw)
+    return argparse.Namespace(**base)
+
+
+def test_library_exports_every_declared_symbol():
+    from satnerf_b200 import capi
+    header = open(os.path.join(ROOT, "include", "satnerf_b200.h")).read()
+    declared = set(re.findall(r"SNB_API\s+[\w\s\*]+?\b(snb_\w+)\s*\(", header))
+    assert len(declared) >= 13
+    lib = capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(capi.exported_symbols())
+    assert lib.snb_abi_version() == 1
+
+
+@pytest.mark.parametrize("model,h", [("sat-nerf", 64), ("sat-nerf", 512), ("s-nerf", 256), ("nerf", 256)])
+def test_flat_layout_matches_module(model, h):
+    import satnerf_b200 as sb
+    from satnerf_b200 import capi
+    m = sb.load_model(_args(model=model, fc_units=h))
+    lay = capi.param_layout(m.desc)
+    named = list(m.named_parameters())
+    assert len(lay) * 2 == len(named)
+    off = 0
+    for i, (w, b, n_out, n_in) in enumerate(lay):
+        assert named[2 * i][0].endswith(".weight") and tuple(named[2 * i][1].shape) == (n_out, n_in)
+        assert w == off; off += n_out * n_in
+        assert b == off; off += n_out
+    assert off == capi.param_count(m.desc) == sum(p.numel() for p in m.parameters())
+    flat = m.flat_params()
+    assert flat.numel() == off and named[0][1].data_ptr() == flat.data_ptr()
+    # in-place updates through the parameters are visible in the flat buffer (what Adam does)
+    with torch.no_grad():
+        named[3][1].add_(1.0)
+    w3, b3, no3, ni3 = lay[1]
+    assert torch.equal(flat[b3:b3 + no3], named[3][1].detach())
+    g = m.flat_grads()
+    assert all(p.grad is not None and p.grad.data_ptr() >= g.data_ptr() for p in m.parameters())
+
+
+def test_param_count_sat_nerf_512():
+    import satnerf_b200 as sb
+    from satnerf_b200 import capi
+    assert capi.param_count(sb.load_model(_args(fc_units=512)).desc) == 2635785
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models"), reason="reference not present")
+@pytest.mark.parametrize("model", ["sat-nerf", "s-nerf", "nerf"])
+def test_names_shapes_and_init_match_reference(model):
+    import importlib
+    import sys
+    import satnerf_b200 as sb
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref_models = importlib.import_module("models")
+    finally:
+        sys.path.remove("/root/reference")
+    a = _args(model=model, fc_units=128)
+    torch.manual_seed(3); ours = sb.load_model(a)
+    torch.manual_seed(3); theirs = ref_models.load_model(a)
+    sd1, sd2 = ours.state_dict(), theirs.state_dict()
+    assert list(sd1) == list(sd2)
+    for k in sd1:
+        assert torch.equal(sd1[k], sd2[k]), k
+    assert ours.number_of_outputs == theirs.number_of_outputs
+    ours.load_state_dict(sd2)          # released checkpoints load by name
+
+
+def test_no_cpu_fallback():
+    import satnerf_b200 as sb
+    a = _args()
+    ms = {"coarse": sb.load_model(a), "t": torch.nn.Embedding(30, 4)}
+    rays = torch.rand(4, 11)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sb.render_rays(ms, a, rays, torch.zeros(4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ms["coarse"](torch.rand(4, 3), input_sun_dir=torch.rand(4, 3), input_t=torch.rand(4, 4))
+
+
+def test_bad_descriptors_are_rejected():
+    from satnerf_b200 import capi
+    with pytest.raises(ValueError):
+        capi.field_desc("foo", 8, 64, [4])
+    d = capi.field_desc("sat-nerf", 8, 63, [4], 4)
+    with pytest.raises(RuntimeError, match="fc_units"):
+        capi.param_count(d)
