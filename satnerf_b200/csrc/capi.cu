@@ -70,13 +70,17 @@ extern "C" SNB_API int snb_render_workspace(const snb_field_desc* f, const snb_p
 extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
                                   void* workspace, size_t workspace_bytes, void* stream) {
     FieldLayout L; SNB_TRY(build_layout(f, &L)); SNB_TRY(check_pass(L, p));
+    if (p->n_rays == 0) return 0;               // empty batch (pointers of empty tensors may be null)
     if (!io || !io->params || !io->z_vals) SNB_FAIL(-1, "snb_render_forward: params and z_vals are required");
     if (!io->rays && !(io->xyz && io->aux_dir)) SNB_FAIL(-1, "snb_render_forward: rays (or xyz + aux_dir) are required");
     if (L.t_dims && !io->t_emb) SNB_FAIL(-1, "snb_render_forward: sat-nerf needs t_emb (the reference raises on ts=None, satnerf.py:204)");
     if (p->n_rays == 0) return 0;
     if (!workspace) SNB_FAIL(-1, "snb_render_forward: null workspace");
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->precision == SNB_FP16_TC) return tc_render_forward(L, p, io, workspace, workspace_bytes, st);
+    if (p->precision == SNB_FP16_TC) {
+        int r = tc_render_forward(L, p, io, workspace, workspace_bytes, st);
+        if (r != 1) return r;      // 1 = configuration not covered by the tensor-core kernel: fp32 CUDA-core path below
+    }
 
     Arena ar(workspace, workspace_bytes); PassPlan pl; plan_pass(ar, L, p, false, &pl);
     if (ar.overflow) SNB_FAIL(-4, "snb_render_forward: workspace too small (%zu bytes given)", workspace_bytes);
@@ -98,6 +102,7 @@ extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pas
 extern "C" SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
                                    const snb_render_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
     FieldLayout L; SNB_TRY(build_layout(f, &L)); SNB_TRY(check_pass(L, p));
+    if (p->n_rays == 0) return 0;
     if (!io || !g || !io->params || !io->z_vals || !g->g_params) SNB_FAIL(-1, "snb_render_backward: missing required pointer");
     if (!io->rays && !(io->xyz && io->aux_dir)) SNB_FAIL(-1, "snb_render_backward: rays (or xyz + aux_dir) are required");
     if (!io->weights || !io->transparency || !io->sigma) SNB_FAIL(-1, "snb_render_backward: forward stash (weights, transparency, sigma) missing");

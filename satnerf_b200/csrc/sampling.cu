@@ -99,9 +99,9 @@ using namespace snb;
 
 extern "C" SNB_API int snb_stratified_depths(const float* rays, int ray_cols, const float* steps, const float* u, float* z,
                                      int R, int S, void* stream) {
-    if (!rays || !steps || !u || !z) SNB_FAIL(-1, "snb_stratified_depths: null pointer");
     if (R < 0 || S < 1 || ray_cols < 8) SNB_FAIL(-1, "snb_stratified_depths: bad shape R=%d S=%d cols=%d", R, S, ray_cols);
-    if (R == 0) return 0;
+    if (R == 0) return 0;                       // empty batch: nothing to do (pointers may be null)
+    if (!rays || !steps || !u || !z) SNB_FAIL(-1, "snb_stratified_depths: null pointer");
     int n = R * S;
     stratified_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(rays, ray_cols, steps, u, z, R, S);
     SNB_CHECK_LAUNCH();
@@ -109,9 +109,9 @@ extern "C" SNB_API int snb_stratified_depths(const float* rays, int ray_cols, co
 }
 
 extern "C" SNB_API int snb_searchsorted_right(const float* cdf, const float* u, int64_t* inds, int R, int n_cdf, int n_u, void* stream) {
-    if (!cdf || !u || !inds) SNB_FAIL(-1, "snb_searchsorted_right: null pointer");
     if (R < 0 || n_cdf < 1 || n_u < 0) SNB_FAIL(-1, "snb_searchsorted_right: bad shape");
     if (R * n_u == 0) return 0;
+    if (!cdf || !u || !inds) SNB_FAIL(-1, "snb_searchsorted_right: null pointer");
     searchsorted_kernel<<<ceil_div(R * n_u, 256), 256, 0, (cudaStream_t)stream>>>(cdf, u, inds, R, n_cdf, n_u);
     SNB_CHECK_LAUNCH();
     return 0;
@@ -119,9 +119,9 @@ extern "C" SNB_API int snb_searchsorted_right(const float* cdf, const float* u, 
 
 extern "C" SNB_API int snb_importance_depths(const float* z_coarse, const float* weights_coarse, const float* u, float* z_out,
                                      int64_t* inds, float* z_new, float* cdf, int R, int S, int N, void* stream) {
-    if (!z_coarse || !weights_coarse || !u || !z_out) SNB_FAIL(-1, "snb_importance_depths: null pointer");
     if (R < 0 || S < 3 || N < 1) SNB_FAIL(-1, "snb_importance_depths: bad shape R=%d S=%d N=%d", R, S, N);
     if (R == 0) return 0;
+    if (!z_coarse || !weights_coarse || !u || !z_out) SNB_FAIL(-1, "snb_importance_depths: null pointer");
     const int warps = 4;
     size_t smem = (size_t)warps * (2 * (S - 1) + S + N) * sizeof(float);
     if (smem > 200 * 1024) SNB_FAIL(-1, "snb_importance_depths: S+N too large for shared memory");

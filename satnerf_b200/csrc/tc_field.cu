@@ -1,8 +1,647 @@
+// Fused tensor-core render pass for sm_100a (SNB_FP16_TC): one persistent, warp-specialised kernel
+// evaluates the whole field (SatNeRF / ShadowNeRF forward, models/satnerf.py:156-208) on 128-point
+// tiles and alpha-composites the rays of the tile group (satnerf.py:43-78) without activations ever
+// leaving the SM:
+//
+//   warp 0      weight producer: streams pre-swizzled fp16 weight tiles (L2-resident, ~5 MB) into a
+//               shared-memory ring with 1-D bulk async copies (TMA engine) + mbarrier transactions
+//   warp 1      MMA issuer: tcgen05.mma (M=128 points, N<=256 features, K=16) with the activation tile
+//               as the K-major A operand in shared memory, accumulators in TMEM (all 512 columns)
+//   warps 2-5   epilogue: sample positions and the K=3 first layer in fp32 on CUDA cores, then per
+//               layer TMEM -> registers, bias (+ fp32 skip / per-ray terms), sin, fp16 pack into the
+//               swizzled A tile of the next layer; the tiny output heads (sigma, rgb, sun, beta) are
+//               dot products folded into the epilogue of the layer that feeds them; finally a
+//               warp-scan transmittance product composites each ray and writes the result dict.
+//
+// Arithmetic: fp16 operands / fp32 accumulation for the h x h contractions; first layer, skip term,
+// per-ray sun / embedding terms, heads and compositing in fp32 (SURVEY.md §7 "Precision").
 #include "tc_field.cuh"
+#include "sm100_ptx.cuh"
+
 namespace snb {
-int tc_workspace(const FieldLayout&, const snb_pass_desc*, bool, size_t* bytes) { *bytes = 0; return 0; }
-int tc_render_forward(const FieldLayout&, const snb_pass_desc*, const snb_render_io*, void*, size_t, cudaStream_t) {
-    SNB_FAIL(-5, "tensor-core path not built yet");
+
+using namespace ptx;
+
+constexpr int kTile = 128;             // points per tile = UMMA M
+constexpr int kMaxGemms = 24;
+constexpr int kMaxGroupRays = 4;
+constexpr int kMaxGroupPts = 384;
+constexpr int kSlabBytes = kTile * 128;      // one 64-wide K slab of the A tile
+constexpr int kTblF = 8192, kTblV = 2048;    // epilogue table region: [N][4] or [N] floats + extra vector
+constexpr int kThreads = 192;
+
+enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3 };
+enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
+
+struct TcGemm {
+    int kind, N, K, n_chunks, chunk_n, k_slabs, skip, last, fmt, has_vec;
+    int tbl_off, vec_off;            // float offsets into the packed table area
+    // weight sources (flat fp32 params): rows [0,rows0) from src0, the rest from src1
+    long long src0, src1; int ld0, ld1, col0, col1, rows0;
+};
+
+struct TcProgram {
+    int H, H2, n_gemms, tau, has_beta, a_slabs, stage_bytes, n_stages;
+    int l0_tbl, consts, sunw, betaw, sky;        // float offsets in the table area
+    long long l0_w, l0_b;                        // flat param offsets of trunk layer 0
+    long long tables_base;                       // byte offset of the table area in the packed buffer
+    TcGemm g[kMaxGemms];
+};
+
+struct TcArgs {
+    TcProgram prog;
+    const float *params, *rays, *z, *t_emb, *noise, *xyz, *aux;
+    float noise_std;
+    float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma;
+    unsigned char* packed;
+    int R, S, ray_cols, dir_col, G, n_groups;
+};
+
+// --------------------------------------------------------------------------------------------------
+// host: build the per-tile GEMM program
+// --------------------------------------------------------------------------------------------------
+static bool tc_supported(const FieldLayout& L, const snb_pass_desc* p) {
+    if (L.variant == SNB_NERF) return false;                 // PE + ReLU variant stays on the fp32 path for now
+    if (L.width % 64 != 0 || L.width > 512 || L.width < 64) return false;
+    if (L.n_layers + 4 > kMaxGemms) return false;
+    if (p->n_samples > kMaxGroupPts) return false;
+    if (L.t_dims > 32) return false;
+    return true;
 }
-int tc_render_backward(const FieldLayout&, const snb_pass_desc*, const snb_render_io*, const snb_render_grads*, void*, size_t, cudaStream_t) { return 1; }
+
+static int build_program(const FieldLayout& L, TcProgram* P) {
+    memset(P, 0, sizeof(*P));
+    const int H = L.width, H2 = H / 2;
+    P->H = H; P->H2 = H2; P->tau = L.t_dims; P->has_beta = L.variant == SNB_SATNERF;
+    P->a_slabs = H / 64;
+    int ng = 0; int tbl = 0;
+    auto add = [&](int kind, int N, int K) -> TcGemm& {
+        TcGemm& g = P->g[ng++]; memset(&g, 0, sizeof(g));
+        g.kind = kind; g.N = N; g.K = K; g.n_chunks = (N + 255) / 256; g.chunk_n = N / g.n_chunks; g.k_slabs = (K + 63) / 64;
+        return g;
+    };
+    auto tables = [&](TcGemm& g, int fmt, int vec) {
+        g.fmt = fmt; g.has_vec = vec; g.tbl_off = tbl; tbl += g.N * (fmt == TF_F4 ? 4 : (fmt == TF_F1 ? 1 : 0));
+        g.vec_off = tbl; if (vec) tbl += g.N;
+    };
+    P->l0_tbl = tbl; tbl += H * 4;
+    P->l0_w = L.trunk[0].w; P->l0_b = L.trunk[0].b;
+    for (int i = 1; i < L.n_layers; ++i) {
+        TcGemm& g = add(GK_TRUNK, H, H);
+        g.skip = i == L.skip; g.last = i == L.n_layers - 1;
+        g.src0 = L.trunk[i].w; g.ld0 = L.trunk[i].n_in; g.col0 = g.skip ? L.in_xyz : 0; g.rows0 = H;
+        tables(g, g.skip ? TF_F4 : TF_F1, g.last);
+    }
+    { TcGemm& g = add(GK_FEAT, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; tables(g, TF_F1, 0); }
+    { int nb = P->has_beta ? H2 : 0;
+      TcGemm& g = add(GK_HEADA, nb + H2, H);
+      g.src0 = P->has_beta ? L.beta0.w : L.rgb0.w; g.ld0 = P->has_beta ? L.beta0.n_in : L.rgb0.n_in; g.rows0 = P->has_beta ? nb : H2;
+      g.src1 = L.rgb0.w; g.ld1 = L.rgb0.n_in;
+      tables(g, TF_F4, 0); }
+    { TcGemm& g = add(GK_SUN1, H2, H); g.src0 = L.sun[0].w; g.ld0 = L.sun[0].n_in; g.rows0 = H2; tables(g, TF_NONE, 0); }
+    { TcGemm& g = add(GK_SUN2, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 0); }
+    { TcGemm& g = add(GK_SUN3, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 1); }
+    P->n_gemms = ng;
+    P->consts = tbl; tbl += 8;
+    P->sunw = tbl; tbl += 4 * H2;                 // [3][H2] weights + [H2] bias
+    P->betaw = tbl; tbl += (L.t_dims + 1) * H2;   // [tau][H2] weights + [H2] bias
+    P->sky = tbl; tbl += 4 * H2 + 3 * H2 + 4;     // sky0 [H2][3]+b[H2] as [H2][4]; sky2 [3][H2]; b2[3]
+    long long wbytes = 0; int max_stage = 0;
+    for (int i = 0; i < ng; ++i) {
+        wbytes += (long long)P->g[i].n_chunks * P->g[i].k_slabs * P->g[i].chunk_n * 128;
+        if (P->g[i].chunk_n * 128 > max_stage) max_stage = P->g[i].chunk_n * 128;
+    }
+    P->stage_bytes = max_stage;
+    P->tables_base = (wbytes + 255) & ~255LL;
+    return tbl;      // number of floats in the table area
 }
+
+static size_t smem_fixed_bytes() {
+    return kTblF + kTblV + 8 * kMaxGroupPts * 4 /*raw SoA incl. z, w, T*/ + 2 * kMaxGroupRays * 256 * 4 + 512;
+}
+
+// --------------------------------------------------------------------------------------------------
+// weight / table packing (runs every call: parameters change every optimiser step; ~5 MB, a few us)
+// --------------------------------------------------------------------------------------------------
+__global__ void tc_pack_kernel(TcProgram P, const float* __restrict__ W, unsigned char* __restrict__ packed) {
+    const int gi = blockIdx.y;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    float* T = reinterpret_cast<float*>(packed + P.tables_base);
+    const int H = P.H;
+    if (gi < P.n_gemms) {
+        const TcGemm g = P.g[gi];
+        long long base = 0;
+        for (int i = 0; i < gi; ++i) base += (long long)P.g[i].n_chunks * P.g[i].k_slabs * P.g[i].chunk_n * 128;
+        __half* out = reinterpret_cast<__half*>(packed + base);
+        // B tiles: for chunk j, slab s: [chunk_n rows][64 k] fp16, 128-byte swizzle
+        const long long total = (long long)g.n_chunks * g.k_slabs * g.chunk_n * 64;
+        for (long long e = tid; e < total; e += nthr) {
+            int kk = (int)(e & 63); long long r = e >> 6;
+            int nl = (int)(r % g.chunk_n); long long t = r / g.chunk_n;
+            int s = (int)(t % g.k_slabs), j = (int)(t / g.k_slabs);
+            int n = j * g.chunk_n + nl, k = s * 64 + kk;
+            float v = 0.f;
+            if (k < g.K) v = n < g.rows0 ? W[g.src0 + (long long)n * g.ld0 + g.col0 + k]
+                                         : W[g.src1 + (long long)(n - g.rows0) * g.ld1 + g.col1 + k];
+            size_t tile = (size_t)(j * g.k_slabs + s) * g.chunk_n * 64;
+            size_t off = tile + (size_t)nl * 64 + ((((kk >> 3) ^ (nl & 7)) << 3) | (kk & 7));
+            out[off] = __float2half_rn(v);
+        }
+        // epilogue tables
+        for (int n = tid; n < g.N; n += nthr) {
+            float* t4 = T + g.tbl_off;
+            switch (g.kind) {
+                case GK_TRUNK: {
+                    // which trunk layer: recover from the weight offset (bias follows the weight block)
+                    long long boff = g.src0 + (long long)H * g.ld0;
+                    if (g.fmt == TF_F4) { t4[n * 4] = W[boff + n]; for (int c = 0; c < 3; ++c) t4[n * 4 + 1 + c] = W[g.src0 + (long long)n * g.ld0 + c]; }
+                    else t4[n] = W[boff + n];
+                    break; }
+                case GK_FEAT: case GK_SUN2: case GK_SUN3: t4[n] = W[g.src0 + (long long)g.N * g.ld0 + n]; break;
+                default: break;      // HEADA / per-ray tables are written by tc_pack_misc_kernel
+            }
+        }
+    }
+}
+
+struct MiscOffsets { long long sigma_w, sigma_b, rgb0_b, rgb2_w, rgb2_b, sun0_w, sun0_b, sun3_w, sun3_b, sky0_w, sky0_b, sky2_w, sky2_b,
+                               beta0_w, beta0_b, beta2_w, beta2_b; int sun0_ld, beta0_ld; };
+
+__global__ void tc_pack_misc_kernel(TcProgram P, MiscOffsets M, const float* __restrict__ W, unsigned char* __restrict__ packed) {
+    float* T = reinterpret_cast<float*>(packed + P.tables_base);
+    const int H = P.H, H2 = P.H2;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    // layer-0 table [H][4] = (wx, wy, wz, b)
+    for (int n = tid; n < H; n += nthr) {
+        float* t = T + P.l0_tbl + n * 4;
+        t[0] = W[P.l0_w + n * 3]; t[1] = W[P.l0_w + n * 3 + 1]; t[2] = W[P.l0_w + n * 3 + 2]; t[3] = W[P.l0_b + n];
+    }
+    // sigma vector on the last trunk GEMM, sun_v_net.6 vector on SUN3, HEADA table
+    for (int gi = 0; gi < P.n_gemms; ++gi) {
+        const TcGemm& g = P.g[gi];
+        if (g.kind == GK_TRUNK && g.last) for (int n = tid; n < H; n += nthr) T[g.vec_off + n] = W[M.sigma_w + n];
+        if (g.kind == GK_SUN3) for (int n = tid; n < H2; n += nthr) T[g.vec_off + n] = W[M.sun3_w + n];
+        if (g.kind == GK_HEADA) {
+            int nb = P.has_beta ? H2 : 0;
+            for (int n = tid; n < g.N; n += nthr) {
+                float* t = T + g.tbl_off + n * 4;
+                if (n < nb) { t[0] = 0.f; t[1] = W[M.beta2_w + n]; t[2] = 0.f; t[3] = 0.f; }
+                else { int m = n - nb; t[0] = W[M.rgb0_b + m]; t[1] = W[M.rgb2_w + m]; t[2] = W[M.rgb2_w + H2 + m]; t[3] = W[M.rgb2_w + 2 * H2 + m]; }
+            }
+        }
+    }
+    if (tid == 0) {
+        float* c = T + P.consts;
+        c[0] = W[M.sigma_b]; c[1] = W[M.rgb2_b]; c[2] = W[M.rgb2_b + 1]; c[3] = W[M.rgb2_b + 2];
+        c[4] = W[M.sun3_b]; c[5] = P.has_beta ? W[M.beta2_b] : 0.f; c[6] = 0.f; c[7] = 0.f;
+    }
+    for (int n = tid; n < H2; n += nthr) {
+        for (int c = 0; c < 3; ++c) T[P.sunw + c * H2 + n] = W[M.sun0_w + (long long)n * M.sun0_ld + H + c];
+        T[P.sunw + 3 * H2 + n] = W[M.sun0_b + n];
+        if (P.has_beta) {
+            for (int c = 0; c < P.tau; ++c) T[P.betaw + c * H2 + n] = W[M.beta0_w + (long long)n * M.beta0_ld + H + c];
+            T[P.betaw + P.tau * H2 + n] = W[M.beta0_b + n];
+        }
+        float* s = T + P.sky + n * 4;
+        s[0] = W[M.sky0_w + n * 3]; s[1] = W[M.sky0_w + n * 3 + 1]; s[2] = W[M.sky0_w + n * 3 + 2]; s[3] = W[M.sky0_b + n];
+        for (int c = 0; c < 3; ++c) T[P.sky + 4 * H2 + c * H2 + n] = W[M.sky2_w + c * H2 + n];
+    }
+    if (tid < 3) T[P.sky + 7 * H2 + tid] = W[M.sky2_b + tid];
+}
+
+// --------------------------------------------------------------------------------------------------
+// the fused kernel
+// --------------------------------------------------------------------------------------------------
+struct Smem {
+    unsigned char* a;        // activation tile: a_slabs x [128 rows x 128 B], 128B-swizzled, K-major
+    unsigned char* b;        // weight ring: n_stages x stage_bytes
+    float* tblF;             // [N][4] or [N]
+    float* tblV;             // [N]
+    float *z, *sg, *al0, *al1, *al2, *sn, *bt, *wt;   // per-point tables of the current group (kMaxGroupPts each)
+    float* sunb;             // [kMaxGroupRays][H2] per-ray bias of sun_v_net.0 (bias + W[:,H:H+3] sun_d)
+    float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
+    float* skyc;             // [kMaxGroupRays][4]
+    float* consts;           // 8 floats
+    uint64_t *full, *empty, *acc_full, *a_ready;
+    uint32_t* tmem_ptr;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P) {
+    Smem s; unsigned char* p = base;
+    s.a = p; p += (size_t)P.a_slabs * kSlabBytes;
+    s.b = p; p += (size_t)P.n_stages * P.stage_bytes;
+    s.tblF = (float*)p; p += kTblF;
+    s.tblV = (float*)p; p += kTblV;
+    float* f = (float*)p;
+    s.z = f; s.sg = f + kMaxGroupPts; s.al0 = f + 2 * kMaxGroupPts; s.al1 = f + 3 * kMaxGroupPts; s.al2 = f + 4 * kMaxGroupPts;
+    s.sn = f + 5 * kMaxGroupPts; s.bt = f + 6 * kMaxGroupPts; s.wt = f + 7 * kMaxGroupPts;
+    p += 8 * kMaxGroupPts * 4;
+    s.sunb = (float*)p; p += kMaxGroupRays * 256 * 4;
+    s.betab = (float*)p; p += kMaxGroupRays * 256 * 4;
+    s.skyc = (float*)p; p += 64;
+    s.consts = (float*)p; p += 32;
+    s.full = (uint64_t*)p; p += 8 * 8;
+    s.empty = (uint64_t*)p; p += 8 * 8;
+    s.acc_full = (uint64_t*)p; p += 8;
+    s.a_ready = (uint64_t*)p; p += 8;
+    s.tmem_ptr = (uint32_t*)p;
+    return s;
+}
+
+__device__ __forceinline__ int group_points(const TcArgs& A, int grp) {
+    int r0 = grp * A.G; int n = A.R - r0; if (n > A.G) n = A.G; return n * A.S;
+}
+
+// byte address of the 16-byte chunk holding k..k+7 (k % 8 == 0) of `row` in the swizzled A tile
+__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int row, int k) {
+    return a_base + (uint32_t)(k >> 6) * kSlabBytes + (uint32_t)row * 128u + ((((uint32_t)(k >> 3) & 7u) ^ ((uint32_t)row & 7u)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// store 32 consecutive activations (k0 % 32 == 0) of one row as fp16
+__device__ __forceinline__ void store_act32(uint32_t a_base, int row, int k0, const float* v) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float* x = v + c * 8;
+        sts128(a_chunk_addr(a_base, row, k0 + c * 8), pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
+    }
+}
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// cooperative copy (128 epilogue threads) of `bytes` (multiple of 16) from global to shared with cp.async
+__device__ __forceinline__ void table_copy(void* dst, const void* src, int bytes, int tid_e) {
+    for (int o = tid_e * 16; o < bytes; o += 128 * 16) cp_async16((char*)dst + o, (const char*)src + o);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const TcProgram& P = A.prog;
+    Smem sm = carve(base, P);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* T = reinterpret_cast<const float*>(A.packed + P.tables_base);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(sm.tmem_ptr, 512);
+    if (threadIdx.x >= 64 && threadIdx.x < 72) sm.consts[threadIdx.x - 64] = T[P.consts + threadIdx.x - 64];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sm.tmem_ptr;
+
+    if (warp == 0) {
+        // ================= weight producer (lane 0 issues; the warp stays converged) =================
+        int st = 0; uint32_t ph = 0;
+        for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
+            const int n_tiles = (group_points(A, grp) + kTile - 1) / kTile;
+            for (int t = 0; t < n_tiles; ++t) {
+                const unsigned char* src = A.packed;
+                for (int gi = 0; gi < P.n_gemms; ++gi) {
+                    const uint32_t bytes = (uint32_t)P.g[gi].chunk_n * 128u;
+                    const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
+                    for (int i = 0; i < n; ++i) {
+                        if (lane == 0) {
+                            mbar_wait(&sm.empty[st], ph ^ 1, 1);
+                            mbar_arrive_expect_tx(&sm.full[st], bytes);
+                            bulk_g2s(sm.b + (size_t)st * P.stage_bytes, src, bytes, &sm.full[st]);
+                        }
+                        __syncwarp();
+                        src += bytes;
+                        if (++st == P.n_stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        int st = 0; uint32_t ph = 0, ready_ph = 0;
+        const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
+        for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
+            const int n_tiles = (group_points(A, grp) + kTile - 1) / kTile;
+            for (int t = 0; t < n_tiles; ++t) {
+                for (int gi = 0; gi < P.n_gemms; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    mbar_wait(sm.a_ready, ready_ph, 2); ready_ph ^= 1;
+                    tc_fence_after();
+                    const uint32_t idesc = umma_idesc_f16((uint32_t)g.chunk_n);
+                    for (int j = 0; j < g.n_chunks; ++j) {
+                        for (int s = 0; s < g.k_slabs; ++s) {
+                            mbar_wait(&sm.full[st], ph, 3);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
+                                const uint32_t a_addr = a_base + (uint32_t)s * kSlabBytes;
+                                const uint32_t b_addr = b_base + (uint32_t)st * P.stage_bytes;
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_f16_ss(tmem + (uint32_t)(j * g.chunk_n), umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
+                                                idesc, (s | k) != 0);
+                                umma_commit(&sm.empty[st]);
+                                if (j == g.n_chunks - 1 && s == g.k_slabs - 1) umma_commit(sm.acc_full);
+                            }
+                            __syncwarp();
+                            if (++st == P.n_stages) { st = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps (128 threads) =================
+        const int tid_e = threadIdx.x - 64;
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;                // point (row of the tile) owned by this thread
+        const uint32_t a_base = smem_u32(sm.a);
+        const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
+        const int H = P.H, H2 = P.H2, S = A.S;
+        uint32_t acc_ph = 0;
+        const int aux_col = 8;
+        for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
+            const int r0 = grp * A.G;
+            const int n_rays = min(A.G, A.R - r0);
+            const int Pg = n_rays * S;
+            const int n_tiles = (Pg + kTile - 1) / kTile;
+            // ---- per-ray tables: sun / embedding terms of the first head layers, sky colour ----
+            for (int idx = tid_e; idx < n_rays * H2; idx += 128) {
+                int gr = idx / H2, n = idx - gr * H2;
+                const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
+                float v = T[P.sunw + 3 * H2 + n];
+                v = fmaf(T[P.sunw + n], sd[0], v); v = fmaf(T[P.sunw + H2 + n], sd[1], v); v = fmaf(T[P.sunw + 2 * H2 + n], sd[2], v);
+                sm.sunb[gr * H2 + n] = v;
+                if (P.has_beta) {
+                    float b = T[P.betaw + P.tau * H2 + n];
+                    const float* te = A.t_emb + (size_t)(r0 + gr) * P.tau;
+                    for (int c = 0; c < P.tau; ++c) b = fmaf(T[P.betaw + c * H2 + n], te[c], b);
+                    sm.betab[gr * H2 + n] = b;
+                }
+            }
+            for (int gr = warp - 2; gr < n_rays; gr += 4) {          // sky_color(sun_d): per ray (satnerf.py:201)
+                const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+                for (int n = lane; n < H2; n += 32) {
+                    const float* s4 = T + P.sky + n * 4;
+                    float hdn = fmaxf(fmaf(s4[2], sd[2], fmaf(s4[1], sd[1], fmaf(s4[0], sd[0], s4[3]))), 0.f);
+                    o0 = fmaf(T[P.sky + 4 * H2 + n], hdn, o0); o1 = fmaf(T[P.sky + 5 * H2 + n], hdn, o1); o2 = fmaf(T[P.sky + 6 * H2 + n], hdn, o2);
+                }
+                for (int off = 16; off; off >>= 1) { o0 += __shfl_xor_sync(~0u, o0, off); o1 += __shfl_xor_sync(~0u, o1, off); o2 += __shfl_xor_sync(~0u, o2, off); }
+                if (lane == 0) {
+                    sm.skyc[gr * 4] = sigmoid_f(o0 + T[P.sky + 7 * H2]); sm.skyc[gr * 4 + 1] = sigmoid_f(o1 + T[P.sky + 7 * H2 + 1]);
+                    sm.skyc[gr * 4 + 2] = sigmoid_f(o2 + T[P.sky + 7 * H2 + 2]);
+                }
+            }
+            for (int t = 0; t < n_tiles; ++t) {
+                // ---- sample position of this thread's point ----
+                const int p = t * kTile + row;
+                const bool valid = p < Pg;
+                int rl = valid ? p / S : 0;                       // ray within the group
+                float px = 0.f, py = 0.f, pz = 0.f;
+                if (valid) {
+                    const size_t gp = (size_t)r0 * S + p;
+                    float zz = A.z[gp];
+                    sm.z[p] = zz;
+                    if (A.xyz) { px = A.xyz[gp * 3]; py = A.xyz[gp * 3 + 1]; pz = A.xyz[gp * 3 + 2]; }
+                    else {
+                        const float* ray = A.rays + (size_t)(r0 + rl) * A.ray_cols;       // rendering.py:81 / :104
+                        px = __fadd_rn(ray[0], __fmul_rn(ray[A.dir_col], zz));
+                        py = __fadd_rn(ray[1], __fmul_rn(ray[A.dir_col + 1], zz));
+                        pz = __fadd_rn(ray[2], __fmul_rn(ray[A.dir_col + 2], zz));
+                    }
+                }
+                // ---- trunk layer 0 on CUDA cores: sin(30 (W0 x + b0)), K = 3 (satnerf.py:105-106) ----
+                table_copy(sm.tblF, T + P.l0_tbl, H * 16, tid_e);
+                cp_async_wait_all();
+                named_bar_sync(1, 128);
+                for (int n0 = 0; n0 < H; n0 += 32) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float4 w = reinterpret_cast<const float4*>(sm.tblF)[n0 + i];
+                        float y = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
+                        v[i] = __sinf(__fmul_rn(30.0f, y));
+                    }
+                    store_act32(a_base, row, n0, v);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);                          // everyone is done with the layer-0 table
+                {   const TcGemm& g0 = P.g[0];
+                    if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
+                    if (g0.has_vec) table_copy(sm.tblV, T + g0.vec_off, g0.N * 4, tid_e); }
+                mbar_arrive(sm.a_ready);
+
+                float sig_dot = 0.f, beta_dot = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f, sun_dot = 0.f;
+                for (int gi = 0; gi < P.n_gemms; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    cp_async_wait_all();
+                    named_bar_sync(1, 128);                      // tables of this GEMM are in shared memory
+                    mbar_wait(sm.acc_full, acc_ph, 4); acc_ph ^= 1;
+                    tc_fence_after();
+                    const float4* T4 = reinterpret_cast<const float4*>(sm.tblF);
+                    for (int n0 = 0; n0 < g.N; n0 += 32) {
+                        float v[32];
+                        tmem_ld32(tm_row + (uint32_t)n0, v);
+                        tmem_ld_wait();
+                        switch (g.kind) {
+                            case GK_TRUNK:
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    float y;
+                                    if (g.skip) { float4 w = T4[n0 + i]; y = v[i] + fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x))); }
+                                    else y = v[i] + sm.tblF[n0 + i];
+                                    v[i] = __sinf(y);
+                                    if (g.last) sig_dot = fmaf(sm.tblV[n0 + i], v[i], sig_dot);
+                                }
+                                store_act32(a_base, row, n0, v);
+                                break;
+                            case GK_FEAT:
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] += sm.tblF[n0 + i];
+                                store_act32(a_base, row, n0, v);
+                                break;
+                            case GK_HEADA:
+                                if (P.has_beta && n0 < H2) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) {
+                                        float a = __sinf(v[i] + sm.betab[rl * H2 + n0 + i]);
+                                        beta_dot = fmaf(T4[n0 + i].y, a, beta_dot);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) {
+                                        float4 w = T4[n0 + i];
+                                        float a = __sinf(v[i] + w.x);
+                                        rgb0 = fmaf(w.y, a, rgb0); rgb1 = fmaf(w.z, a, rgb1); rgb2 = fmaf(w.w, a, rgb2);
+                                    }
+                                }
+                                break;
+                            case GK_SUN1:
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i] + sm.sunb[rl * H2 + n0 + i]);
+                                store_act32(a_base, row, n0, v);
+                                break;
+                            case GK_SUN2:
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i] + sm.tblF[n0 + i]);
+                                store_act32(a_base, row, n0, v);
+                                break;
+                            default:   // GK_SUN3
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) sun_dot = fmaf(sm.tblV[n0 + i], __sinf(v[i] + sm.tblF[n0 + i]), sun_dot);
+                                break;
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);                      // all TMEM reads / A writes / table reads of this GEMM done
+                    if (gi + 1 < P.n_gemms) {
+                        const TcGemm& gn = P.g[gi + 1];
+                        if (gn.fmt != TF_NONE) table_copy(sm.tblF, T + gn.tbl_off, gn.N * gn.fmt * 4, tid_e);
+                        if (gn.has_vec) table_copy(sm.tblV, T + gn.vec_off, gn.N * 4, tid_e);
+                        mbar_arrive(sm.a_ready);
+                    }
+                }
+                // ---- head outputs of this point ----
+                if (valid) {
+                    sm.sg[p] = softplus_f(sig_dot + sm.consts[0]);                                    // satnerf.py:183
+                    sm.al0[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb0 + sm.consts[1]), 1.002f), 0.001f);  // :193-195
+                    sm.al1[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb1 + sm.consts[2]), 1.002f), 0.001f);
+                    sm.al2[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb2 + sm.consts[3]), 1.002f), 0.001f);
+                    sm.sn[p] = sigmoid_f(sun_dot + sm.consts[4]);                                      // :200
+                    sm.bt[p] = P.has_beta ? softplus_f(beta_dot + sm.consts[5]) : 0.f;                 // :205
+                }
+            }
+            named_bar_sync(1, 128);
+            // ---- alpha compositing: one warp per ray, transmittance by warp scan (satnerf.py:52-70) ----
+            for (int gr = warp - 2; gr < n_rays; gr += 4) {
+                const int ray = r0 + gr;
+                float carry = 1.f, depth = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+                const float k0 = sm.skyc[gr * 4], k1 = sm.skyc[gr * 4 + 1], k2 = sm.skyc[gr * 4 + 2];
+                for (int b0 = 0; b0 < S; b0 += 32) {
+                    const int i = b0 + lane, p = gr * S + i;
+                    const bool ok = i < S;
+                    float alpha = 0.f, q = 1.f, zi = 0.f;
+                    if (ok) {
+                        zi = sm.z[p];
+                        float delta = i < S - 1 ? __fsub_rn(sm.z[p + 1], zi) : 1e10f;
+                        float nz = A.noise ? A.noise[(size_t)ray * S + i] * A.noise_std : 0.f;
+                        alpha = 1.0f - expf(-delta * fmaxf(sm.sg[p] + nz, 0.f));
+                        q = (1.0f - alpha) + 1e-10f;
+                    }
+                    float incl = q;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) { float o = __shfl_up_sync(~0u, incl, off); if (lane >= off) incl *= o; }
+                    float excl = __shfl_up_sync(~0u, incl, 1); if (lane == 0) excl = 1.f;
+                    const float Tr = carry * excl, w = alpha * Tr;
+                    carry *= __shfl_sync(~0u, incl, 31);
+                    if (ok) {
+                        const size_t gp = (size_t)ray * S + i;
+                        if (A.weights) A.weights[gp] = w;
+                        if (A.transparency) A.transparency[gp] = Tr;
+                        if (A.sigma) A.sigma[gp] = sm.sg[p];
+                        const float s = sm.sn[p];
+                        depth = fmaf(w, zi, depth);
+                        c0 += w * sm.al0[p] * (s + (1.f - s) * k0);
+                        c1 += w * sm.al1[p] * (s + (1.f - s) * k1);
+                        c2 += w * sm.al2[p] * (s + (1.f - s) * k2);
+                        if (A.sun) A.sun[gp] = s;
+                        if (A.beta && P.has_beta) A.beta[gp] = sm.bt[p];
+                        if (A.albedo) { A.albedo[gp * 3] = sm.al0[p]; A.albedo[gp * 3 + 1] = sm.al1[p]; A.albedo[gp * 3 + 2] = sm.al2[p]; }
+                        if (A.sky) { A.sky[gp * 3] = k0; A.sky[gp * 3 + 1] = k1; A.sky[gp * 3 + 2] = k2; }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off; off >>= 1) {
+                    depth += __shfl_xor_sync(~0u, depth, off); c0 += __shfl_xor_sync(~0u, c0, off);
+                    c1 += __shfl_xor_sync(~0u, c1, off); c2 += __shfl_xor_sync(~0u, c2, off);
+                }
+                if (lane == 0) {
+                    if (A.depth) A.depth[ray] = depth;
+                    if (A.rgb) { A.rgb[ray * 3] = fminf(fmaxf(c0, 0.f), 1.f); A.rgb[ray * 3 + 1] = fminf(fmaxf(c1, 0.f), 1.f); A.rgb[ray * 3 + 2] = fminf(fmaxf(c2, 0.f), 1.f); }
+                }
+            }
+            named_bar_sync(1, 128);                              // group tables are reused by the next group
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// --------------------------------------------------------------------------------------------------
+// host entry points
+// --------------------------------------------------------------------------------------------------
+static int choose_group(int S) {
+    int best = 1; double best_u = 0.0;
+    for (int G = 1; G <= kMaxGroupRays; ++G) {
+        int pts = G * S; if (pts > kMaxGroupPts) break;
+        double u = (double)pts / (double)(((pts + kTile - 1) / kTile) * kTile);
+        if (u > best_u + 1e-9) { best_u = u; best = G; }
+    }
+    return best;
+}
+
+int tc_workspace(const FieldLayout& L, const snb_pass_desc* p, bool backward, size_t* bytes) {
+    *bytes = 0;
+    if (!tc_supported(L, p)) return 0;
+    TcProgram P; int nfl = build_program(L, &P);
+    *bytes = (size_t)P.tables_base + (size_t)nfl * 4 + 1024;
+    (void)backward;
+    return 0;
+}
+
+int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_render_io* io, void* workspace, size_t workspace_bytes,
+                      cudaStream_t st) {
+    if (!tc_supported(L, p)) return 1;
+    static int sm_count = 0, max_smem = 0;
+    if (!sm_count) {
+        int dev = 0; SNB_CUDA(cudaGetDevice(&dev));
+        int major = 0; SNB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (major != 10) SNB_FAIL(-6, "the tensor-core path needs an sm_100 device (compute capability %d.x found)", major);
+        SNB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        SNB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    TcArgs A; memset(&A, 0, sizeof(A));
+    int nfl = build_program(L, &A.prog);
+    TcProgram& P = A.prog;
+    size_t need = (size_t)P.tables_base + (size_t)nfl * 4;
+    if (need > workspace_bytes) SNB_FAIL(-4, "tensor-core path: workspace too small (%zu < %zu)", workspace_bytes, need);
+    size_t fixed = (size_t)P.a_slabs * kSlabBytes + smem_fixed_bytes() + 1024;
+    int ns = (int)(((size_t)max_smem - fixed) / P.stage_bytes); if (ns > 8) ns = 8;
+    if (ns < 2) SNB_FAIL(-6, "tensor-core path: not enough shared memory for the weight ring");
+    P.n_stages = ns;
+    size_t smem = fixed + (size_t)ns * P.stage_bytes;
+
+    A.params = io->params; A.rays = io->rays; A.z = io->z_vals; A.t_emb = io->t_emb; A.noise = p->noise_std != 0.f ? io->noise : nullptr;
+    A.noise_std = p->noise_std; A.xyz = io->xyz; A.aux = io->aux_dir;
+    A.rgb = io->rgb; A.depth = io->depth; A.weights = io->weights; A.transparency = io->transparency; A.albedo = io->albedo;
+    A.sun = io->sun; A.sky = io->sky; A.beta = io->beta; A.sigma = io->sigma;
+    A.packed = (unsigned char*)workspace;
+    A.R = p->n_rays; A.S = p->n_samples; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
+    A.G = choose_group(A.S); A.n_groups = (A.R + A.G - 1) / A.G;
+
+    MiscOffsets M; memset(&M, 0, sizeof(M));
+    M.sigma_w = L.sigma.w; M.sigma_b = L.sigma.b; M.rgb0_b = L.rgb0.b; M.rgb2_w = L.rgb2.w; M.rgb2_b = L.rgb2.b;
+    M.sun0_w = L.sun[0].w; M.sun0_b = L.sun[0].b; M.sun0_ld = L.sun[0].n_in; M.sun3_w = L.sun[3].w; M.sun3_b = L.sun[3].b;
+    M.sky0_w = L.sky0.w; M.sky0_b = L.sky0.b; M.sky2_w = L.sky2.w; M.sky2_b = L.sky2.b;
+    M.beta0_w = L.beta0.w; M.beta0_b = L.beta0.b; M.beta0_ld = L.beta0.n_in; M.beta2_w = L.beta2.w; M.beta2_b = L.beta2.b;
+
+    tc_pack_kernel<<<dim3(64, P.n_gemms), 256, 0, st>>>(P, io->params, A.packed);
+    SNB_CHECK_LAUNCH();
+    tc_pack_misc_kernel<<<8, 256, 0, st>>>(P, M, io->params, A.packed);
+    SNB_CHECK_LAUNCH();
+    SNB_CUDA(cudaFuncSetAttribute(tc_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = A.n_groups < sm_count ? A.n_groups : sm_count;
+    tc_render_kernel<<<grid, kThreads, smem, st>>>(A);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+int tc_render_backward(const FieldLayout&, const snb_pass_desc*, const snb_render_io*, const snb_render_grads*, void*, size_t, cudaStream_t) {
+    return 1;   // round 1: gradients of the tensor-core forward are taken by the fp32 CUDA-core backward chain
+}
+
+}  // namespace snb

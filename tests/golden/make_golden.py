@@ -61,8 +61,9 @@ class Recorder:
 
 
 def pcg_params(shapes, seed):
-    """Deterministic weights from numpy PCG64: SIREN-like scale U(+-sqrt(6/fan_in)) for matrices
-    (U(+-1/fan_in) for fc_net.0 / sun_v_net.0), U(+-1/sqrt(fan_in)) for biases."""
+    """Deterministic weights from numpy PCG64 with the scales load_model() produces: U(+-sqrt(6/fan_in)) for the
+    sine_init layers (fc_net, sun_v_net; U(+-1/fan_in) for their first layers), nn.Linear's default
+    U(+-1/sqrt(fan_in)) for every other weight and for all biases."""
     rng = np.random.Generator(np.random.PCG64(seed))
     out = {}
     fan = {}
@@ -70,7 +71,8 @@ def pcg_params(shapes, seed):
         u = rng.random(int(np.prod(shape)), dtype=np.float32).reshape(shape) * 2 - 1
         if name.endswith(".weight"):
             fan[name[:-7]] = shape[1]
-            bound = 1.0 / shape[1] if name in ("fc_net.0.weight", "sun_v_net.0.weight") else np.sqrt(6.0 / shape[1])
+            siren = name.startswith(("fc_net.", "sun_v_net."))      # sine_init layers (satnerf.py:145-149); others keep nn.Linear's default scale
+            bound = 1.0 / shape[1] if name in ("fc_net.0.weight", "sun_v_net.0.weight") else (np.sqrt(6.0 / shape[1]) if siren else 1.0 / np.sqrt(shape[1]))
         else:
             bound = 1.0 / np.sqrt(fan[name[:-5]])
         out[name] = (u * np.float32(bound)).astype(np.float32)

@@ -20,7 +20,8 @@ def pcg_params(shapes, seed):
         u = rng.random(int(np.prod(shape)), dtype=np.float32).reshape(shape) * 2 - 1
         if name.endswith(".weight"):
             fan[name[:-7]] = shape[1]
-            bound = 1.0 / shape[1] if name in ("fc_net.0.weight", "sun_v_net.0.weight") else np.sqrt(6.0 / shape[1])
+            siren = name.startswith(("fc_net.", "sun_v_net."))      # sine_init layers (satnerf.py:145-149); others keep nn.Linear's default scale
+            bound = 1.0 / shape[1] if name in ("fc_net.0.weight", "sun_v_net.0.weight") else (np.sqrt(6.0 / shape[1]) if siren else 1.0 / np.sqrt(shape[1]))
         else:
             bound = 1.0 / np.sqrt(fan[name[:-5]])
         out[name] = (u * np.float32(bound)).astype(np.float32)

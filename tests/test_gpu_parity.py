@@ -55,21 +55,42 @@ def _loss(g, res, dev):
     return orc.loss_depth(res, g.depth_target.to(dev), g.depth_weights.to(dev), lam_ds=1000.0)[0]
 
 
+def _grads_fp64(g):
+    """Gradients of the oracle in float64 on the CPU: the yardstick both fp32 implementations are measured against."""
+    P = {lvl: ({k: v.double().requires_grad_(True) for k, v in p.items()} if lvl != "t" else p.double().requires_grad_(True))
+         for lvl, p in g.params.items()}
+    res = orc.render_rays(P, g.cfg, g.rays.double(), g.ts, orc.Draws(g.draws, dtype=torch.float64))
+    tgt = g.target.double()
+    if g.loss_kind == "satnerf":
+        loss = orc.loss_satnerf(res, tgt, lam_sc=g.cfg.sc_lambda)[0]
+    elif g.loss_kind == "snerf":
+        loss = orc.loss_snerf(res, tgt, lam_sc=g.cfg.sc_lambda)[0]
+    else:
+        loss = orc.loss_depth(res, g.depth_target.double(), g.depth_weights.double(), lam_ds=1000.0)[0]
+    loss.backward()
+    return {key: (P["t"].grad if key == "t" else P[key.partition(".")[0]][key.partition(".")[2]].grad) for key in g.grads}
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
 @pytest.mark.parametrize("name", [c for c in CASES if "h64" in c])
 def test_gradients_match_golden(name, precision):
+    """Parameter gradients against the reference's own (golden, fp32 autograd) gradients.  Where the reference's
+    fp32 gradient is itself dominated by rounding (tiny, cancellation-heavy gradients of the nerf variant at
+    init) the bound is 3x the reference's own distance to the float64 gradient."""
     g = Golden(name)
     ms, _, res = run_golden(g, precision)
     loss = _loss(g, res, "cuda")
     assert abs(float(loss.detach()) - g.loss) <= TOL[precision] * 10 * max(1.0, abs(g.loss))
     loss.backward()
+    exact = _grads_fp64(g)
     checked = 0
     for key, ref in g.grads.items():
         lvl, _, pname = key.partition(".")
         got = ms["t"].weight.grad if key == "t" else dict(ms[lvl].named_parameters())[pname].grad
         assert got is not None, key
-        err = rel_err(got.cpu(), ref, floor=1e-9)
-        assert err < GRAD_TOL[precision], (key, err)
+        ref_noise = rel_err(ref, exact[key], floor=1e-12)
+        err = rel_err(got.cpu(), exact[key], floor=1e-12)
+        assert err < max(GRAD_TOL[precision], 3 * ref_noise), (key, err, ref_noise)
         checked += 1
     assert checked > 10
 
