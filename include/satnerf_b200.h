@@ -102,6 +102,8 @@ SNB_API int         snb_abi_version(void);
 SNB_API const char* snb_last_error(void);
 /* number of CUDA kernels this library has launched since the last reset (bench accounting) */
 SNB_API int64_t     snb_launch_count(int reset);
+/* developer aid: copies the fused kernel's phase timestamps (int64 clock64 values) to a HOST buffer */
+SNB_API int         snb_debug_read(void* host_dst, size_t bytes);
 /* 1 when the device of the current context can run the tcgen05 path (compute capability 10.x). */
 SNB_API int         snb_device_supports_tc(void);
 

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "snb_last_error": (C.c_char_p, []),
     "snb_device_supports_tc": (C.c_int, []),
     "snb_launch_count": (C.c_int64, [C.c_int]),
+    "snb_debug_read": (C.c_int, [C.c_void_p, C.c_size_t]),
     "snb_param_layout": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
     "snb_param_count": (C.c_int64, [C.POINTER(FieldDesc)]),
@@ -142,6 +143,14 @@ def param_count(desc: FieldDesc) -> int:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().snb_launch_count(int(reset)))
+
+
+def debug_timestamps():
+    """(64,4) int64 phase timestamps of the fused kernel's block 0 (developer aid)."""
+    import numpy as np
+    buf = np.zeros((64, 4), dtype=np.int64)
+    _check(lib().snb_debug_read(buf.ctypes.data_as(C.c_void_p), buf.nbytes), "snb_debug_read")
+    return buf
 
 
 def device_supports_tc() -> bool:

@@ -172,3 +172,6 @@ extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* p
     }
     return 0;
 }
+
+// Developer aid: phase timestamps recorded by the fused kernel (see tc_field.cu); host buffer of int64.
+extern "C" SNB_API int snb_debug_read(void* host_dst, size_t bytes) { return tc_debug_read(host_dst, bytes); }

@@ -7,7 +7,7 @@
 //               shared-memory ring with 1-D bulk async copies (TMA engine) + mbarrier transactions
 //   warp 1      MMA issuer: tcgen05.mma (M=128 points, N<=256 features, K=16) with the activation tile
 //               as the K-major A operand in shared memory, accumulators in TMEM (all 512 columns)
-//   warps 2-5   epilogue: sample positions and the K=3 first layer in fp32 on CUDA cores, then per
+//   warps 2-17  epilogue: sample positions and the K=3 first layer in fp32 on CUDA cores, then per
 //               layer TMEM -> registers, bias (+ fp32 skip / per-ray terms), sin, fp16 pack into the
 //               swizzled A tile of the next layer; the tiny output heads (sigma, rgb, sun, beta) are
 //               dot products folded into the epilogue of the layer that feeds them; finally a
@@ -17,6 +17,7 @@
 // per-ray sun / embedding terms, heads and compositing in fp32 (SURVEY.md §7 "Precision").
 #include "tc_field.cuh"
 #include "sm100_ptx.cuh"
+#include <cstdlib>
 
 namespace snb {
 
@@ -28,7 +29,10 @@ constexpr int kMaxGroupRays = 4;
 constexpr int kMaxGroupPts = 384;
 constexpr int kSlabBytes = kTile * 128;      // one 64-wide K slab of the A tile
 constexpr int kTblF = 8192, kTblV = 2048;    // epilogue table region: [N][4] or [N] floats + extra vector
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;                 // 4 warps per TMEM lane quadrant
+constexpr int kEpiSub = kEpiWarps / 4;         // column-block interleave factor within a quadrant
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 
 enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3 };
 enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
@@ -55,6 +59,8 @@ struct TcArgs {
     float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma;
     unsigned char* packed;
     int R, S, ray_cols, dir_col, G, n_groups;
+    int dbg;      // developer knobs (env SNB_TC_DBG): 1 = skip sin, 2 = skip TMEM loads, 4 = skip activation stores,
+                  // 8 = skip MMA issue, 16 = skip weight copies
 };
 
 // --------------------------------------------------------------------------------------------------
@@ -117,7 +123,7 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
 }
 
 static size_t smem_fixed_bytes() {
-    return kTblF + kTblV + 8 * kMaxGroupPts * 4 /*raw SoA incl. z, w, T*/ + 2 * kMaxGroupRays * 256 * 4 + 512;
+    return kTblF + kTblV + 8 * kMaxGroupPts * 4 /*raw SoA incl. z, w, T*/ + 2 * kMaxGroupRays * 256 * 4 + 768;
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -212,6 +218,11 @@ __global__ void tc_pack_misc_kernel(TcProgram P, MiscOffsets M, const float* __r
 // --------------------------------------------------------------------------------------------------
 // the fused kernel
 // --------------------------------------------------------------------------------------------------
+// Phase timestamps (clock64) of block 0's second tile, read back through snb_debug_read: per GEMM
+// [wait-for-accumulator start, accumulator ready, epilogue done]; slot 60.. = layer-0 / compositing marks.
+__device__ long long g_tc_dbg[64 * 4];
+#define TC_MARK(slot, k) do { if (dbg_on && tid_e == 0) g_tc_dbg[(slot) * 4 + (k)] = clock64(); } while (0)
+
 struct Smem {
     unsigned char* a;        // activation tile: a_slabs x [128 rows x 128 B], 128B-swizzled, K-major
     unsigned char* b;        // weight ring: n_stages x stage_bytes
@@ -222,14 +233,14 @@ struct Smem {
     float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
     float* skyc;             // [kMaxGroupRays][4]
     float* consts;           // 8 floats
-    uint64_t *full, *empty, *acc_full, *a_ready;
+    uint64_t *full, *empty, *peer_full, *acc_full, *a_ready;
     uint32_t* tmem_ptr;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P) {
+__device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, int cg) {
     Smem s; unsigned char* p = base;
     s.a = p; p += (size_t)P.a_slabs * kSlabBytes;
-    s.b = p; p += (size_t)P.n_stages * P.stage_bytes;
+    s.b = p; p += (size_t)P.n_stages * (P.stage_bytes / cg);
     s.tblF = (float*)p; p += kTblF;
     s.tblV = (float*)p; p += kTblV;
     float* f = (float*)p;
@@ -242,6 +253,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P) {
     s.consts = (float*)p; p += 32;
     s.full = (uint64_t*)p; p += 8 * 8;
     s.empty = (uint64_t*)p; p += 8 * 8;
+    s.peer_full = (uint64_t*)p; p += 8 * 8;
     s.acc_full = (uint64_t*)p; p += 8;
     s.a_ready = (uint64_t*)p; p += 8;
     s.tmem_ptr = (uint32_t*)p;
@@ -270,104 +282,241 @@ __device__ __forceinline__ void store_act32(uint32_t a_base, int row, int k0, co
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// cooperative copy (128 epilogue threads) of `bytes` (multiple of 16) from global to shared with cp.async
+// cooperative copy (all epilogue threads) of `bytes` (multiple of 16) from global to shared with cp.async
 __device__ __forceinline__ void table_copy(void* dst, const void* src, int bytes, int tid_e) {
-    for (int o = tid_e * 16; o < bytes; o += 128 * 16) cp_async16((char*)dst + o, (const char*)src + o);
+    for (int o = tid_e * 16; o < bytes; o += kEpiThreads * 16) cp_async16((char*)dst + o, (const char*)src + o);
 }
 
+
+// Shared-memory table read that the compiler may schedule freely (no "memory" clobber, so reads of a block
+// pipeline instead of paying the LDS latency one by one).  `tok` is a value produced by fresh_token() AFTER the
+// barrier that published the table: the data dependence keeps the read below that barrier and keeps reads of
+// different table generations (same address, next layer) from being merged.
+__device__ __forceinline__ float4 lds128(uint32_t addr, uint32_t tok) {
+    float4 r;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+0];  // gen %5" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr), "r"(tok));
+    return r;
+}
+__device__ __forceinline__ uint32_t fresh_token(uint32_t x) {
+    uint32_t t;
+    asm volatile("mov.u32 %0, %1;" : "=r"(t) : "r"(x) : "memory");
+    return t;
+}
+
+// Epilogue of one 32-column block of one row: v = fp32 accumulators of columns n0..n0+31.
+// Tables live in shared memory (32-bit addresses): tF = [N] floats (F1) or [N][4] (F4), tV = [N] extra vector.
+#define SIN_(x) ((dbg & 1) ? (x) : __sinf(x))
+__device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool skip, bool last, int has_beta, int n0, int H2, float* v,
+                                          uint32_t a_base, int row, uint32_t tF, uint32_t tV, uint32_t sunb_row, uint32_t betab_row,
+                                          float px, float py, float pz,
+                                          float& sig_dot, float& beta_dot, float& rgb0, float& rgb1, float& rgb2, float& sun_dot) {
+    if (kind == GK_TRUNK) {
+        if (skip) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
+                v[i] = SIN_(v[i] + fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x))));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+                v[i] = SIN_(v[i] + b.x); v[i + 1] = SIN_(v[i + 1] + b.y); v[i + 2] = SIN_(v[i + 2] + b.z); v[i + 3] = SIN_(v[i + 3] + b.w);
+            }
+        }
+        if (last) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float4 w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
+                sig_dot = fmaf(w.x, v[i], sig_dot); sig_dot = fmaf(w.y, v[i + 1], sig_dot);
+                sig_dot = fmaf(w.z, v[i + 2], sig_dot); sig_dot = fmaf(w.w, v[i + 3], sig_dot);
+            }
+        }
+        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
+    } else if (kind == GK_FEAT) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
+    } else if (kind == GK_HEADA) {
+        if (has_beta && n0 < H2) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float4 b = lds128(betab_row + (uint32_t)(n0 + i) * 4u, tok);
+                float a0 = SIN_(v[i] + b.x), a1 = SIN_(v[i + 1] + b.y), a2 = SIN_(v[i + 2] + b.z), a3 = SIN_(v[i + 3] + b.w);
+                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i) * 16u, tok).y, a0, beta_dot);
+                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i + 1) * 16u, tok).y, a1, beta_dot);
+                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i + 2) * 16u, tok).y, a2, beta_dot);
+                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i + 3) * 16u, tok).y, a3, beta_dot);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
+                float a = SIN_(v[i] + w.x);
+                rgb0 = fmaf(w.y, a, rgb0); rgb1 = fmaf(w.z, a, rgb1); rgb2 = fmaf(w.w, a, rgb2);
+            }
+        }
+    } else if (kind == GK_SUN1) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 b = lds128(sunb_row + (uint32_t)(n0 + i) * 4u, tok);
+            v[i] = SIN_(v[i] + b.x); v[i + 1] = SIN_(v[i + 1] + b.y); v[i + 2] = SIN_(v[i + 2] + b.z); v[i + 3] = SIN_(v[i + 3] + b.w);
+        }
+        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
+    } else if (kind == GK_SUN2) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+            v[i] = SIN_(v[i] + b.x); v[i + 1] = SIN_(v[i + 1] + b.y); v[i + 2] = SIN_(v[i + 2] + b.z); v[i + 3] = SIN_(v[i + 3] + b.w);
+        }
+        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
+    } else {   // GK_SUN3
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok), w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
+            sun_dot = fmaf(w.x, SIN_(v[i] + b.x), sun_dot); sun_dot = fmaf(w.y, SIN_(v[i + 1] + b.y), sun_dot);
+            sun_dot = fmaf(w.z, SIN_(v[i + 2] + b.z), sun_dot); sun_dot = fmaf(w.w, SIN_(v[i + 3] + b.w), sun_dot);
+        }
+    }
+}
+
+#undef SIN_
+// CG = 1: one CTA per 128-point tile.  CG = 2: CTA pair (cta_group::2): two SMs run two tiles in lockstep, the
+// leader issues M=256 MMAs that read each CTA's own activation tile and HALF of every weight tile from each
+// CTA's shared memory, so each SM streams / buffers only half of the weights.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcProgram& P = A.prog;
-    Smem sm = carve(base, P);
+    Smem sm = carve(base, P, CG);
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // work unit index (cluster or CTA)
+    const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int stage_bytes = P.stage_bytes / CG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* T = reinterpret_cast<const float*>(A.packed + P.tables_base);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, 128);
+        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); mbar_init(&sm.peer_full[i], 1); }
+        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, CG);     // one elected arrival per CTA of the pair
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(sm.tmem_ptr, 512);
+    if (CG == 2) { __syncthreads(); cluster_sync_all(); }       // both CTAs of the pair are running and their barriers are initialised
+    if (warp == 1) { if (CG == 2) tmem_alloc_2cta(sm.tmem_ptr, 512); else tmem_alloc(sm.tmem_ptr, 512); }
     if (threadIdx.x >= 64 && threadIdx.x < 72) sm.consts[threadIdx.x - 64] = T[P.consts + threadIdx.x - 64];
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();          // peer barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_ptr;
+    // Work: groups of G rays.  CG = 2: the pair takes groups (2q, 2q+1); a missing / short group runs as masked rows.
+    const int tiles_per_group = (A.G * A.S + kTile - 1) / kTile;
+    const int n_work = CG == 2 ? (A.n_groups + 1) / 2 : A.n_groups;
 
     if (warp == 0) {
         // ================= weight producer (lane 0 issues; the warp stays converged) =================
         int st = 0; uint32_t ph = 0;
-        for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
-            const int n_tiles = (group_points(A, grp) + kTile - 1) / kTile;
-            for (int t = 0; t < n_tiles; ++t) {
+        for (int wk = unit; wk < n_work; wk += n_units) {
+            for (int t = 0; t < tiles_per_group; ++t) {
                 const unsigned char* src = A.packed;
                 for (int gi = 0; gi < P.n_gemms; ++gi) {
-                    const uint32_t bytes = (uint32_t)P.g[gi].chunk_n * 128u;
+                    const uint32_t tile_bytes = (uint32_t)P.g[gi].chunk_n * 128u, bytes = tile_bytes / CG;
                     const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
                     for (int i = 0; i < n; ++i) {
                         if (lane == 0) {
                             mbar_wait(&sm.empty[st], ph ^ 1, 1);
-                            mbar_arrive_expect_tx(&sm.full[st], bytes);
-                            bulk_g2s(sm.b + (size_t)st * P.stage_bytes, src, bytes, &sm.full[st]);
+                            if (A.dbg & 16) mbar_arrive(&sm.full[st]);        // knob: no copy (tensor pipe alone)
+                            else {
+                                mbar_arrive_expect_tx(&sm.full[st], bytes);
+                                bulk_g2s(sm.b + (size_t)st * stage_bytes, src + cta_rank * bytes, bytes, &sm.full[st]);   // this CTA's rows of the tile
+                            }
                         }
                         __syncwarp();
-                        src += bytes;
+                        src += tile_bytes;
                         if (++st == P.n_stages) { st = 0; ph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
+        // ================= MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =================
         int st = 0; uint32_t ph = 0, ready_ph = 0;
         const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
-        for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
-            const int n_tiles = (group_points(A, grp) + kTile - 1) / kTile;
-            for (int t = 0; t < n_tiles; ++t) {
-                for (int gi = 0; gi < P.n_gemms; ++gi) {
-                    const TcGemm& g = P.g[gi];
-                    mbar_wait(sm.a_ready, ready_ph, 2); ready_ph ^= 1;
-                    tc_fence_after();
-                    const uint32_t idesc = umma_idesc_f16((uint32_t)g.chunk_n);
-                    for (int j = 0; j < g.n_chunks; ++j) {
-                        for (int s = 0; s < g.k_slabs; ++s) {
-                            mbar_wait(&sm.full[st], ph, 3);
-                            tc_fence_after();
-                            if (lane == 0) {
-                                int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
-                                const uint32_t a_addr = a_base + (uint32_t)s * kSlabBytes;
-                                const uint32_t b_addr = b_base + (uint32_t)st * P.stage_bytes;
-                                for (int k = 0; k < ksteps; ++k)
-                                    umma_f16_ss(tmem + (uint32_t)(j * g.chunk_n), umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
-                                                idesc, (s | k) != 0);
-                                umma_commit(&sm.empty[st]);
-                                if (j == g.n_chunks - 1 && s == g.k_slabs - 1) umma_commit(sm.acc_full);
-                            }
+        if (CG == 2 && cta_rank == 1) {
+            // the leader's MMA reads this CTA's half of every weight tile: tell it when each stage has landed
+            for (int wk = unit; wk < n_work; wk += n_units)
+                for (int t = 0; t < tiles_per_group; ++t)
+                    for (int gi = 0; gi < P.n_gemms; ++gi) {
+                        const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
+                        for (int i = 0; i < n; ++i) {
+                            mbar_wait(&sm.full[st], ph, 5);
+                            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.peer_full[st]), 0));
                             __syncwarp();
                             if (++st == P.n_stages) { st = 0; ph ^= 1; }
+                        }
+                    }
+        } else {
+            for (int wk = unit; wk < n_work; wk += n_units) {
+                for (int t = 0; t < tiles_per_group; ++t) {
+                    for (int gi = 0; gi < P.n_gemms; ++gi) {
+                        const TcGemm& g = P.g[gi];
+                        mbar_wait(sm.a_ready, ready_ph, 2); ready_ph ^= 1;
+                        tc_fence_after();
+                        const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)g.chunk_n) : umma_idesc_f16((uint32_t)g.chunk_n);
+                        for (int j = 0; j < g.n_chunks; ++j) {
+                            for (int s = 0; s < g.k_slabs; ++s) {
+                                mbar_wait(&sm.full[st], ph, 3);
+                                if (CG == 2) mbar_wait(&sm.peer_full[st], ph, 6);
+                                tc_fence_after();
+                                if (lane == 0) {
+                                    int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
+                                    const uint32_t a_addr = a_base + (uint32_t)s * kSlabBytes;
+                                    const uint32_t b_addr = b_base + (uint32_t)st * stage_bytes;
+                                    const bool last = j == g.n_chunks - 1 && s == g.k_slabs - 1;
+                                    if (A.dbg & 8) ksteps = 0;              // knob: no MMA (load pipeline alone)
+                                    for (int k = 0; k < ksteps; ++k) {
+                                        const uint64_t da = umma_desc_k_sw128(a_addr + k * 32), db = umma_desc_k_sw128(b_addr + k * 32);
+                                        if (CG == 2) umma_f16_ss_2cta(tmem + (uint32_t)(j * g.chunk_n), da, db, idesc, (s | k) != 0);
+                                        else umma_f16_ss(tmem + (uint32_t)(j * g.chunk_n), da, db, idesc, (s | k) != 0);
+                                    }
+                                    if (CG == 2) { umma_commit_2cta(&sm.empty[st], 3); if (last) umma_commit_2cta(sm.acc_full, 3); }
+                                    else { umma_commit(&sm.empty[st]); if (last) umma_commit(sm.acc_full); }
+                                }
+                                __syncwarp();
+                                if (++st == P.n_stages) { st = 0; ph ^= 1; }
+                            }
                         }
                     }
                 }
             }
         }
     } else {
-        // ================= epilogue warps (128 threads) =================
+        // ================= epilogue warps (kEpiWarps warps; kEpiSub threads per point) =================
+        // Warp w may touch TMEM lanes [32*(w%4), +32).  The kEpiSub warps of a quadrant interleave the 32-column
+        // blocks of every layer; several warps per scheduler let MUFU work of one overlap pack/store work of another.
         const int tid_e = threadIdx.x - 64;
-        const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int quad = warp & 3, half = (warp - 2) >> 2;      // half = sub-warp index 0..kEpiSub-1 within the quadrant
         const int row = quad * 32 + lane;                // point (row of the tile) owned by this thread
         const uint32_t a_base = smem_u32(sm.a);
         const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
+        const uint32_t tF = smem_u32(sm.tblF), tV = smem_u32(sm.tblV);
         const int H = P.H, H2 = P.H2, S = A.S;
         uint32_t acc_ph = 0;
         const int aux_col = 8;
-        for (int grp = blockIdx.x; grp < A.n_groups; grp += gridDim.x) {
+        int tile_counter = 0;
+        const uint32_t ready_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready), 0) : 0u;     // the leader's a_ready barrier
+        for (int wk = unit; wk < n_work; wk += n_units) {
+            const int grp = CG == 2 ? 2 * wk + (int)cta_rank : wk;
             const int r0 = grp * A.G;
-            const int n_rays = min(A.G, A.R - r0);
+            const int n_rays = grp < A.n_groups ? min(A.G, A.R - r0) : 0;        // 0: this CTA only keeps the pair in lockstep
             const int Pg = n_rays * S;
-            const int n_tiles = (Pg + kTile - 1) / kTile;
+            const int n_tiles = tiles_per_group;
             // ---- per-ray tables: sun / embedding terms of the first head layers, sky colour ----
-            for (int idx = tid_e; idx < n_rays * H2; idx += 128) {
+            for (int idx = tid_e; idx < n_rays * H2; idx += kEpiThreads) {
                 int gr = idx / H2, n = idx - gr * H2;
                 const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
                 float v = T[P.sunw + 3 * H2 + n];
@@ -380,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     sm.betab[gr * H2 + n] = b;
                 }
             }
-            for (int gr = warp - 2; gr < n_rays; gr += 4) {          // sky_color(sun_d): per ray (satnerf.py:201)
+            for (int gr = warp - 2; gr < n_rays; gr += kEpiWarps) {          // sky_color(sun_d): per ray (satnerf.py:201)
                 const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
                 for (int n = lane; n < H2; n += 32) {
@@ -395,15 +544,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 }
             }
             for (int t = 0; t < n_tiles; ++t) {
+                const bool dbg_on = blockIdx.x == 0 && (tile_counter++ == 1);
+                TC_MARK(60, 0);
                 // ---- sample position of this thread's point ----
                 const int p = t * kTile + row;
                 const bool valid = p < Pg;
-                int rl = valid ? p / S : 0;                       // ray within the group
+                const int rl = valid ? p / S : 0;                 // ray within the group
                 float px = 0.f, py = 0.f, pz = 0.f;
                 if (valid) {
                     const size_t gp = (size_t)r0 * S + p;
                     float zz = A.z[gp];
-                    sm.z[p] = zz;
+                    if (half == 0) sm.z[p] = zz;
                     if (A.xyz) { px = A.xyz[gp * 3]; py = A.xyz[gp * 3 + 1]; pz = A.xyz[gp * 3 + 2]; }
                     else {
                         const float* ray = A.rays + (size_t)(r0 + rl) * A.ray_cols;       // rendering.py:81 / :104
@@ -412,100 +563,73 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         pz = __fadd_rn(ray[2], __fmul_rn(ray[A.dir_col + 2], zz));
                     }
                 }
+                const uint32_t sunb_row = smem_u32(sm.sunb) + (uint32_t)(rl * H2) * 4u;
+                const uint32_t betab_row = smem_u32(sm.betab) + (uint32_t)(rl * H2) * 4u;
                 // ---- trunk layer 0 on CUDA cores: sin(30 (W0 x + b0)), K = 3 (satnerf.py:105-106) ----
                 table_copy(sm.tblF, T + P.l0_tbl, H * 16, tid_e);
                 cp_async_wait_all();
-                named_bar_sync(1, 128);
-                for (int n0 = 0; n0 < H; n0 += 32) {
+                named_bar_sync(1, kEpiThreads);
+                const uint32_t tok0 = fresh_token(0xffffu);
+                for (int n0 = half * 32; n0 < H; n0 += 32 * kEpiSub) {
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        float4 w = reinterpret_cast<const float4*>(sm.tblF)[n0 + i];
+                        float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok0);
                         float y = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
                         v[i] = __sinf(__fmul_rn(30.0f, y));
                     }
                     store_act32(a_base, row, n0, v);
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);                          // everyone is done with the layer-0 table
+                named_bar_sync(1, kEpiThreads);                  // everyone is done with the layer-0 table
                 {   const TcGemm& g0 = P.g[0];
                     if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
                     if (g0.has_vec) table_copy(sm.tblV, T + g0.vec_off, g0.N * 4, tid_e); }
-                mbar_arrive(sm.a_ready);
+                if (tid_e == 0) { if (CG == 2) mbar_arrive_cluster(ready_bar); else mbar_arrive(sm.a_ready); }
+                TC_MARK(60, 1);
 
                 float sig_dot = 0.f, beta_dot = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f, sun_dot = 0.f;
                 for (int gi = 0; gi < P.n_gemms; ++gi) {
                     const TcGemm& g = P.g[gi];
                     cp_async_wait_all();
-                    named_bar_sync(1, 128);                      // tables of this GEMM are in shared memory
+                    named_bar_sync(1, kEpiThreads);              // tables of this GEMM are in shared memory
+                    TC_MARK(gi, 0);
                     mbar_wait(sm.acc_full, acc_ph, 4); acc_ph ^= 1;
                     tc_fence_after();
-                    const float4* T4 = reinterpret_cast<const float4*>(sm.tblF);
-                    for (int n0 = 0; n0 < g.N; n0 += 32) {
-                        float v[32];
-                        tmem_ld32(tm_row + (uint32_t)n0, v);
-                        tmem_ld_wait();
-                        switch (g.kind) {
-                            case GK_TRUNK:
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    float y;
-                                    if (g.skip) { float4 w = T4[n0 + i]; y = v[i] + fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x))); }
-                                    else y = v[i] + sm.tblF[n0 + i];
-                                    v[i] = __sinf(y);
-                                    if (g.last) sig_dot = fmaf(sm.tblV[n0 + i], v[i], sig_dot);
-                                }
-                                store_act32(a_base, row, n0, v);
-                                break;
-                            case GK_FEAT:
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] += sm.tblF[n0 + i];
-                                store_act32(a_base, row, n0, v);
-                                break;
-                            case GK_HEADA:
-                                if (P.has_beta && n0 < H2) {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
-                                        float a = __sinf(v[i] + sm.betab[rl * H2 + n0 + i]);
-                                        beta_dot = fmaf(T4[n0 + i].y, a, beta_dot);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
-                                        float4 w = T4[n0 + i];
-                                        float a = __sinf(v[i] + w.x);
-                                        rgb0 = fmaf(w.y, a, rgb0); rgb1 = fmaf(w.z, a, rgb1); rgb2 = fmaf(w.w, a, rgb2);
-                                    }
-                                }
-                                break;
-                            case GK_SUN1:
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i] + sm.sunb[rl * H2 + n0 + i]);
-                                store_act32(a_base, row, n0, v);
-                                break;
-                            case GK_SUN2:
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i] + sm.tblF[n0 + i]);
-                                store_act32(a_base, row, n0, v);
-                                break;
-                            default:   // GK_SUN3
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) sun_dot = fmaf(sm.tblV[n0 + i], __sinf(v[i] + sm.tblF[n0 + i]), sun_dot);
-                                break;
-                        }
+                    const uint32_t tok = fresh_token((uint32_t)gi);
+                    TC_MARK(gi, 1);
+                    // this warp's 32-column blocks: n0 = 32*half, + 32*kEpiSub, ...
+                    const int kind = g.kind, N = g.N;
+                    const bool skip = g.skip != 0, last = g.last != 0;
+                    for (int n0 = half * 32; n0 < N; n0 += 32 * kEpiSub) {
+                        float va[32];
+                        if (!(A.dbg & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
+                        else { for (int i = 0; i < 32; ++i) va[i] = 0.01f * i; }
+                        epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz,
+                                  sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
                     }
                     tc_fence_before();
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);                      // all TMEM reads / A writes / table reads of this GEMM done
+                    named_bar_sync(1, kEpiThreads);              // all TMEM reads / A writes / table reads of this GEMM done
+                    TC_MARK(gi, 2);
                     if (gi + 1 < P.n_gemms) {
                         const TcGemm& gn = P.g[gi + 1];
                         if (gn.fmt != TF_NONE) table_copy(sm.tblF, T + gn.tbl_off, gn.N * gn.fmt * 4, tid_e);
                         if (gn.has_vec) table_copy(sm.tblV, T + gn.vec_off, gn.N * 4, tid_e);
-                        mbar_arrive(sm.a_ready);
+                        if (tid_e == 0) { if (CG == 2) mbar_arrive_cluster(ready_bar); else mbar_arrive(sm.a_ready); }
                     }
                 }
-                // ---- head outputs of this point ----
-                if (valid) {
+                // ---- head outputs of this point: combine the partial dot products of the kEpiSub column interleaves.
+                //      The activation tile is dead here (every MMA that read it has completed), so it is the scratch. ----
+                float* dots = reinterpret_cast<float*>(sm.a) + (size_t)((half * kTile + row) * 8);
+                if (half != 0) { dots[0] = sig_dot; dots[1] = beta_dot; dots[2] = rgb0; dots[3] = rgb1; dots[4] = rgb2; dots[5] = sun_dot; }
+                named_bar_sync(1, kEpiThreads);
+                if (half == 0 && valid) {
+#pragma unroll
+                    for (int h2 = 1; h2 < kEpiSub; ++h2) {
+                        const float* d = reinterpret_cast<const float*>(sm.a) + (size_t)((h2 * kTile + row) * 8);
+                        sig_dot += d[0]; beta_dot += d[1]; rgb0 += d[2]; rgb1 += d[3]; rgb2 += d[4]; sun_dot += d[5];
+                    }
                     sm.sg[p] = softplus_f(sig_dot + sm.consts[0]);                                    // satnerf.py:183
                     sm.al0[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb0 + sm.consts[1]), 1.002f), 0.001f);  // :193-195
                     sm.al1[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb1 + sm.consts[2]), 1.002f), 0.001f);
@@ -513,10 +637,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     sm.sn[p] = sigmoid_f(sun_dot + sm.consts[4]);                                      // :200
                     sm.bt[p] = P.has_beta ? softplus_f(beta_dot + sm.consts[5]) : 0.f;                 // :205
                 }
+                named_bar_sync(1, kEpiThreads);                  // scratch reads done before the next tile's layer 0 overwrites A
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1, kEpiThreads);
+            { const bool dbg_on = blockIdx.x == 0 && tile_counter == 2; TC_MARK(61, 0); }
             // ---- alpha compositing: one warp per ray, transmittance by warp scan (satnerf.py:52-70) ----
-            for (int gr = warp - 2; gr < n_rays; gr += 4) {
+            for (int gr = warp - 2; gr < n_rays; gr += kEpiWarps) {
                 const int ray = r0 + gr;
                 float carry = 1.f, depth = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
                 const float k0 = sm.skyc[gr * 4], k1 = sm.skyc[gr * 4 + 1], k2 = sm.skyc[gr * 4 + 2];
@@ -563,12 +689,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     if (A.rgb) { A.rgb[ray * 3] = fminf(fmaxf(c0, 0.f), 1.f); A.rgb[ray * 3 + 1] = fminf(fmaxf(c1, 0.f), 1.f); A.rgb[ray * 3 + 2] = fminf(fmaxf(c2, 0.f), 1.f); }
                 }
             }
-            named_bar_sync(1, 128);                              // group tables are reused by the next group
+            named_bar_sync(1, kEpiThreads);                      // group tables are reused by the next group
+            { const bool dbg_on = blockIdx.x == 0 && tile_counter == 2; TC_MARK(61, 1); }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (CG == 2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory: leave together
+    if (warp == 1) { if (CG == 2) tmem_dealloc_2cta(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -609,11 +737,15 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     TcProgram& P = A.prog;
     size_t need = (size_t)P.tables_base + (size_t)nfl * 4;
     if (need > workspace_bytes) SNB_FAIL(-4, "tensor-core path: workspace too small (%zu < %zu)", workspace_bytes, need);
+    // CTA pairs (SNB_TC_CG=2) are functional but measured no faster: the tensor pipe, not the weight stream, bounds
+    // the MMA phase (profiles/r1_phase_probe.md), so the simpler single-CTA form is the default.
+    int cg = 1;
+    { const char* e = getenv("SNB_TC_CG"); if (e && atoi(e) == 2) cg = 2; }
     size_t fixed = (size_t)P.a_slabs * kSlabBytes + smem_fixed_bytes() + 1024;
-    int ns = (int)(((size_t)max_smem - fixed) / P.stage_bytes); if (ns > 8) ns = 8;
+    int ns = (int)(((size_t)max_smem - fixed) / (P.stage_bytes / cg)); if (ns > 8) ns = 8;
     if (ns < 2) SNB_FAIL(-6, "tensor-core path: not enough shared memory for the weight ring");
     P.n_stages = ns;
-    size_t smem = fixed + (size_t)ns * P.stage_bytes;
+    size_t smem = fixed + (size_t)ns * (P.stage_bytes / cg);
 
     A.params = io->params; A.rays = io->rays; A.z = io->z_vals; A.t_emb = io->t_emb; A.noise = p->noise_std != 0.f ? io->noise : nullptr;
     A.noise_std = p->noise_std; A.xyz = io->xyz; A.aux = io->aux_dir;
@@ -622,6 +754,7 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     A.packed = (unsigned char*)workspace;
     A.R = p->n_rays; A.S = p->n_samples; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
     A.G = choose_group(A.S); A.n_groups = (A.R + A.G - 1) / A.G;
+    { const char* e = getenv("SNB_TC_DBG"); A.dbg = e ? atoi(e) : 0; }
 
     MiscOffsets M; memset(&M, 0, sizeof(M));
     M.sigma_w = L.sigma.w; M.sigma_b = L.sigma.b; M.rgb0_b = L.rgb0.b; M.rgb2_w = L.rgb2.w; M.rgb2_b = L.rgb2.b;
@@ -633,10 +766,29 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     SNB_CHECK_LAUNCH();
     tc_pack_misc_kernel<<<8, 256, 0, st>>>(P, M, io->params, A.packed);
     SNB_CHECK_LAUNCH();
-    SNB_CUDA(cudaFuncSetAttribute(tc_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = A.n_groups < sm_count ? A.n_groups : sm_count;
-    tc_render_kernel<<<grid, kThreads, smem, st>>>(A);
-    SNB_CHECK_LAUNCH();
+    if (cg == 2) {
+        SNB_CUDA(cudaFuncSetAttribute(tc_render_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n_pairs = (A.n_groups + 1) / 2, max_pairs = sm_count / 2;
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SNB_CUDA(cudaLaunchKernelEx(&cfg, tc_render_kernel<2>, A));
+        ++g_launches;
+    } else {
+        SNB_CUDA(cudaFuncSetAttribute(tc_render_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = A.n_groups < sm_count ? A.n_groups : sm_count;
+        tc_render_kernel<1><<<grid, kThreads, smem, st>>>(A);
+        SNB_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int tc_debug_read(void* dst, size_t bytes) {
+    if (bytes > sizeof(long long) * 64 * 4) bytes = sizeof(long long) * 64 * 4;
+    SNB_CUDA(cudaMemcpyFromSymbol(dst, g_tc_dbg, bytes));
     return 0;
 }
 

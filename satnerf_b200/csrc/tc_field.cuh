@@ -12,4 +12,6 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
 int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_render_io* io,
                        const snb_render_grads* g, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+int tc_debug_read(void* dst, size_t bytes);
+
 }  // namespace snb
