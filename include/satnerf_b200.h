@@ -87,6 +87,8 @@ typedef struct snb_render_io {
     float* beta;                /* (R,S,1)  sat-nerf only                                       */
     float* sigma;               /* (R,S) densities; stash needed by snb_render_backward         */
     float* nerf_rgb;            /* (R,S,3) per-sample colour of the nerf variant (stash)        */
+    void*  stash;               /* training only: activation stash of snb_render_stash_bytes() bytes written by the
+                                   tensor-core forward and consumed by its backward; NULL = inference / fp32 path  */
 } snb_render_io;
 
 typedef struct snb_render_grads {
@@ -104,6 +106,10 @@ SNB_API const char* snb_last_error(void);
 SNB_API int64_t     snb_launch_count(int reset);
 /* developer aid: copies the fused kernel's phase timestamps (int64 clock64 values) to a HOST buffer */
 SNB_API int         snb_debug_read(void* host_dst, size_t bytes);
+/* developer / test entry: out (Fa x Fb) = Xa^T Xb through the point-atom packing and the tensor-core
+ * weight-gradient kernel (csrc/tc_backward.cu); Xa (P x Fa), Xb (P x Fb) fp32 row-major, Fa % 128 == 0, Fb % 64 == 0 */
+SNB_API int         snb_debug_dw_gemm(const float* xa, const float* xb, int P, int Fa, int Fb, int k_splits, float* out,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 /* 1 when the device of the current context can run the tcgen05 path (compute capability 10.x). */
 SNB_API int         snb_device_supports_tc(void);
 
@@ -133,6 +139,10 @@ SNB_API int snb_searchsorted_right(const float* cdf, const float* u, int64_t* in
 
 /* Workspace (bytes) needed by forward / backward of a pass. */
 SNB_API int snb_render_workspace(const snb_field_desc* f, const snb_pass_desc* p, int backward, size_t* bytes);
+
+/* Bytes of the activation stash the tensor-core forward fills for its backward (0 when the pass runs on the
+ * fp32 path, which recomputes instead). */
+SNB_API int snb_render_stash_bytes(const snb_field_desc* f, const snb_pass_desc* p, size_t* bytes);
 
 /* inference(): field at every sample + alpha compositing (satnerf.py:4-79, snerf.py:4-75, nerf.py:71-133) */
 SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,

@@ -32,7 +32,7 @@ class PassDesc(C.Structure):
 
 
 _IO_FIELDS = ["params", "rays", "z_vals", "t_emb", "noise", "xyz", "aux_dir", "rgb", "depth", "weights", "transparency",
-              "albedo", "sun", "sky", "beta", "sigma", "nerf_rgb"]
+              "albedo", "sun", "sky", "beta", "sigma", "nerf_rgb", "stash"]
 _GRAD_FIELDS = ["g_rgb", "g_depth", "g_weights", "g_transparency", "g_albedo", "g_sun", "g_sky", "g_beta",
                 "g_params", "g_t_emb"]
 
@@ -51,6 +51,7 @@ _SIGNATURES = {
     "snb_device_supports_tc": (C.c_int, []),
     "snb_launch_count": (C.c_int64, [C.c_int]),
     "snb_debug_read": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "snb_debug_dw_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_param_layout": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
     "snb_param_count": (C.c_int64, [C.POINTER(FieldDesc)]),
@@ -59,6 +60,7 @@ _SIGNATURES = {
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "snb_searchsorted_right": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "snb_render_workspace": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.c_int, C.POINTER(C.c_size_t)]),
+    "snb_render_stash_bytes": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.POINTER(C.c_size_t)]),
     "snb_render_forward": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.POINTER(RenderIO), C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_render_backward": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(RenderGrads),
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -153,6 +155,20 @@ def debug_timestamps():
     return buf
 
 
+def debug_dw_gemm(xa, xb, k_splits=1):
+    """out = xa^T xb on the tensor-core weight-gradient kernel (developer / test entry)."""
+    P, Fa = xa.shape
+    Fb = xb.shape[1]
+    out = torch.empty(Fa, Fb, device=xa.device, dtype=torch.float32)
+    tiles = (P + 127) // 128
+    nbytes = tiles * (Fa // 64 + Fb // 64) * 16384 + (Fa // 128) * ((Fb // 64 + 3) // 4) * k_splits * (128 * 256 * 4 + 64) + (1 << 16)
+    ws = _workspace(xa.device, nbytes)
+    with torch.cuda.device(xa.device):
+        _check(lib().snb_debug_dw_gemm(_ptr(xa), _ptr(xb), P, Fa, Fb, k_splits, _ptr(out), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                       _stream(xa.device)), "snb_debug_dw_gemm")
+    return out
+
+
 def device_supports_tc() -> bool:
     return bool(lib().snb_device_supports_tc())
 
@@ -200,9 +216,16 @@ def searchsorted_right(cdf, u):
     return inds
 
 
+def render_stash_bytes(desc: FieldDesc, pd: PassDesc) -> int:
+    n = C.c_size_t(0)
+    _check(lib().snb_render_stash_bytes(C.byref(desc), C.byref(pd), C.byref(n)), "snb_render_stash_bytes")
+    return int(n.value)
+
+
 def _fill(struct, names, tensors: Dict[str, Optional[torch.Tensor]]):
     for n in names:
-        setattr(struct, n, _ptr(tensors.get(n)))
+        t = tensors.get(n)
+        setattr(struct, n, _ptr(t, torch.uint8) if n == "stash" else _ptr(t))
     return struct
 
 

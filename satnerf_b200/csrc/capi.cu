@@ -67,6 +67,14 @@ extern "C" SNB_API int snb_render_workspace(const snb_field_desc* f, const snb_p
     return 0;
 }
 
+extern "C" SNB_API int snb_render_stash_bytes(const snb_field_desc* f, const snb_pass_desc* p, size_t* bytes) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L)); SNB_TRY(check_pass(L, p));
+    if (!bytes) SNB_FAIL(-1, "null output pointer");
+    *bytes = 0;
+    if (p->precision != SNB_FP16_TC) return 0;
+    return tc_stash_bytes(L, p, bytes);
+}
+
 extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
                                   void* workspace, size_t workspace_bytes, void* stream) {
     FieldLayout L; SNB_TRY(build_layout(f, &L)); SNB_TRY(check_pass(L, p));

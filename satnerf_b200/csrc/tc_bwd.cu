@@ -1,0 +1,681 @@
+// Tensor-core backward of the render pass (SNB_FP16_TC, sat-nerf / s-nerf):
+//
+//   1. composite_bwd (composite.cu)      d_head (P x C, fp32): gradient w.r.t. the pre-activation head outputs
+//   2. tc_bwd_kernel (this file)         fused INPUT-gradient chain per 128-point tile, same warp-specialised tile machinery
+//                                        as the forward: A operand = dY tile in shared memory, transposed weight tiles
+//                                        streamed by the producer warp, accumulators in TMEM, epilogue multiplies by
+//                                        cos(y) (y from the forward's stash) and writes the next dY tile; every dY tile is
+//                                        also dumped (bulk S2G) in the point-atom layout for step 3
+//   3. tc_dw_kernel (tc_backward.cu)     WEIGHT gradients dW = dY^T [a | x sun t 1] as split-K GEMMs over the points
+//   4. finalize kernels (this file)      ordered reduction of the split-K partials, un-scaling, scatter-add into the flat
+//                                        gradient buffer; tiny head biases, sky-colour MLP and embedding gradients
+//
+// Gradients travel in fp16 with one global power-of-two loss scale (taken from max |d_head|) and are accumulated in fp32.
+// Everything is deterministic: no float atomics, fixed reduction orders.
+#include "tc_common.cuh"
+#include "tc_backward.cuh"
+#include "tc_field.cuh"
+#include "composite.cuh"
+#include <vector>
+
+namespace snb {
+
+enum { BK_S2 = 0, BK_S1, BK_FA, BK_FB, BK_A7, BK_TRUNK };
+
+struct TcBwdStash {                 // dY arrays written by the chain kernel (atoms), byte offsets from the workspace base
+    long long dy[kMaxTrunk], df, dr1y, ds1y, ds2y, ds3y, db1y, dhead;
+    long long total;
+};
+
+struct TcBwdArgs {
+    TcProgram prog;                 // backward GEMM list (kind = BK_*), transposed weight tiles
+    TcStash fs; const unsigned char* fbase;       // forward stash
+    TcBwdStash bs; unsigned char* bbase;          // backward stash (workspace)
+    const float* d_head; int C;                   // (P, C) fp32
+    const float* absmax;                          // device scalar: max |d_head|
+    float* d_t;                                   // (P, tau) fp32, unscaled; or null
+    unsigned char* packed;
+    int n_layers, R, S, G, n_groups, tiles_per_group;
+};
+
+__device__ __forceinline__ float loss_scale(float absmax) {      // power of two that brings max |d_head| to ~64
+    if (!(absmax > 0.f) || !isfinite(absmax)) return 1.f;
+    int e; frexpf(absmax, &e);                                    // absmax = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.f, 6 - e);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// packing: transposed weight tiles B[n][k] = W[k][col + n] (sources split along k) + epilogue tables
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void tc_bwd_pack_kernel(TcProgram P, const float* __restrict__ W, unsigned char* __restrict__ packed) {
+    const int gi = blockIdx.y;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const TcGemm g = P.g[gi];
+    long long base = 0;
+    for (int i = 0; i < gi; ++i) base += (long long)P.g[i].n_chunks * P.g[i].k_slabs * P.g[i].chunk_n * 128;
+    __half* out = reinterpret_cast<__half*>(packed + base);
+    const long long total = (long long)g.n_chunks * g.k_slabs * g.chunk_n * 64;
+    for (long long e = tid; e < total; e += nthr) {
+        int kk = (int)(e & 63); long long r = e >> 6;
+        int nl = (int)(r % g.chunk_n); long long t = r / g.chunk_n;
+        int s = (int)(t % g.k_slabs), j = (int)(t / g.k_slabs);
+        int n = j * g.chunk_n + nl, k = s * 64 + kk;
+        float v = 0.f;
+        if (k < g.K) v = k < g.rows0 ? W[g.src0 + (long long)k * g.ld0 + g.col0 + n]
+                                     : W[g.src1 + (long long)(k - g.rows0) * g.ld1 + g.col1 + n];
+        size_t tile = (size_t)(j * g.k_slabs + s) * g.chunk_n * 64;
+        out[tile + (size_t)nl * 64 + ((((kk >> 3) ^ (nl & 7)) << 3) | (kk & 7))] = __float2half_rn(v);
+    }
+}
+
+struct BwdMisc { long long s3_w, r2_w, b2_w, b0_w, sigma_w; int b0_ld, H, H2, tau, has_beta; int t_seed, t_r2, t_beta, t_betav, t_sigma; };
+
+__global__ void tc_bwd_tables_kernel(BwdMisc M, long long tables_base, const float* __restrict__ W, unsigned char* __restrict__ packed) {
+    float* T = reinterpret_cast<float*>(packed + tables_base);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int n = tid; n < M.H2; n += nthr) {
+        T[M.t_seed + n] = W[M.s3_w + n];                                        // sun_v_net.6 weight (1 x H2)
+        float* r = T + M.t_r2 + n * 4;                                         // rgb_from_xyzdir.2 weight (3 x H2) as [n][4]
+        r[0] = W[M.r2_w + n]; r[1] = W[M.r2_w + M.H2 + n]; r[2] = W[M.r2_w + 2 * M.H2 + n]; r[3] = 0.f;
+        if (M.has_beta) {
+            float* b = T + M.t_beta + n * 4;                                   // [beta2 weight, W_b0[n][H], [H+1], [H+2]]
+            b[0] = W[M.b2_w + n];
+            for (int c = 0; c < 3; ++c) b[1 + c] = c < M.tau ? W[M.b0_w + (long long)n * M.b0_ld + M.H + c] : 0.f;
+            T[M.t_betav + n] = M.tau > 3 ? W[M.b0_w + (long long)n * M.b0_ld + M.H + 3] : 0.f;
+        }
+    }
+    for (int n = tid; n < M.H; n += nthr) T[M.t_sigma + n] = W[M.sigma_w + n];
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(~0u, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));     // order-independent: exact max
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the fused input-gradient chain
+// ---------------------------------------------------------------------------------------------------------------
+struct YBuf { uint4 q[4]; };
+__device__ __forceinline__ YBuf yb_load(const unsigned char* arr, int gt, int F, int n0, int row) {
+    const uint4* s = reinterpret_cast<const uint4*>(arr + (((size_t)gt * (F >> 5) + (n0 >> 5)) * kTile + row) * 64);
+    YBuf b; b.q[0] = __ldg(s); b.q[1] = __ldg(s + 1); b.q[2] = __ldg(s + 2); b.q[3] = __ldg(s + 3);
+    return b;
+}
+// v[i] *= mul * cos(2 pi r_i)
+__device__ __forceinline__ void mul_cos32(float* v, const YBuf& b, float mul) {
+    const __half2* h = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float2 r = __half22float2(h[i]);
+        v[2 * i] *= mul * __cosf(6.283185307179586f * r.x);
+        v[2 * i + 1] *= mul * __cosf(6.283185307179586f * r.y);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_constant__ TcBwdArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const TcProgram& P = A.prog;
+    Smem sm = carve(base, P, 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* T = reinterpret_cast<const float*>(A.packed + P.tables_base);
+    const int stage_bytes = P.stage_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(sm.tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sm.tmem_ptr;
+    const int n_work = A.n_groups, tpg = A.tiles_per_group;
+
+    if (warp == 0) {
+        int st = 0; uint32_t ph = 0;
+        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x)
+            for (int t = 0; t < tpg; ++t) {
+                const unsigned char* src = A.packed;
+                for (int gi = 0; gi < P.n_gemms; ++gi) {
+                    const uint32_t bytes = (uint32_t)P.g[gi].chunk_n * 128u;
+                    const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
+                    for (int i = 0; i < n; ++i) {
+                        if (lane == 0) {
+                            mbar_wait(&sm.empty[st], ph ^ 1, 21);
+                            mbar_arrive_expect_tx(&sm.full[st], bytes);
+                            bulk_g2s(sm.b + (size_t)st * stage_bytes, src, bytes, &sm.full[st]);
+                        }
+                        __syncwarp();
+                        src += bytes;
+                        if (++st == P.n_stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+    } else if (warp == 1) {
+        int st = 0; uint32_t ph = 0, ready_ph = 0;
+        const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
+        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x)
+            for (int t = 0; t < tpg; ++t)
+                for (int gi = 0; gi < P.n_gemms; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    mbar_wait(sm.a_ready, ready_ph, 22); ready_ph ^= 1;
+                    tc_fence_after();
+                    const uint32_t idesc = umma_idesc_f16((uint32_t)g.chunk_n);
+                    for (int j = 0; j < g.n_chunks; ++j)
+                        for (int s = 0; s < g.k_slabs; ++s) {
+                            mbar_wait(&sm.full[st], ph, 23);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
+                                const uint32_t a_addr = a_base + (uint32_t)s * kSlabBytes, b_addr = b_base + (uint32_t)st * stage_bytes;
+                                for (int k = 0; k < ksteps; ++k)      // g.skip = 1: accumulate onto what the previous GEMM left in TMEM
+                                    umma_f16_ss(tmem + (uint32_t)(j * g.chunk_n), umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
+                                                idesc, ((s | k) != 0 || g.skip) ? 1u : 0u);
+                                umma_commit(&sm.empty[st]);
+                                if (j == g.n_chunks - 1 && s == g.k_slabs - 1) umma_commit(sm.acc_full);
+                            }
+                            __syncwarp();
+                            if (++st == P.n_stages) { st = 0; ph ^= 1; }
+                        }
+                }
+    } else {
+        const int tid_e = threadIdx.x - 64;
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;
+        const uint32_t a_base = smem_u32(sm.a);
+        const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
+        const uint32_t tF = smem_u32(sm.tblF), tV = smem_u32(sm.tblV);
+        const int H = P.H, H2 = P.H2, S = A.S, fgsH = H >> 6, fgs2 = H2 >> 6;
+        const float scale = loss_scale(*A.absmax), inv_scale = 1.0f / scale;
+        uint32_t acc_ph = 0;
+        float* scratch = sm.z;                                    // per-point tables of the forward are unused here: (4 x 128 x 4) floats
+        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+            const int r0 = wk * A.G;
+            const int n_rays = min(A.G, A.R - r0);
+            const int Pg = n_rays * S;
+            for (int t = 0; t < tpg; ++t) {
+                const int gt = wk * tpg + t;
+                const int p = t * kTile + row;
+                const bool valid = p < Pg;
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, gsig = 0.f, gsun = 0.f, gbeta = 0.f;
+                if (valid) {
+                    const float* dh = A.d_head + ((size_t)r0 * S + p) * A.C;
+                    g0 = dh[0] * scale; g1 = dh[1] * scale; g2 = dh[2] * scale; gsig = dh[3] * scale; gsun = dh[4] * scale;
+                    if (P.has_beta) gbeta = dh[8] * scale;
+                }
+                if (half == 0) {                                  // head-gradient block for the tiny-N weight gradients
+                    unsigned char* da = A.bbase + A.bs.dhead;
+                    *reinterpret_cast<uint4*>(atom_chunk(da, gt, 1, row, 0)) = make_uint4(pack_half2(g0, g1), pack_half2(g2, gsig), pack_half2(gsun, gbeta), 0u);
+#pragma unroll
+                    for (int c = 1; c < 8; ++c) *reinterpret_cast<uint4*>(atom_chunk(da, gt, 1, row, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                // ---- seed: d s3y = g_sun * w_s3 * cos(s3y)  ->  A[:, 0:H2) ----
+                table_copy(sm.tblF, T + P.l0_tbl, H2 * 4, tid_e);
+                cp_async_wait_all();
+                if (tid_e == 0) bulk_wait_read();
+                named_bar_sync(1, kEpiThreads);
+                {
+                    const uint32_t tok = fresh_token(0x7fffu);
+                    for (int n0 = half * 32; n0 < H2; n0 += 32 * kEpiSub) {
+                        YBuf yb = yb_load(A.fbase + A.fs.s3y, gt, H2, n0, row);
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 w = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+                            v[i] = gsun * w.x; v[i + 1] = gsun * w.y; v[i + 2] = gsun * w.z; v[i + 3] = gsun * w.w;
+                        }
+                        mul_cos32(v, yb, 1.f);
+                        store_act32(a_base, row, n0, v);
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, kEpiThreads);
+                if (tid_e == 0) {
+                    bulk_s2g(A.bbase + A.bs.ds3y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit();
+                    mbar_arrive(sm.a_ready);
+                }
+                int trunk_l = A.n_layers - 1;                     // layer whose dY the next BK_TRUNK GEMM consumes
+                for (int gi = 0; gi < P.n_gemms; ++gi) {
+                    const TcGemm& g = P.g[gi];
+                    const int kind = g.kind;
+                    // epilogue tables of this GEMM (tiny) + make sure earlier stash dumps have left shared memory
+                    if (kind == BK_S1) table_copy(sm.tblF, T + g.tbl_off, H2 * 16, tid_e);
+                    else if (kind == BK_FA && P.has_beta) { table_copy(sm.tblF, T + g.tbl_off, H2 * 16, tid_e); table_copy(sm.tblV, T + g.vec_off, H2 * 4, tid_e); }
+                    else if (kind == BK_A7) table_copy(sm.tblF, T + g.tbl_off, H * 4, tid_e);
+                    cp_async_wait_all();
+                    if (tid_e == 0) bulk_wait_read();
+                    named_bar_sync(1, kEpiThreads);
+                    // first cos block prefetched while the MMAs run
+                    const unsigned char* yarr = nullptr; int yF = H; float ymul = 1.f;
+                    if (kind == BK_S2) { yarr = A.fbase + A.fs.s2y; yF = H2; }
+                    else if (kind == BK_S1) { yarr = A.fbase + A.fs.s1y; yF = H2; }
+                    else if (kind == BK_A7) yarr = A.fbase + A.fs.y[A.n_layers - 1];
+                    else if (kind == BK_TRUNK) { yarr = A.fbase + A.fs.y[trunk_l - 1]; if (trunk_l - 1 == 0) ymul = 30.f; }
+                    const int N = g.N;
+                    int n0 = half * 32;
+                    YBuf ynext;
+                    if (yarr && n0 < N) ynext = yb_load(yarr, gt, yF, n0, row);
+                    mbar_wait(sm.acc_full, acc_ph, 24); acc_ph ^= 1;
+                    tc_fence_after();
+                    const uint32_t tok = fresh_token((uint32_t)gi);
+                    float dt0 = 0.f, dt1 = 0.f, dt2 = 0.f, dt3 = 0.f;
+                    if (kind == BK_FA && P.has_beta) {
+                        // D (= d feat so far) stays in TMEM; build d b1y = g_beta * w_b2 * cos(b1y) as the next A operand
+                        for (; n0 < H2; n0 += 32 * kEpiSub) {
+                            YBuf yb = yb_load(A.fbase + A.fs.b1y, gt, H2, n0, row);
+                            float v[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = gbeta * lds128(tF + (uint32_t)(n0 + i) * 16u, tok).x;
+                            mul_cos32(v, yb, 1.f);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
+                                dt0 = fmaf(w.y, v[i], dt0); dt1 = fmaf(w.z, v[i], dt1); dt2 = fmaf(w.w, v[i], dt2);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
+                                dt3 = fmaf(w.x, v[i], dt3); dt3 = fmaf(w.y, v[i + 1], dt3); dt3 = fmaf(w.z, v[i + 2], dt3); dt3 = fmaf(w.w, v[i + 3], dt3);
+                            }
+                            store_act32(a_base, row, n0, v);
+                        }
+                    } else {
+                        for (; n0 < N; n0 += 32 * kEpiSub) {
+                            float v[32];
+                            tmem_ld32(tm_row + (uint32_t)n0, v);
+                            tmem_ld_wait();
+                            YBuf ycur = ynext;
+                            if (yarr && n0 + 32 * kEpiSub < N) ynext = yb_load(yarr, gt, yF, n0 + 32 * kEpiSub, row);
+                            if (kind == BK_A7) {
+#pragma unroll
+                                for (int i = 0; i < 32; i += 4) {
+                                    float4 w = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+                                    v[i] = fmaf(gsig, w.x, v[i]); v[i + 1] = fmaf(gsig, w.y, v[i + 1]); v[i + 2] = fmaf(gsig, w.z, v[i + 2]); v[i + 3] = fmaf(gsig, w.w, v[i + 3]);
+                                }
+                            }
+                            if (yarr) mul_cos32(v, ycur, ymul);
+                            store_act32(a_base, row, n0, v);
+                            if (kind == BK_S1) {
+                                // d r1y = (sum_c g_c W_r2[c][m]) cos(r1y)  ->  A[:, H2 + m)
+                                YBuf yr = yb_load(A.fbase + A.fs.r1y, gt, H2, n0, row);
+                                float u[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
+                                    u[i] = fmaf(g2, w.z, fmaf(g1, w.y, g0 * w.x));
+                                }
+                                mul_cos32(u, yr, 1.f);
+                                store_act32(a_base, row, H2 + n0, u);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    if (kind == BK_FA && P.has_beta && A.d_t) {
+                        float* sc = scratch + (size_t)(half * kTile + row) * 4;
+                        sc[0] = dt0; sc[1] = dt1; sc[2] = dt2; sc[3] = dt3;
+                    }
+                    named_bar_sync(1, kEpiThreads);
+                    if (kind == BK_FA && P.has_beta && A.d_t && half == 0 && valid) {
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int h2 = 0; h2 < kEpiSub; ++h2) { const float* sc = scratch + (size_t)(h2 * kTile + row) * 4; s0 += sc[0]; s1 += sc[1]; s2 += sc[2]; s3 += sc[3]; }
+                        float* o = A.d_t + ((size_t)r0 * S + p) * P.tau;
+                        o[0] = s0 * inv_scale; if (P.tau > 1) o[1] = s1 * inv_scale; if (P.tau > 2) o[2] = s2 * inv_scale; if (P.tau > 3) o[3] = s3 * inv_scale;
+                    }
+                    if (tid_e == 0) {
+                        // dump the dY tile(s) this step produced
+                        unsigned char* bb = A.bbase;
+                        if (kind == BK_S2) bulk_s2g(bb + A.bs.ds2y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
+                        else if (kind == BK_S1) {
+                            bulk_s2g(bb + A.bs.ds1y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
+                            bulk_s2g(bb + A.bs.dr1y + (size_t)gt * fgs2 * kSlabBytes, sm.a + (size_t)fgs2 * kSlabBytes, (uint32_t)fgs2 * kSlabBytes);
+                        } else if (kind == BK_FA && P.has_beta) bulk_s2g(bb + A.bs.db1y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
+                        else if (kind == BK_FB || kind == BK_FA) bulk_s2g(bb + A.bs.df + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
+                        else if (kind == BK_A7) bulk_s2g(bb + A.bs.dy[A.n_layers - 1] + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
+                        else bulk_s2g(bb + A.bs.dy[trunk_l - 1] + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
+                        bulk_commit();
+                        if (gi + 1 < P.n_gemms) mbar_arrive(sm.a_ready);
+                    }
+                    if (kind == BK_TRUNK) --trunk_l;
+                }
+            }
+        }
+        if (tid_e == 0) bulk_wait_read();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// finalize: ordered split-K reduction + scatter-add into the flat gradient buffer
+// ---------------------------------------------------------------------------------------------------------------
+struct DwOut {
+    long long part_off, part_stride; int ks, N;      // partial tiles: [ks][128][N] floats
+    int kind;                                         // 0 weight block, 1 extra-input block [x sun t 1], 2 tiny head (transposed)
+    long long w_off, b_off; int ld, m0, M, col_off, n0, ncols;    // kind 0: G[w_off + (m0+r)*ld + col_off + n0 + c], c < ncols
+    int xcol, suncol, tcol, tau;                      // kind 1: destination columns of x / sun / t (-1: none); bias always
+    int hc0, nhc;                                     // kind 2: head columns [hc0, hc0+nhc) -> rows of the tiny weight (ld = its n_in)
+};
+
+__global__ void dw_finalize_kernel(const DwOut* __restrict__ outs, const float* __restrict__ partial, const float* __restrict__ absmax, float* __restrict__ G) {
+    const DwOut o = outs[blockIdx.x];
+    const float inv = 1.0f / loss_scale(*absmax);
+    for (int e = threadIdx.x; e < 128 * o.N; e += blockDim.x) {
+        const int r = e / o.N, c = e - r * o.N;
+        if (o.m0 + r >= o.M) continue;
+        long long dst = -1;
+        if (o.kind == 0) { if (c < o.ncols) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.col_off + o.n0 + c; }
+        else if (o.kind == 1) {
+            if (c < 3) { if (o.xcol >= 0) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.xcol + c; }
+            else if (c < 6) { if (o.suncol >= 0) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.suncol + (c - 3); }
+            else if (c < 10) { if (o.tcol >= 0 && c - 6 < o.tau) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.tcol + (c - 6); }
+            else if (c == 10) dst = o.b_off + o.m0 + r;
+        } else { if (c >= o.hc0 && c < o.hc0 + o.nhc) dst = o.w_off + (long long)(c - o.hc0) * o.ld + o.m0 + r; }
+        if (dst < 0) continue;
+        float acc = 0.f;
+        for (int s = 0; s < o.ks; ++s) acc += partial[o.part_off + (long long)s * o.part_stride + e];
+        G[dst] += acc * inv;
+    }
+}
+
+// biases of the N<=3 heads: column sums of d_head over the points (fixed-order tree per column)
+__global__ void head_bias_kernel(const float* __restrict__ d_head, long long P, int C, int col, float* __restrict__ dst) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (long long p = threadIdx.x; p < P; p += blockDim.x) acc += (double)d_head[p * C + col];
+    sh[threadIdx.x] = acc; __syncthreads();
+    for (int s = 128; s; s >>= 1) { if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0) *dst += (float)sh[0];
+}
+
+// sky_color MLP (per ray, satnerf.py:138-143): gradients of sky0 (H2 x 3) and sky2 (3 x H2); block b owns hidden units n = b*blockDim + tid
+__global__ void sky_bwd_kernel(const float* __restrict__ d_head, int C, const float* __restrict__ rays, int ray_cols, const float* __restrict__ aux,
+                               int R, int S, int H2, const float* __restrict__ W, long long w0, long long b0, long long w2, float* __restrict__ G, long long gb2) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = n < H2;
+    float w0x = 0, w0y = 0, w0z = 0, bb = 0, v0 = 0, v1 = 0, v2 = 0;
+    if (on) { w0x = W[w0 + n * 3]; w0y = W[w0 + n * 3 + 1]; w0z = W[w0 + n * 3 + 2]; bb = W[b0 + n]; v0 = W[w2 + n]; v1 = W[w2 + H2 + n]; v2 = W[w2 + 2 * H2 + n]; }
+    float gw2_0 = 0, gw2_1 = 0, gw2_2 = 0, gw0x = 0, gw0y = 0, gw0z = 0, gb0 = 0, gbias0 = 0, gbias1 = 0, gbias2 = 0;
+    for (int r = 0; r < R; ++r) {
+        float d0 = 0, d1 = 0, d2 = 0;
+        for (int i = 0; i < S; ++i) { const float* dh = d_head + ((size_t)r * S + i) * C; d0 += dh[5]; d1 += dh[6]; d2 += dh[7]; }
+        const float* sd = aux ? aux + (size_t)r * 3 : rays + (size_t)r * ray_cols + 8;
+        float pre = fmaf(w0z, sd[2], fmaf(w0y, sd[1], fmaf(w0x, sd[0], bb)));
+        float h = fmaxf(pre, 0.f);
+        gw2_0 = fmaf(d0, h, gw2_0); gw2_1 = fmaf(d1, h, gw2_1); gw2_2 = fmaf(d2, h, gw2_2);
+        float dh_ = pre > 0.f ? fmaf(d2, v2, fmaf(d1, v1, d0 * v0)) : 0.f;
+        gw0x = fmaf(dh_, sd[0], gw0x); gw0y = fmaf(dh_, sd[1], gw0y); gw0z = fmaf(dh_, sd[2], gw0z); gb0 += dh_;
+        gbias0 += d0; gbias1 += d1; gbias2 += d2;
+    }
+    if (on) {
+        G[w2 + n] += gw2_0; G[w2 + H2 + n] += gw2_1; G[w2 + 2 * H2 + n] += gw2_2;
+        G[w0 + n * 3] += gw0x; G[w0 + n * 3 + 1] += gw0y; G[w0 + n * 3 + 2] += gw0z; G[b0 + n] += gb0;
+    }
+    if (n == 0) { G[gb2] += gbias0; G[gb2 + 1] += gbias1; G[gb2 + 2] += gbias2; }
+}
+
+__global__ void ray_sum_t_kernel(const float* __restrict__ per_point, float* __restrict__ per_ray, int n_rays, int S, int D) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rays * D) return;
+    int r = idx / D, d = idx - r * D;
+    float acc = 0.f;
+    for (int i = 0; i < S; ++i) acc += per_point[((size_t)r * S + i) * D + d];
+    per_ray[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------------
+static bool bwd_supported(const FieldLayout& L, const snb_pass_desc* p) {
+    if (L.variant == SNB_NERF) return false;
+    if (L.width % 128 != 0 || L.width > 512) return false;
+    if (L.n_layers + 4 > kMaxGemms || L.n_layers < 2) return false;
+    if (p->n_samples > kMaxGroupPts) return false;
+    if (L.t_dims > 4) return false;
+    return true;
+}
+
+static int group_for(int S) {
+    int best = 1; double best_u = 0.0;
+    for (int G = 1; G <= kMaxGroupRays; ++G) {
+        int pts = G * S; if (pts > kMaxGroupPts) break;
+        double u = (double)pts / (double)(((pts + kTile - 1) / kTile) * kTile);
+        if (u > best_u + 1e-9) { best_u = u; best = G; }
+    }
+    return best;
+}
+
+static int build_bwd_program(const FieldLayout& L, TcProgram* P, BwdMisc* M) {
+    memset(P, 0, sizeof(*P)); memset(M, 0, sizeof(*M));
+    const int H = L.width, H2 = H / 2;
+    P->H = H; P->H2 = H2; P->tau = L.t_dims; P->has_beta = L.variant == SNB_SATNERF; P->a_slabs = H / 64;
+    int ng = 0, tbl = 0;
+    auto add = [&](int kind, int N, int K) -> TcGemm& {
+        TcGemm& g = P->g[ng++]; memset(&g, 0, sizeof(g));
+        g.kind = kind; g.N = N; g.K = K; g.n_chunks = (N + 255) / 256; g.chunk_n = N / g.n_chunks; g.k_slabs = (K + 63) / 64;
+        return g;
+    };
+    P->l0_tbl = tbl; M->t_seed = tbl; tbl += H2;                                      // sun_v_net.6 weight
+    { TcGemm& g = add(BK_S2, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; }
+    { TcGemm& g = add(BK_S1, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; g.tbl_off = tbl; M->t_r2 = tbl; tbl += 4 * H2; }
+    { TcGemm& g = add(BK_FA, H, H); g.src0 = L.sun[0].w; g.ld0 = L.sun[0].n_in; g.rows0 = H2; g.src1 = L.rgb0.w; g.ld1 = L.rgb0.n_in;
+      g.tbl_off = tbl; M->t_beta = tbl; tbl += 4 * H2; g.vec_off = tbl; M->t_betav = tbl; tbl += H2; }
+    if (P->has_beta) { TcGemm& g = add(BK_FB, H, H2); g.src0 = L.beta0.w; g.ld0 = L.beta0.n_in; g.rows0 = H2; g.skip = 1; }
+    { TcGemm& g = add(BK_A7, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; g.tbl_off = tbl; M->t_sigma = tbl; tbl += H; }
+    for (int l = L.n_layers - 1; l >= 1; --l) {
+        TcGemm& g = add(BK_TRUNK, H, H); g.src0 = L.trunk[l].w; g.ld0 = L.trunk[l].n_in; g.col0 = l == L.skip ? L.in_xyz : 0; g.rows0 = H;
+    }
+    P->n_gemms = ng;
+    long long wbytes = 0; int max_stage = 0;
+    for (int i = 0; i < ng; ++i) {
+        wbytes += (long long)P->g[i].n_chunks * P->g[i].k_slabs * P->g[i].chunk_n * 128;
+        if (P->g[i].chunk_n * 128 > max_stage) max_stage = P->g[i].chunk_n * 128;
+    }
+    P->stage_bytes = max_stage; P->tables_base = (wbytes + 255) & ~255LL;
+    M->s3_w = L.sun[3].w; M->r2_w = L.rgb2.w; M->b2_w = L.beta2.w; M->b0_w = L.beta0.w; M->b0_ld = L.beta0.n_in; M->sigma_w = L.sigma.w;
+    M->H = H; M->H2 = H2; M->tau = L.t_dims; M->has_beta = P->has_beta;
+    return tbl;
+}
+
+static void fwd_stash_layout(const FieldLayout& L, int n_tiles, int tpg, TcStash* S) {      // must mirror tc_field.cu::stash_layout
+    memset(S, 0, sizeof(*S));
+    const int H = L.width, H2 = H / 2;
+    const long long tH = (long long)(H / 64) * kSlabBytes, tH2 = (long long)((H2 + 63) / 64) * kSlabBytes;
+    const long long yH = (long long)kTile * H * 2, yH2 = (long long)kTile * H2 * 2;
+    long long off = 0;
+    auto take = [&](long long per_tile) { long long o = off; off += per_tile * n_tiles; off = (off + 1023) & ~1023LL; return o; };
+    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(yH); }
+    S->feat = take(tH);
+    S->r1 = take(tH2); S->s1 = take(tH2); S->s2 = take(tH2); S->s3 = take(tH2); S->b1 = take(tH2);
+    S->r1y = take(yH2); S->s1y = take(yH2); S->s2y = take(yH2); S->s3y = take(yH2); S->b1y = take(yH2);
+    S->e = take(kSlabBytes);
+    S->total = off; S->n_tiles = n_tiles; S->tiles_per_group = tpg;
+}
+
+struct BwdPlan {
+    int G, groups, tpg, n_tiles, ks, n_outs, n_items;
+    TcBwdStash bs;
+    size_t off_dhead, off_absmax, off_dt, off_packed, packed_bytes, off_bstash, off_items, off_outs, off_partial, partial_floats, total;
+};
+
+static void plan_bwd(const FieldLayout& L, const snb_pass_desc* p, const TcProgram& P, int n_tbl_floats, BwdPlan* B) {
+    const int H = L.width, H2 = H / 2, S = p->n_samples;
+    B->G = group_for(S); B->groups = (p->n_rays + B->G - 1) / B->G; B->tpg = (B->G * S + kTile - 1) / kTile; B->n_tiles = B->groups * B->tpg;
+    const long long tH = (long long)(H / 64) * kSlabBytes, tH2 = (long long)(H2 / 64) * kSlabBytes;
+    long long off = 0;
+    auto take = [&](long long per_tile) { long long o = off; off += per_tile * B->n_tiles; off = (off + 1023) & ~1023LL; return o; };
+    for (int l = 0; l < L.n_layers; ++l) B->bs.dy[l] = take(tH);
+    B->bs.df = take(tH); B->bs.dr1y = take(tH2); B->bs.ds1y = take(tH2); B->bs.ds2y = take(tH2); B->bs.ds3y = take(tH2); B->bs.db1y = take(tH2);
+    B->bs.dhead = take(kSlabBytes);
+    B->bs.total = off;
+    // output tiles of the weight-gradient GEMMs
+    const int mH = H / 128, mH2 = H2 / 128 > 0 ? H2 / 128 : 1;
+    const int cH = (H / 64 + 3) / 4, cH2 = (H2 / 64 + 3) / 4;
+    int outs = 0;
+    outs += (L.n_layers - 1) * mH * (cH + 1) + mH;             // trunk layers >= 1: [a_{l-1} | E]; layer 0: E only
+    outs += mH * (cH + 1);                                    // feats
+    outs += (L.variant == SNB_SATNERF ? 3 : 2) * mH2 * (cH + 1);   // rgb0, sun0 (, beta0): [feat | E]
+    outs += 2 * mH2 * (cH2 + 1);                              // sun1, sun2
+    outs += mH + (L.variant == SNB_SATNERF ? 3 : 2) * mH2;    // tiny heads: sigma (a_7), rgb2 (r1), sun3 (s3) (, beta2 (b1))
+    B->n_outs = outs;
+    int ks = (148 * 3 + outs - 1) / outs; if (ks < 1) ks = 1; if (ks > B->n_tiles) ks = B->n_tiles; if (ks > 16) ks = 16;
+    B->ks = ks; B->n_items = outs * ks;
+    Arena ar(nullptr, 0);
+    B->off_dhead = ar.off; ar.take<float>((size_t)p->n_rays * S * L.n_channels);
+    B->off_absmax = ar.off; ar.take<float>(64);
+    B->off_dt = ar.off; ar.take<float>((size_t)p->n_rays * S * (L.t_dims > 0 ? L.t_dims : 1));
+    B->packed_bytes = (size_t)P.tables_base + (size_t)n_tbl_floats * 4 + 256;
+    B->off_packed = ar.off; ar.take<unsigned char>(B->packed_bytes);
+    B->off_bstash = ar.off; ar.take<unsigned char>((size_t)B->bs.total + 1024);
+    B->off_items = ar.off; ar.take<DwItem>(B->n_items);
+    B->off_outs = ar.off; ar.take<DwOut>(outs);
+    B->partial_floats = (size_t)B->n_items * 128 * 256;
+    B->off_partial = ar.off; ar.take<float>(B->partial_floats);
+    B->total = ar.off;
+}
+
+int tc_bwd_workspace(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes) {
+    *bytes = 0;
+    if (!bwd_supported(L, p)) return 0;
+    TcProgram P; BwdMisc M; int nt = build_bwd_program(L, &P, &M);
+    BwdPlan B; memset(&B, 0, sizeof(B)); plan_bwd(L, p, P, nt, &B);
+    *bytes = B.total + 4096;
+    return 0;
+}
+
+int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_render_io* io, const snb_render_grads* g,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (!bwd_supported(L, p) || !io->stash) return 1;
+    { const char* e = getenv("SNB_TC_BWD"); if (e && atoi(e) == 0) return 1; }
+    static int sm_count = 0, max_smem = 0;
+    if (!sm_count) {
+        int dev = 0; SNB_CUDA(cudaGetDevice(&dev));
+        SNB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        SNB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int H = L.width, H2 = H / 2, S = p->n_samples, C = L.n_channels, R = p->n_rays;
+    const long long Ptot = (long long)R * S;
+    TcBwdArgs A; memset(&A, 0, sizeof(A));
+    BwdMisc M; int nt = build_bwd_program(L, &A.prog, &M);
+    TcProgram& P = A.prog;
+    BwdPlan B; memset(&B, 0, sizeof(B)); plan_bwd(L, p, P, nt, &B);
+    if (B.total > workspace_bytes) SNB_FAIL(-4, "tensor-core backward: workspace too small (%zu < %zu)", workspace_bytes, B.total);
+    unsigned char* ws = (unsigned char*)workspace;
+    float* d_head = (float*)(ws + B.off_dhead);
+    float* absmax = (float*)(ws + B.off_absmax);
+    float* d_t = (float*)(ws + B.off_dt);
+
+    // 1. compositing backward -> d_head
+    CompositeBwdArgs b{};
+    b.R = R; b.S = S; b.C = C; b.z = io->z_vals; b.noise = p->noise_std != 0.f ? io->noise : nullptr; b.noise_std = p->noise_std;
+    b.weights = io->weights; b.transparency = io->transparency; b.sigma = io->sigma; b.albedo = io->albedo; b.sun = io->sun;
+    b.sky = io->sky; b.beta = io->beta; b.nerf_rgb = io->nerf_rgb;
+    b.g_rgb = g->g_rgb; b.g_depth = g->g_depth; b.g_weights = g->g_weights; b.g_transparency = g->g_transparency;
+    b.g_albedo = g->g_albedo; b.g_sun = g->g_sun; b.g_sky = g->g_sky; b.g_beta = g->g_beta; b.d_head = d_head;
+    SNB_TRY(launch_composite_bwd(b, st));
+    SNB_CUDA(cudaMemsetAsync(absmax, 0, 256, st));
+    absmax_kernel<<<148, 256, 0, st>>>(d_head, Ptot * C, absmax);
+    SNB_CHECK_LAUNCH();
+
+    // 2. packed transposed weights + tables, then the input-gradient chain
+    A.packed = ws + B.off_packed;
+    tc_bwd_pack_kernel<<<dim3(64, P.n_gemms), 256, 0, st>>>(P, io->params, A.packed);
+    SNB_CHECK_LAUNCH();
+    tc_bwd_tables_kernel<<<4, 256, 0, st>>>(M, P.tables_base, io->params, A.packed);
+    SNB_CHECK_LAUNCH();
+    size_t fixed = (size_t)P.a_slabs * kSlabBytes + (kTblF + kTblV + 8 * kMaxGroupPts * 4 + 2 * kMaxGroupRays * 256 * 4 + 768) + 1024;
+    int ns = (int)(((size_t)max_smem - fixed) / P.stage_bytes); if (ns > 8) ns = 8;
+    if (ns < 2) SNB_FAIL(-6, "tensor-core backward: not enough shared memory for the weight ring");
+    P.n_stages = ns;
+    size_t smem = fixed + (size_t)ns * P.stage_bytes;
+    fwd_stash_layout(L, B.n_tiles, B.tpg, &A.fs); A.fbase = (const unsigned char*)io->stash;
+    A.bs = B.bs; A.bbase = ws + B.off_bstash;
+    A.d_head = d_head; A.C = C; A.absmax = absmax; A.d_t = (L.t_dims && g->g_t_emb) ? d_t : nullptr;
+    A.n_layers = L.n_layers; A.R = R; A.S = S; A.G = B.G; A.n_groups = B.groups; A.tiles_per_group = B.tpg;
+    SNB_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_bwd_kernel<<<B.groups < sm_count ? B.groups : sm_count, kThreads, smem, st>>>(A);
+    SNB_CHECK_LAUNCH();
+
+    // 3. weight-gradient GEMMs: work list
+    std::vector<DwItem> items; std::vector<DwOut> outs;
+    items.reserve(B.n_items); outs.reserve(B.n_outs);
+    const unsigned char* fb = (const unsigned char*)io->stash; const unsigned char* bb = ws + B.off_bstash;
+    const int fgH = H / 64, fg2 = H2 / 64;
+    auto add_out = [&](const unsigned char* a_arr, int a_fgs, int a_fg0, const unsigned char* b_arr, int b_fgs, int b_fg0, int b_nfg, DwOut o) {
+        o.N = b_nfg * 64; o.ks = B.ks; o.part_off = (long long)items.size() * 128 * 256; o.part_stride = 128 * 256;
+        for (int s = 0; s < B.ks; ++s) {
+            DwItem w; memset(&w, 0, sizeof(w));
+            w.a_off = (long long)(uintptr_t)a_arr; w.b_off = (long long)(uintptr_t)b_arr; w.a_fgs = a_fgs; w.b_fgs = b_fgs;
+            w.a_fg0 = a_fg0; w.b_fg0 = b_fg0; w.b_nfg = b_nfg;
+            w.k_tile0 = (int)((long long)B.n_tiles * s / B.ks); w.k_tiles = (int)((long long)B.n_tiles * (s + 1) / B.ks) - w.k_tile0;
+            w.out_off = (long long)items.size() * 128 * 256;
+            items.push_back(w);
+        }
+        outs.push_back(o);
+    };
+    // one linear layer: dY (out features M, atoms dy_arr with dy_fgs groups) x [IN (in features Nin, atoms) | E]
+    auto layer = [&](const Lin& l, const unsigned char* dy_arr, int dy_fgs, const unsigned char* in_arr, int in_fgs, int Nin, int col_off,
+                     int xcol, int suncol, int tcol) {
+        const int M_ = l.n_out;
+        for (int m = 0; m * 128 < M_; ++m) {
+            if (in_arr) for (int c0 = 0; c0 < in_fgs; c0 += 4) {
+                DwOut o; memset(&o, 0, sizeof(o)); o.kind = 0; o.w_off = l.w; o.ld = l.n_in; o.m0 = m * 128; o.M = M_; o.col_off = col_off; o.n0 = c0 * 64;
+                int nfg = in_fgs - c0 < 4 ? in_fgs - c0 : 4; o.ncols = Nin - c0 * 64 < nfg * 64 ? Nin - c0 * 64 : nfg * 64;
+                add_out(dy_arr, dy_fgs, 2 * m, in_arr, in_fgs, c0, nfg, o);
+            }
+            DwOut o; memset(&o, 0, sizeof(o)); o.kind = 1; o.w_off = l.w; o.b_off = l.b; o.ld = l.n_in; o.m0 = m * 128; o.M = M_;
+            o.xcol = xcol; o.suncol = suncol; o.tcol = tcol; o.tau = L.t_dims;
+            add_out(dy_arr, dy_fgs, 2 * m, fb + A.fs.e, 1, 0, 1, o);
+        }
+    };
+    auto tiny = [&](const Lin& l, const unsigned char* in_arr, int in_fgs, int hc0, int nhc) {     // W (nhc x n_in): rows = head columns
+        for (int m = 0; m * 128 < l.n_in; ++m) {
+            DwOut o; memset(&o, 0, sizeof(o)); o.kind = 2; o.w_off = l.w; o.ld = l.n_in; o.m0 = m * 128; o.M = l.n_in; o.hc0 = hc0; o.nhc = nhc;
+            add_out(in_arr, in_fgs, 2 * m, bb + B.bs.dhead, 1, 0, 1, o);
+        }
+    };
+    for (int l = L.n_layers - 1; l >= 1; --l)
+        layer(L.trunk[l], bb + B.bs.dy[l], fgH, fb + A.fs.a[l - 1], fgH, H, l == L.skip ? L.in_xyz : 0, l == L.skip ? 0 : -1, -1, -1);
+    layer(L.trunk[0], bb + B.bs.dy[0], fgH, nullptr, 0, 0, 0, 0, -1, -1);
+    layer(L.feats, bb + B.bs.df, fgH, fb + A.fs.a[L.n_layers - 1], fgH, H, 0, -1, -1, -1);
+    layer(L.rgb0, bb + B.bs.dr1y, fg2, fb + A.fs.feat, fgH, H, 0, -1, -1, -1);
+    layer(L.sun[0], bb + B.bs.ds1y, fg2, fb + A.fs.feat, fgH, H, 0, -1, H, -1);
+    if (L.variant == SNB_SATNERF) layer(L.beta0, bb + B.bs.db1y, fg2, fb + A.fs.feat, fgH, H, 0, -1, -1, H);
+    layer(L.sun[1], bb + B.bs.ds2y, fg2, fb + A.fs.s1, fg2, H2, 0, -1, -1, -1);
+    layer(L.sun[2], bb + B.bs.ds3y, fg2, fb + A.fs.s2, fg2, H2, 0, -1, -1, -1);
+    tiny(L.sigma, fb + A.fs.a[L.n_layers - 1], fgH, 3, 1);
+    tiny(L.rgb2, fb + A.fs.r1, fg2, 0, 3);
+    tiny(L.sun[3], fb + A.fs.s3, fg2, 4, 1);
+    if (L.variant == SNB_SATNERF) tiny(L.beta2, fb + A.fs.b1, fg2, 5, 1);
+    if ((int)items.size() > B.n_items || (int)outs.size() > B.n_outs) SNB_FAIL(-3, "internal: weight-gradient work list overflow (%zu/%d, %zu/%d)", items.size(), B.n_items, outs.size(), B.n_outs);
+    DwItem* d_items = (DwItem*)(ws + B.off_items); DwOut* d_outs = (DwOut*)(ws + B.off_outs);
+    SNB_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(DwItem) * items.size(), cudaMemcpyHostToDevice, st));
+    SNB_CUDA(cudaMemcpyAsync(d_outs, outs.data(), sizeof(DwOut) * outs.size(), cudaMemcpyHostToDevice, st));
+    SNB_CUDA(cudaStreamSynchronize(st));          // the host vectors go out of scope; the copies are tiny
+    float* partial = (float*)(ws + B.off_partial);
+    SNB_TRY(launch_dw(d_items, (int)items.size(), nullptr, partial, st));
+
+    // 4. reductions / scatter into the flat gradient
+    dw_finalize_kernel<<<(unsigned)outs.size(), 256, 0, st>>>(d_outs, partial, absmax, g->g_params);
+    SNB_CHECK_LAUNCH();
+    head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, 3, g->g_params + L.sigma.b); SNB_CHECK_LAUNCH();
+    for (int c = 0; c < 3; ++c) { head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, c, g->g_params + L.rgb2.b + c); SNB_CHECK_LAUNCH(); }
+    head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, 4, g->g_params + L.sun[3].b); SNB_CHECK_LAUNCH();
+    if (L.variant == SNB_SATNERF) { head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, 8, g->g_params + L.beta2.b); SNB_CHECK_LAUNCH(); }
+    sky_bwd_kernel<<<(H2 + 63) / 64, 64, 0, st>>>(d_head, C, io->rays, p->ray_cols, io->aux_dir, R, S, H2, io->params, L.sky0.w, L.sky0.b, L.sky2.w,
+                                                   g->g_params, L.sky2.b);
+    SNB_CHECK_LAUNCH();
+    if (A.d_t) {
+        ray_sum_t_kernel<<<(R * L.t_dims + 127) / 128, 128, 0, st>>>(d_t, g->g_t_emb, R, S, L.t_dims);
+        SNB_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+}  // namespace snb

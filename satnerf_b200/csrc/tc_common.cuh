@@ -1,0 +1,179 @@
+// Shared tile machinery of the fused tensor-core kernels (forward: tc_field.cu, input-gradient chain: tc_bwd.cu).
+#pragma once
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include <cstdlib>
+
+namespace snb {
+
+using namespace ptx;
+
+constexpr int kTile = 128;             // points per tile = UMMA M
+constexpr int kMaxGemms = 24;
+constexpr int kMaxGroupRays = 4;
+constexpr int kMaxGroupPts = 384;
+constexpr int kSlabBytes = kTile * 128;      // one 64-wide K slab of the A tile
+constexpr int kTblF = 8192, kTblV = 2048;    // epilogue table region: [N][4] or [N] floats + extra vector
+constexpr int kEpiWarps = 16;                 // 4 warps per TMEM lane quadrant
+constexpr int kEpiSub = kEpiWarps / 4;         // column-block interleave factor within a quadrant
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
+
+enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3 };
+enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
+
+struct TcGemm {
+    int kind, N, K, n_chunks, chunk_n, k_slabs, skip, last, fmt, has_vec;
+    int tbl_off, vec_off;            // float offsets into the packed table area
+    // weight sources (flat fp32 params): rows [0,rows0) from src0, the rest from src1
+    long long src0, src1; int ld0, ld1, col0, col1, rows0;
+};
+
+struct TcProgram {
+    int H, H2, n_gemms, tau, has_beta, a_slabs, stage_bytes, n_stages;
+    int l0_tbl, consts, sunw, betaw, sky;        // float offsets in the table area
+    long long l0_w, l0_b;                        // flat param offsets of trunk layer 0
+    long long tables_base;                       // byte offset of the table area in the packed buffer
+    TcGemm g[kMaxGemms];
+};
+
+// Activation stash written by the training-mode forward (byte offsets from the stash base; every array is indexed
+// by the global tile id gt = group * tiles_per_group + tile).
+//   atoms : [gt][fg = f/64][pg][8 points][64 features] fp16, 128B-swizzled (see tc_backward.cu) — A-tile images
+//   yb    : [gt][f/32][128 rows][32] fp16 pre-activations as revolutions frac(y / 2pi) (cos() argument of the backward)
+struct TcStash {
+    long long a[kMaxTrunk];                 // a_l = sin(.) outputs of trunk layer l (atoms, H wide)
+    long long feat, r1, s1, s2, s3, b1;     // feats_from_xyz output; first-layer activations of the rgb / sun / beta heads
+    long long y[kMaxTrunk], r1y, s1y, s2y, s3y, b1y;   // yb arrays
+    long long e;                            // atoms, one feature group: [x y z | sun(3) | t_emb(<=4) | 1 | 0...]
+    long long total;
+    int n_tiles, tiles_per_group;
+};
+
+struct TcArgs {
+    TcProgram prog;
+    TcStash stash; unsigned char* stash_base;    // stash_base == nullptr: inference, nothing is stashed
+    const float *params, *rays, *z, *t_emb, *noise, *xyz, *aux;
+    float noise_std;
+    float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma;
+    unsigned char* packed;
+    int R, S, ray_cols, dir_col, G, n_groups;
+    int dbg;      // developer knobs (env SNB_TC_DBG): 1 = skip sin, 2 = skip TMEM loads, 4 = skip activation stores,
+                  // 8 = skip MMA issue, 16 = skip weight copies
+};
+
+
+struct Smem {
+    unsigned char* a;        // activation tile: a_slabs x [128 rows x 128 B], 128B-swizzled, K-major
+    unsigned char* b;        // weight ring: n_stages x stage_bytes
+    float* tblF;             // [N][4] or [N]
+    float* tblV;             // [N]
+    float *z, *sg, *al0, *al1, *al2, *sn, *bt, *wt;   // per-point tables of the current group (kMaxGroupPts each)
+    float* sunb;             // [kMaxGroupRays][H2] per-ray bias of sun_v_net.0 (bias + W[:,H:H+3] sun_d)
+    float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
+    float* skyc;             // [kMaxGroupRays][4]
+    float* consts;           // 8 floats
+    uint64_t *full, *empty, *peer_full, *acc_full, *a_ready;
+    uint32_t* tmem_ptr;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, int cg) {
+    Smem s; unsigned char* p = base;
+    s.a = p; p += (size_t)P.a_slabs * kSlabBytes;
+    s.b = p; p += (size_t)P.n_stages * (P.stage_bytes / cg);
+    s.tblF = (float*)p; p += kTblF;
+    s.tblV = (float*)p; p += kTblV;
+    float* f = (float*)p;
+    s.z = f; s.sg = f + kMaxGroupPts; s.al0 = f + 2 * kMaxGroupPts; s.al1 = f + 3 * kMaxGroupPts; s.al2 = f + 4 * kMaxGroupPts;
+    s.sn = f + 5 * kMaxGroupPts; s.bt = f + 6 * kMaxGroupPts; s.wt = f + 7 * kMaxGroupPts;
+    p += 8 * kMaxGroupPts * 4;
+    s.sunb = (float*)p; p += kMaxGroupRays * 256 * 4;
+    s.betab = (float*)p; p += kMaxGroupRays * 256 * 4;
+    s.skyc = (float*)p; p += 64;
+    s.consts = (float*)p; p += 32;
+    s.full = (uint64_t*)p; p += 8 * 8;
+    s.empty = (uint64_t*)p; p += 8 * 8;
+    s.peer_full = (uint64_t*)p; p += 8 * 8;
+    s.acc_full = (uint64_t*)p; p += 8;
+    s.a_ready = (uint64_t*)p; p += 8;
+    s.tmem_ptr = (uint32_t*)p;
+    return s;
+}
+
+__device__ __forceinline__ int group_points(const TcArgs& A, int grp) {
+    int r0 = grp * A.G; int n = A.R - r0; if (n > A.G) n = A.G; return n * A.S;
+}
+
+// byte address of the 16-byte chunk holding k..k+7 (k % 8 == 0) of `row` in the swizzled A tile
+__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int row, int k) {
+    return a_base + (uint32_t)(k >> 6) * kSlabBytes + (uint32_t)row * 128u + ((((uint32_t)(k >> 3) & 7u) ^ ((uint32_t)row & 7u)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// store 32 consecutive activations (k0 % 32 == 0) of one row as fp16
+__device__ __forceinline__ void store_act32(uint32_t a_base, int row, int k0, const float* v) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float* x = v + c * 8;
+        sts128(a_chunk_addr(a_base, row, k0 + c * 8), pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
+    }
+}
+// ---- training stash helpers -------------------------------------------------------------------------------
+// pre-activations are stashed as fp16 revolutions r = frac(y / 2pi) in [-0.5, 0.5]: cos(2 pi r) = cos(y) with a uniform
+// absolute error (fp16 ulp 2.4e-4 rev = 1.5e-3 rad) whatever |y| is (first layer: y = 30 (W0 x + b0) reaches +-50 rad)
+__device__ __forceinline__ float to_rev(float y) {
+    float r = __fmul_rn(y, 0.15915494309189535f);
+    return __fsub_rn(r, __fsub_rn(__fadd_rn(r, 12582912.0f), 12582912.0f));       // r - rint(r)
+}
+// 64-byte slot of (tile gt, 32-column block n0/32, row) in a yb array with F features
+__device__ __forceinline__ unsigned char* yb_slot(unsigned char* arr, int gt, int F, int n0, int row) {
+    return arr + (((size_t)gt * (F >> 5) + (n0 >> 5)) * kTile + row) * 64;
+}
+__device__ __forceinline__ void yb_store32(unsigned char* slot, const float* y) {
+    uint4* d = reinterpret_cast<uint4*>(slot);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float* x = y + c * 8;
+        d[c] = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
+                          pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
+    }
+}
+// address of the 16-byte chunk (features k..k+7, k % 8 == 0) of point `row` of tile gt in an atoms array with `fgs` groups
+__device__ __forceinline__ unsigned char* atom_chunk(unsigned char* arr, int gt, int fgs, int row, int k) {
+    return arr + (((size_t)gt * fgs + (k >> 6)) * 16 + (row >> 3)) * 1024 + (size_t)(row & 7) * 128 + (size_t)((((k >> 3) & 7) ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void atom_store32(unsigned char* arr, int gt, int fgs, int row, int k0, const float* v) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float* x = v + c * 8;
+        *reinterpret_cast<uint4*>(atom_chunk(arr, gt, fgs, row, k0 + c * 8)) =
+            make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
+    }
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// cooperative copy (all epilogue threads) of `bytes` (multiple of 16) from global to shared with cp.async
+__device__ __forceinline__ void table_copy(void* dst, const void* src, int bytes, int tid_e) {
+    for (int o = tid_e * 16; o < bytes; o += kEpiThreads * 16) cp_async16((char*)dst + o, (const char*)src + o);
+}
+
+
+// Shared-memory table read that the compiler may schedule freely (no "memory" clobber, so reads of a block
+// pipeline instead of paying the LDS latency one by one).  `tok` is a value produced by fresh_token() AFTER the
+// barrier that published the table: the data dependence keeps the read below that barrier and keeps reads of
+// different table generations (same address, next layer) from being merged.
+__device__ __forceinline__ float4 lds128(uint32_t addr, uint32_t tok) {
+    float4 r;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+0];  // gen %5" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr), "r"(tok));
+    return r;
+}
+__device__ __forceinline__ uint32_t fresh_token(uint32_t x) {
+    uint32_t t;
+    asm volatile("mov.u32 %0, %1;" : "=r"(t) : "r"(x) : "memory");
+    return t;
+}
+
+}  // namespace snb

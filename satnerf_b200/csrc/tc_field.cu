@@ -16,52 +16,9 @@
 // Arithmetic: fp16 operands / fp32 accumulation for the h x h contractions; first layer, skip term,
 // per-ray sun / embedding terms, heads and compositing in fp32 (SURVEY.md §7 "Precision").
 #include "tc_field.cuh"
-#include "sm100_ptx.cuh"
-#include <cstdlib>
+#include "tc_common.cuh"
 
 namespace snb {
-
-using namespace ptx;
-
-constexpr int kTile = 128;             // points per tile = UMMA M
-constexpr int kMaxGemms = 24;
-constexpr int kMaxGroupRays = 4;
-constexpr int kMaxGroupPts = 384;
-constexpr int kSlabBytes = kTile * 128;      // one 64-wide K slab of the A tile
-constexpr int kTblF = 8192, kTblV = 2048;    // epilogue table region: [N][4] or [N] floats + extra vector
-constexpr int kEpiWarps = 16;                 // 4 warps per TMEM lane quadrant
-constexpr int kEpiSub = kEpiWarps / 4;         // column-block interleave factor within a quadrant
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;
-
-enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3 };
-enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
-
-struct TcGemm {
-    int kind, N, K, n_chunks, chunk_n, k_slabs, skip, last, fmt, has_vec;
-    int tbl_off, vec_off;            // float offsets into the packed table area
-    // weight sources (flat fp32 params): rows [0,rows0) from src0, the rest from src1
-    long long src0, src1; int ld0, ld1, col0, col1, rows0;
-};
-
-struct TcProgram {
-    int H, H2, n_gemms, tau, has_beta, a_slabs, stage_bytes, n_stages;
-    int l0_tbl, consts, sunw, betaw, sky;        // float offsets in the table area
-    long long l0_w, l0_b;                        // flat param offsets of trunk layer 0
-    long long tables_base;                       // byte offset of the table area in the packed buffer
-    TcGemm g[kMaxGemms];
-};
-
-struct TcArgs {
-    TcProgram prog;
-    const float *params, *rays, *z, *t_emb, *noise, *xyz, *aux;
-    float noise_std;
-    float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma;
-    unsigned char* packed;
-    int R, S, ray_cols, dir_col, G, n_groups;
-    int dbg;      // developer knobs (env SNB_TC_DBG): 1 = skip sin, 2 = skip TMEM loads, 4 = skip activation stores,
-                  // 8 = skip MMA issue, 16 = skip weight copies
-};
 
 // --------------------------------------------------------------------------------------------------
 // host: build the per-tile GEMM program
@@ -120,6 +77,22 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
     P->stage_bytes = max_stage;
     P->tables_base = (wbytes + 255) & ~255LL;
     return tbl;      // number of floats in the table area
+}
+
+// Stash layout for n_tiles tiles (see TcStash).
+static void stash_layout(const FieldLayout& L, int n_tiles, int tiles_per_group, TcStash* S) {
+    memset(S, 0, sizeof(*S));
+    const int H = L.width, H2 = H / 2;
+    const long long tH = (long long)(H / 64) * kSlabBytes, tH2 = (long long)((H2 + 63) / 64) * kSlabBytes;   // atoms bytes per tile
+    const long long yH = (long long)kTile * H * 2, yH2 = (long long)kTile * H2 * 2;                           // yb bytes per tile
+    long long off = 0;
+    auto take = [&](long long per_tile) { long long o = off; off += per_tile * n_tiles; off = (off + 1023) & ~1023LL; return o; };
+    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(yH); }
+    S->feat = take(tH);
+    S->r1 = take(tH2); S->s1 = take(tH2); S->s2 = take(tH2); S->s3 = take(tH2); S->b1 = take(tH2);
+    S->r1y = take(yH2); S->s1y = take(yH2); S->s2y = take(yH2); S->s3y = take(yH2); S->b1y = take(yH2);
+    S->e = take(kSlabBytes);
+    S->total = off; S->n_tiles = n_tiles; S->tiles_per_group = tiles_per_group;
 }
 
 static size_t smem_fixed_bytes() {
@@ -223,107 +196,38 @@ __global__ void tc_pack_misc_kernel(TcProgram P, MiscOffsets M, const float* __r
 __device__ long long g_tc_dbg[64 * 4];
 #define TC_MARK(slot, k) do { if (dbg_on && tid_e == 0) g_tc_dbg[(slot) * 4 + (k)] = clock64(); } while (0)
 
-struct Smem {
-    unsigned char* a;        // activation tile: a_slabs x [128 rows x 128 B], 128B-swizzled, K-major
-    unsigned char* b;        // weight ring: n_stages x stage_bytes
-    float* tblF;             // [N][4] or [N]
-    float* tblV;             // [N]
-    float *z, *sg, *al0, *al1, *al2, *sn, *bt, *wt;   // per-point tables of the current group (kMaxGroupPts each)
-    float* sunb;             // [kMaxGroupRays][H2] per-ray bias of sun_v_net.0 (bias + W[:,H:H+3] sun_d)
-    float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
-    float* skyc;             // [kMaxGroupRays][4]
-    float* consts;           // 8 floats
-    uint64_t *full, *empty, *peer_full, *acc_full, *a_ready;
-    uint32_t* tmem_ptr;
-};
-
-__device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, int cg) {
-    Smem s; unsigned char* p = base;
-    s.a = p; p += (size_t)P.a_slabs * kSlabBytes;
-    s.b = p; p += (size_t)P.n_stages * (P.stage_bytes / cg);
-    s.tblF = (float*)p; p += kTblF;
-    s.tblV = (float*)p; p += kTblV;
-    float* f = (float*)p;
-    s.z = f; s.sg = f + kMaxGroupPts; s.al0 = f + 2 * kMaxGroupPts; s.al1 = f + 3 * kMaxGroupPts; s.al2 = f + 4 * kMaxGroupPts;
-    s.sn = f + 5 * kMaxGroupPts; s.bt = f + 6 * kMaxGroupPts; s.wt = f + 7 * kMaxGroupPts;
-    p += 8 * kMaxGroupPts * 4;
-    s.sunb = (float*)p; p += kMaxGroupRays * 256 * 4;
-    s.betab = (float*)p; p += kMaxGroupRays * 256 * 4;
-    s.skyc = (float*)p; p += 64;
-    s.consts = (float*)p; p += 32;
-    s.full = (uint64_t*)p; p += 8 * 8;
-    s.empty = (uint64_t*)p; p += 8 * 8;
-    s.peer_full = (uint64_t*)p; p += 8 * 8;
-    s.acc_full = (uint64_t*)p; p += 8;
-    s.a_ready = (uint64_t*)p; p += 8;
-    s.tmem_ptr = (uint32_t*)p;
-    return s;
-}
-
-__device__ __forceinline__ int group_points(const TcArgs& A, int grp) {
-    int r0 = grp * A.G; int n = A.R - r0; if (n > A.G) n = A.G; return n * A.S;
-}
-
-// byte address of the 16-byte chunk holding k..k+7 (k % 8 == 0) of `row` in the swizzled A tile
-__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int row, int k) {
-    return a_base + (uint32_t)(k >> 6) * kSlabBytes + (uint32_t)row * 128u + ((((uint32_t)(k >> 3) & 7u) ^ ((uint32_t)row & 7u)) << 4);
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// store 32 consecutive activations (k0 % 32 == 0) of one row as fp16
-__device__ __forceinline__ void store_act32(uint32_t a_base, int row, int k0, const float* v) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float* x = v + c * 8;
-        sts128(a_chunk_addr(a_base, row, k0 + c * 8), pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
-    }
-}
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// cooperative copy (all epilogue threads) of `bytes` (multiple of 16) from global to shared with cp.async
-__device__ __forceinline__ void table_copy(void* dst, const void* src, int bytes, int tid_e) {
-    for (int o = tid_e * 16; o < bytes; o += kEpiThreads * 16) cp_async16((char*)dst + o, (const char*)src + o);
-}
-
-
-// Shared-memory table read that the compiler may schedule freely (no "memory" clobber, so reads of a block
-// pipeline instead of paying the LDS latency one by one).  `tok` is a value produced by fresh_token() AFTER the
-// barrier that published the table: the data dependence keeps the read below that barrier and keeps reads of
-// different table generations (same address, next layer) from being merged.
-__device__ __forceinline__ float4 lds128(uint32_t addr, uint32_t tok) {
-    float4 r;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+0];  // gen %5" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr), "r"(tok));
-    return r;
-}
-__device__ __forceinline__ uint32_t fresh_token(uint32_t x) {
-    uint32_t t;
-    asm volatile("mov.u32 %0, %1;" : "=r"(t) : "r"(x) : "memory");
-    return t;
-}
-
 // Epilogue of one 32-column block of one row: v = fp32 accumulators of columns n0..n0+31.
 // Tables live in shared memory (32-bit addresses): tF = [N] floats (F1) or [N][4] (F4), tV = [N] extra vector.
+// Training mode (ys != nullptr): the pre-activations go to the yb stash and activations that are consumed in
+// registers (first layers of the rgb / beta heads, last sun layer) go to their atoms stash.
+struct EpiStash { unsigned char *y0, *y1, *act0, *act1; int gt; };     // 0: first column half of HEADA (beta) / every other kind
+
 #define SIN_(x) ((dbg & 1) ? (x) : __sinf(x))
+__device__ __forceinline__ void sin32(int dbg, float* v, unsigned char* yarr, int gt, int F, int n0, int row) {
+    if (yarr) yb_store32(yb_slot(yarr, gt, F, n0, row), v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = SIN_(v[i]);
+}
 __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool skip, bool last, int has_beta, int n0, int H2, float* v,
                                           uint32_t a_base, int row, uint32_t tF, uint32_t tV, uint32_t sunb_row, uint32_t betab_row,
-                                          float px, float py, float pz,
+                                          float px, float py, float pz, const EpiStash& es,
                                           float& sig_dot, float& beta_dot, float& rgb0, float& rgb1, float& rgb2, float& sun_dot) {
+    const int H = 2 * H2;
     if (kind == GK_TRUNK) {
         if (skip) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
-                v[i] = SIN_(v[i] + fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x))));
+                v[i] += fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x)));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
-                v[i] = SIN_(v[i] + b.x); v[i + 1] = SIN_(v[i + 1] + b.y); v[i + 2] = SIN_(v[i + 2] + b.z); v[i + 3] = SIN_(v[i + 3] + b.w);
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
         }
+        sin32(dbg, v, es.y0, es.gt, H, n0, row);
         if (last) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -345,49 +249,56 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 float4 b = lds128(betab_row + (uint32_t)(n0 + i) * 4u, tok);
-                float a0 = SIN_(v[i] + b.x), a1 = SIN_(v[i + 1] + b.y), a2 = SIN_(v[i + 2] + b.z), a3 = SIN_(v[i + 3] + b.w);
-                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i) * 16u, tok).y, a0, beta_dot);
-                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i + 1) * 16u, tok).y, a1, beta_dot);
-                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i + 2) * 16u, tok).y, a2, beta_dot);
-                beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i + 3) * 16u, tok).y, a3, beta_dot);
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
+            sin32(dbg, v, es.y0, es.gt, H2, n0, row);
+            if (es.act0) atom_store32(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i) * 16u, tok).y, v[i], beta_dot);
         } else {
+            const int m0 = has_beta ? n0 - H2 : n0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += lds128(tF + (uint32_t)(n0 + i) * 16u, tok).x;
+            sin32(dbg, v, es.y1, es.gt, H2, m0, row);
+            if (es.act1) atom_store32(es.act1, es.gt, (H2 + 63) >> 6, row, m0, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
-                float a = SIN_(v[i] + w.x);
-                rgb0 = fmaf(w.y, a, rgb0); rgb1 = fmaf(w.z, a, rgb1); rgb2 = fmaf(w.w, a, rgb2);
+                rgb0 = fmaf(w.y, v[i], rgb0); rgb1 = fmaf(w.z, v[i], rgb1); rgb2 = fmaf(w.w, v[i], rgb2);
             }
         }
     } else if (kind == GK_SUN1) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             float4 b = lds128(sunb_row + (uint32_t)(n0 + i) * 4u, tok);
-            v[i] = SIN_(v[i] + b.x); v[i + 1] = SIN_(v[i + 1] + b.y); v[i + 2] = SIN_(v[i + 2] + b.z); v[i + 3] = SIN_(v[i + 3] + b.w);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
+        sin32(dbg, v, es.y0, es.gt, H2, n0, row);
         if (!(dbg & 4)) store_act32(a_base, row, n0, v);
-    } else if (kind == GK_SUN2) {
+    } else {   // GK_SUN2 / GK_SUN3
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
-            v[i] = SIN_(v[i] + b.x); v[i + 1] = SIN_(v[i + 1] + b.y); v[i + 2] = SIN_(v[i + 2] + b.z); v[i + 3] = SIN_(v[i + 3] + b.w);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
-        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
-    } else {   // GK_SUN3
+        sin32(dbg, v, es.y0, es.gt, H2, n0, row);
+        if (kind == GK_SUN2) { if (!(dbg & 4)) store_act32(a_base, row, n0, v); }
+        else {
+            if (es.act0) atom_store32(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok), w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
-            sun_dot = fmaf(w.x, SIN_(v[i] + b.x), sun_dot); sun_dot = fmaf(w.y, SIN_(v[i + 1] + b.y), sun_dot);
-            sun_dot = fmaf(w.z, SIN_(v[i + 2] + b.z), sun_dot); sun_dot = fmaf(w.w, SIN_(v[i + 3] + b.w), sun_dot);
+            for (int i = 0; i < 32; i += 4) {
+                float4 w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
+                sun_dot = fmaf(w.x, v[i], sun_dot); sun_dot = fmaf(w.y, v[i + 1], sun_dot);
+                sun_dot = fmaf(w.z, v[i + 2], sun_dot); sun_dot = fmaf(w.w, v[i + 3], sun_dot);
+            }
         }
     }
 }
-
 #undef SIN_
 // CG = 1: one CTA per 128-point tile.  CG = 2: CTA pair (cta_group::2): two SMs run two tiles in lockstep, the
 // leader issues M=256 MMAs that read each CTA's own activation tile and HALF of every weight tile from each
 // CTA's shared memory, so each SM streams / buffers only half of the weights.
-template <int CG>
+template <int CG, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -563,6 +474,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         pz = __fadd_rn(ray[2], __fmul_rn(ray[A.dir_col + 2], zz));
                     }
                 }
+                const int gt = grp * tiles_per_group + t;         // global tile id (stash index)
+                unsigned char* const sb = TRAIN ? A.stash_base : nullptr;     // compile-time null in the inference instantiation
+                if (sb && half == 0) {
+                    // extra input block of the weight-gradient GEMMs: [x y z | sun_d | t_emb | 1 | 0 ...] (64 fp16 per point)
+                    float e[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) e[i] = 0.f;
+                    if (valid) {
+                        const float* sd = A.aux ? A.aux + (size_t)(r0 + rl) * 3 : A.rays + (size_t)(r0 + rl) * A.ray_cols + aux_col;
+                        e[0] = px; e[1] = py; e[2] = pz; e[3] = sd[0]; e[4] = sd[1]; e[5] = sd[2]; e[10] = 1.f;
+                        if (P.has_beta) {
+                            const float* te = A.t_emb + (size_t)(r0 + rl) * P.tau;
+                            e[6] = te[0]; if (P.tau > 1) e[7] = te[1]; if (P.tau > 2) e[8] = te[2]; if (P.tau > 3) e[9] = te[3];
+                        }
+                    }
+                    unsigned char* ea = sb + A.stash.e;
+                    *reinterpret_cast<uint4*>(atom_chunk(ea, gt, 1, row, 0)) = make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
+                    *reinterpret_cast<uint4*>(atom_chunk(ea, gt, 1, row, 8)) = make_uint4(pack_half2(e[8], e[9]), pack_half2(e[10], e[11]), 0u, 0u);
+#pragma unroll
+                    for (int c = 2; c < 8; ++c) *reinterpret_cast<uint4*>(atom_chunk(ea, gt, 1, row, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
+                }
                 const uint32_t sunb_row = smem_u32(sm.sunb) + (uint32_t)(rl * H2) * 4u;
                 const uint32_t betab_row = smem_u32(sm.betab) + (uint32_t)(rl * H2) * 4u;
                 // ---- trunk layer 0 on CUDA cores: sin(30 (W0 x + b0)), K = 3 (satnerf.py:105-106) ----
@@ -576,12 +508,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     for (int i = 0; i < 32; ++i) {
                         float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok0);
                         float y = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
-                        v[i] = __sinf(__fmul_rn(30.0f, y));
+                        v[i] = __fmul_rn(30.0f, y);
                     }
+                    if (sb) yb_store32(yb_slot(sb + A.stash.y[0], gt, H, n0, row), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i]);
                     store_act32(a_base, row, n0, v);
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, kEpiThreads);                  // everyone is done with the layer-0 table
+                if (sb && tid_e == 0) { bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
                 {   const TcGemm& g0 = P.g[0];
                     if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
                     if (g0.has_vec) table_copy(sm.tblV, T + g0.vec_off, g0.N * 4, tid_e); }
@@ -592,6 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 for (int gi = 0; gi < P.n_gemms; ++gi) {
                     const TcGemm& g = P.g[gi];
                     cp_async_wait_all();
+                    if (sb && tid_e == 0) bulk_wait_read();      // the stash copy of the previous activation tile has left shared memory
                     named_bar_sync(1, kEpiThreads);              // tables of this GEMM are in shared memory
                     TC_MARK(gi, 0);
                     mbar_wait(sm.acc_full, acc_ph, 4); acc_ph ^= 1;
@@ -601,17 +538,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     // this warp's 32-column blocks: n0 = 32*half, + 32*kEpiSub, ...
                     const int kind = g.kind, N = g.N;
                     const bool skip = g.skip != 0, last = g.last != 0;
+                    EpiStash es; es.gt = gt; es.y0 = es.y1 = es.act0 = es.act1 = nullptr;
+                    if (sb) {
+                        if (kind == GK_TRUNK) es.y0 = sb + A.stash.y[gi + 1];
+                        else if (kind == GK_HEADA) { es.y0 = sb + A.stash.b1y; es.act0 = sb + A.stash.b1; es.y1 = sb + A.stash.r1y; es.act1 = sb + A.stash.r1; }
+                        else if (kind == GK_SUN1) es.y0 = sb + A.stash.s1y;
+                        else if (kind == GK_SUN2) es.y0 = sb + A.stash.s2y;
+                        else if (kind == GK_SUN3) { es.y0 = sb + A.stash.s3y; es.act0 = sb + A.stash.s3; }
+                    }
                     for (int n0 = half * 32; n0 < N; n0 += 32 * kEpiSub) {
                         float va[32];
                         if (!(A.dbg & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
                         else { for (int i = 0; i < 32; ++i) va[i] = 0.01f * i; }
-                        epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz,
+                        epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz, es,
                                   sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
                     }
                     tc_fence_before();
                     fence_proxy_async_smem();
                     named_bar_sync(1, kEpiThreads);              // all TMEM reads / A writes / table reads of this GEMM done
                     TC_MARK(gi, 2);
+                    if (sb && tid_e == 0) {                      // dump the activation tile this GEMM produced (A-tile image = atoms)
+                        const int fgs2 = (H2 + 63) >> 6;
+                        if (kind == GK_TRUNK) { bulk_s2g(sb + A.stash.a[gi + 1] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
+                        else if (kind == GK_FEAT) { bulk_s2g(sb + A.stash.feat + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
+                        else if (kind == GK_SUN1) { bulk_s2g(sb + A.stash.s1 + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit(); }
+                        else if (kind == GK_SUN2) { bulk_s2g(sb + A.stash.s2 + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit(); }
+                    }
                     if (gi + 1 < P.n_gemms) {
                         const TcGemm& gn = P.g[gi + 1];
                         if (gn.fmt != TF_NONE) table_copy(sm.tblF, T + gn.tbl_off, gn.N * gn.fmt * 4, tid_e);
@@ -621,6 +573,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 }
                 // ---- head outputs of this point: combine the partial dot products of the kEpiSub column interleaves.
                 //      The activation tile is dead here (every MMA that read it has completed), so it is the scratch. ----
+                if (sb && tid_e == 0) bulk_wait_read();
+                named_bar_sync(1, kEpiThreads);
                 float* dots = reinterpret_cast<float*>(sm.a) + (size_t)((half * kTile + row) * 8);
                 if (half != 0) { dots[0] = sig_dot; dots[1] = beta_dot; dots[2] = rgb0; dots[3] = rgb1; dots[4] = rgb2; dots[5] = sun_dot; }
                 named_bar_sync(1, kEpiThreads);
@@ -715,9 +669,9 @@ static int choose_group(int S) {
 int tc_workspace(const FieldLayout& L, const snb_pass_desc* p, bool backward, size_t* bytes) {
     *bytes = 0;
     if (!tc_supported(L, p)) return 0;
+    if (backward) return tc_bwd_workspace(L, p, bytes);
     TcProgram P; int nfl = build_program(L, &P);
     *bytes = (size_t)P.tables_base + (size_t)nfl * 4 + 1024;
-    (void)backward;
     return 0;
 }
 
@@ -754,6 +708,8 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     A.packed = (unsigned char*)workspace;
     A.R = p->n_rays; A.S = p->n_samples; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
     A.G = choose_group(A.S); A.n_groups = (A.R + A.G - 1) / A.G;
+    A.stash_base = (unsigned char*)io->stash;
+    if (A.stash_base) { int tpg = (A.G * A.S + kTile - 1) / kTile; stash_layout(L, A.n_groups * tpg, tpg, &A.stash); }
     { const char* e = getenv("SNB_TC_DBG"); A.dbg = e ? atoi(e) : 0; }
 
     MiscOffsets M; memset(&M, 0, sizeof(M));
@@ -766,8 +722,10 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     SNB_CHECK_LAUNCH();
     tc_pack_misc_kernel<<<8, 256, 0, st>>>(P, M, io->params, A.packed);
     SNB_CHECK_LAUNCH();
+    const bool train = A.stash_base != nullptr;
     if (cg == 2) {
-        SNB_CUDA(cudaFuncSetAttribute(tc_render_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kern = train ? tc_render_kernel<2, true> : tc_render_kernel<2, false>;
+        SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n_pairs = (A.n_groups + 1) / 2, max_pairs = sm_count / 2;
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(kThreads);
@@ -775,14 +733,24 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        SNB_CUDA(cudaLaunchKernelEx(&cfg, tc_render_kernel<2>, A));
+        SNB_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
         ++g_launches;
     } else {
-        SNB_CUDA(cudaFuncSetAttribute(tc_render_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        auto kern = train ? tc_render_kernel<1, true> : tc_render_kernel<1, false>;
+        SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = A.n_groups < sm_count ? A.n_groups : sm_count;
-        tc_render_kernel<1><<<grid, kThreads, smem, st>>>(A);
+        kern<<<grid, kThreads, smem, st>>>(A);
         SNB_CHECK_LAUNCH();
     }
+    return 0;
+}
+
+int tc_stash_bytes(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes) {
+    *bytes = 0;
+    if (!tc_supported(L, p)) return 0;
+    int G = choose_group(p->n_samples), tpg = (G * p->n_samples + kTile - 1) / kTile, groups = (p->n_rays + G - 1) / G;
+    TcStash S; stash_layout(L, groups * tpg, tpg, &S);
+    *bytes = (size_t)S.total + 1024;
     return 0;
 }
 
@@ -792,8 +760,6 @@ int tc_debug_read(void* dst, size_t bytes) {
     return 0;
 }
 
-int tc_render_backward(const FieldLayout&, const snb_pass_desc*, const snb_render_io*, const snb_render_grads*, void*, size_t, cudaStream_t) {
-    return 1;   // round 1: gradients of the tensor-core forward are taken by the fp32 CUDA-core backward chain
-}
+
 
 }  // namespace snb

@@ -51,9 +51,16 @@ class _Pass(torch.autograd.Function):
         stash = {"sigma": torch.empty(R, S, device=dev, dtype=torch.float32)}
         if variant == "nerf":
             stash["nerf_rgb"] = torch.empty(R, S, 3, device=dev, dtype=torch.float32)
+        # training: the tensor-core forward stashes its activations for the tensor-core backward (the fp32 path recomputes)
+        act_stash = None
+        if any(ctx.needs_input_grad) and cfg["precision"] == capi.FP16_TC:
+            nbytes = capi.render_stash_bytes(field.desc, pd)
+            if nbytes:
+                act_stash = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         tensors = dict(params=field.flat_params(), rays=rays, z_vals=z, t_emb=t_emb,
-                       noise=noise if cfg["noise_std"] != 0 else None, xyz=xyz, aux_dir=aux_dir, **outs, **stash)
+                       noise=noise if cfg["noise_std"] != 0 else None, xyz=xyz, aux_dir=aux_dir, stash=act_stash, **outs, **stash)
         capi.render_forward(field.desc, pd, tensors)
+        ctx.act_stash = act_stash
         ctx.field, ctx.pd, ctx.variant = field, pd, variant
         ctx.keys = list(outs)
         ctx.use_noise = cfg["noise_std"] != 0
@@ -75,7 +82,7 @@ class _Pass(torch.autograd.Function):
         g_flat = torch.zeros_like(flat)
         g_t = torch.empty_like(t_emb) if t_emb is not None else None
         tensors = dict(params=flat, rays=rays, z_vals=z, t_emb=t_emb, noise=noise if ctx.use_noise else None,
-                       xyz=xyz, aux_dir=aux_dir, **saved)
+                       xyz=xyz, aux_dir=aux_dir, stash=ctx.act_stash, **saved)
         grads = {"g_params": g_flat, "g_t_emb": g_t}
         for k, g in zip(ctx.keys, gouts):
             grads["g_" + k] = None if g is None else g.to(torch.float32).contiguous()
