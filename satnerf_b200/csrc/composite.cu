@@ -116,6 +116,102 @@ __global__ void composite_bwd_kernel(CompositeBwdArgs a) {
     }
 }
 
+// Same gradient, one WARP per ray: lanes hold samples (coalesced loads), the suffix sum of the transmittance
+// recurrence is a warp shuffle scan.  Also emits per-ray sums of every d_head channel (ray_sums: (R, 16) floats),
+// which the head-bias / sky-colour gradients reduce further.  Used by the tensor-core backward.
+__global__ void composite_bwd_warp_kernel(CompositeBwdArgs a, float* __restrict__ ray_sums) {
+    const int lane = threadIdx.x & 31;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= a.R) return;
+    const int S = a.S, C = a.C;
+    const size_t base = (size_t)r * S;
+    const bool sat = C >= 8;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (a.g_rgb) { g0 = a.g_rgb[r * 3]; g1 = a.g_rgb[r * 3 + 1]; g2 = a.g_rgb[r * 3 + 2]; }
+    const float gd = a.g_depth ? a.g_depth[r] : 0.f;
+    const float* col = sat ? a.albedo : a.nerf_rgb;
+    if (sat && a.g_rgb) {                              // clamp mask from the un-clamped colour
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        for (int i = lane; i < S; i += 32) {
+            size_t p = base + i; float w = a.weights[p], s = a.sun[p];
+            c0 += w * col[p * 3] * (s + (1.f - s) * a.sky[p * 3]);
+            c1 += w * col[p * 3 + 1] * (s + (1.f - s) * a.sky[p * 3 + 1]);
+            c2 += w * col[p * 3 + 2] * (s + (1.f - s) * a.sky[p * 3 + 2]);
+        }
+        for (int off = 16; off; off >>= 1) { c0 += __shfl_xor_sync(~0u, c0, off); c1 += __shfl_xor_sync(~0u, c1, off); c2 += __shfl_xor_sync(~0u, c2, off); }
+        if (!(c0 >= 0.f && c0 <= 1.f)) g0 = 0.f;
+        if (!(c1 >= 0.f && c1 <= 1.f)) g1 = 0.f;
+        if (!(c2 >= 0.f && c2 <= 1.f)) g2 = 0.f;
+    }
+    float carry = 0.f;                                  // sum over samples beyond the current 32-sample window
+    float sums[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int hi = ((S + 31) / 32) * 32; hi > 0; hi -= 32) {
+        const int i = hi - 32 + lane;
+        const bool ok = i < S;
+        size_t p = base + (ok ? i : 0);
+        float w = 0.f, T = 0.f, sg = 0.f, delta = 0.f, act = 0.f, e = 1.f, alpha = 0.f, q = 1.f, G = 0.f, gT = 0.f, zi = 0.f;
+        float c_r = 0.f, c_g = 0.f, c_b = 0.f, s = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, i0 = 1.f, i1 = 1.f, i2 = 1.f;
+        if (ok) {
+            w = a.weights[p]; T = a.transparency[p]; sg = a.sigma[p]; zi = a.z[p];
+            float nz = a.noise ? a.noise[p] * a.noise_std : 0.f;
+            delta = i < S - 1 ? __fsub_rn(a.z[p + 1], zi) : 1e10f;
+            act = sg + nz; e = expf(-delta * fmaxf(act, 0.f)); alpha = 1.0f - e; q = (1.0f - alpha) + 1e-10f;
+            c_r = col[p * 3]; c_g = col[p * 3 + 1]; c_b = col[p * 3 + 2];
+            if (sat) {
+                s = a.sun[p]; k0 = a.sky[p * 3]; k1 = a.sky[p * 3 + 1]; k2 = a.sky[p * 3 + 2];
+                i0 = s + (1.f - s) * k0; i1 = s + (1.f - s) * k1; i2 = s + (1.f - s) * k2;
+            }
+            G = (a.g_weights ? a.g_weights[p] : 0.f) + gd * zi + g0 * c_r * i0 + g1 * c_g * i1 + g2 * c_b * i2;
+            gT = a.g_transparency ? a.g_transparency[p] : 0.f;
+        }
+        // suffix (exclusive) sum of term_k = (G_k alpha_k + gT_k) T_k over k > i
+        float term = ok ? (G * alpha + gT) * T : 0.f;
+        float incl = term;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { float o = __shfl_down_sync(~0u, incl, off); if (lane + off < 32) incl += o; }
+        const float suffix = incl - term + carry;
+        carry += __shfl_sync(~0u, incl, 0);
+        if (ok) {
+            float d_alpha = G * T - suffix / q;
+            float d_sigma = act > 0.f ? d_alpha * (delta * e) : 0.f;
+            float* out = a.d_head + p * C;
+            float dc0 = g0 * w * i0, dc1 = g1 * w * i1, dc2 = g2 * w * i2;
+            if (sat && a.g_albedo) { dc0 += a.g_albedo[p * 3]; dc1 += a.g_albedo[p * 3 + 1]; dc2 += a.g_albedo[p * 3 + 2]; }
+            float s0 = (c_r + 0.001f) / 1.002f, s1 = (c_g + 0.001f) / 1.002f, s2 = (c_b + 0.001f) / 1.002f;
+            float o0 = dc0 * 1.002f * s0 * (1.f - s0), o1 = dc1 * 1.002f * s1 * (1.f - s1), o2 = dc2 * 1.002f * s2 * (1.f - s2);
+            float o3 = d_sigma * (-expm1f(-sg));
+            out[0] = o0; out[1] = o1; out[2] = o2; out[3] = o3;
+            sums[0] += o0; sums[1] += o1; sums[2] += o2; sums[3] += o3;
+            if (sat) {
+                float ds = g0 * w * c_r * (1.f - k0) + g1 * w * c_g * (1.f - k1) + g2 * w * c_b * (1.f - k2);
+                if (a.g_sun) ds += a.g_sun[p];
+                float o4 = ds * s * (1.f - s);
+                float dk0 = g0 * w * c_r * (1.f - s), dk1 = g1 * w * c_g * (1.f - s), dk2 = g2 * w * c_b * (1.f - s);
+                if (a.g_sky) { dk0 += a.g_sky[p * 3]; dk1 += a.g_sky[p * 3 + 1]; dk2 += a.g_sky[p * 3 + 2]; }
+                float o5 = dk0 * k0 * (1.f - k0), o6 = dk1 * k1 * (1.f - k1), o7 = dk2 * k2 * (1.f - k2);
+                out[4] = o4; out[5] = o5; out[6] = o6; out[7] = o7;
+                sums[4] += o4; sums[5] += o5; sums[6] += o6; sums[7] += o7;
+                if (C == 9) { float b = a.beta[p]; float o8 = (a.g_beta ? a.g_beta[p] : 0.f) * (-expm1f(-b)); out[8] = o8; sums[8] += o8; }
+            }
+        }
+    }
+    if (ray_sums) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            float v = sums[c];
+            for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(~0u, v, off);
+            if (lane == 0) ray_sums[(size_t)r * 16 + c] = v;
+        }
+    }
+}
+
+int launch_composite_bwd_warp(const CompositeBwdArgs& a, float* ray_sums, cudaStream_t st) {
+    if (a.R == 0) return 0;
+    composite_bwd_warp_kernel<<<ceil_div(a.R, 4), 128, 0, st>>>(a, ray_sums);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
 int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st) {
     if (a.R == 0) return 0;
     composite_fwd_kernel<<<ceil_div(a.R, 128), 128, 0, st>>>(a);

@@ -23,5 +23,7 @@ struct CompositeBwdArgs {
 
 int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st);
 int launch_composite_bwd(const CompositeBwdArgs& a, cudaStream_t st);
+// warp-per-ray variant; ray_sums (R,16): per-ray sums of the d_head channels (nullable)
+int launch_composite_bwd_warp(const CompositeBwdArgs& a, float* ray_sums, cudaStream_t st);
 
 }  // namespace snb

@@ -366,7 +366,7 @@ struct DwOut {
 __global__ void dw_finalize_kernel(const DwOut* __restrict__ outs, const float* __restrict__ partial, const float* __restrict__ absmax, float* __restrict__ G) {
     const DwOut o = outs[blockIdx.x];
     const float inv = 1.0f / loss_scale(*absmax);
-    for (int e = threadIdx.x; e < 128 * o.N; e += blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 128 * o.N; e += gridDim.y * blockDim.x) {
         const int r = e / o.N, c = e - r * o.N;
         if (o.m0 + r >= o.M) continue;
         long long dst = -1;
@@ -384,40 +384,40 @@ __global__ void dw_finalize_kernel(const DwOut* __restrict__ outs, const float* 
     }
 }
 
-// biases of the N<=3 heads: column sums of d_head over the points (fixed-order tree per column)
-__global__ void head_bias_kernel(const float* __restrict__ d_head, long long P, int C, int col, float* __restrict__ dst) {
+// biases of the N<=3 heads: sums over the rays of the per-ray channel sums (fixed-order tree, double accumulation).
+// block c handles channel c of ray_sums (R,16); dst[c] < 0: channel not wanted.
+struct BiasDst { long long off[9]; };
+__global__ void head_bias_kernel(const float* __restrict__ ray_sums, int R, BiasDst d, float* __restrict__ G) {
     __shared__ double sh[256];
+    const int c = blockIdx.x;
+    if (d.off[c] < 0) return;
     double acc = 0.0;
-    for (long long p = threadIdx.x; p < P; p += blockDim.x) acc += (double)d_head[p * C + col];
+    for (int r = threadIdx.x; r < R; r += blockDim.x) acc += (double)ray_sums[(size_t)r * 16 + c];
     sh[threadIdx.x] = acc; __syncthreads();
     for (int s = 128; s; s >>= 1) { if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
-    if (threadIdx.x == 0) *dst += (float)sh[0];
+    if (threadIdx.x == 0) G[d.off[c]] += (float)sh[0];
 }
 
-// sky_color MLP (per ray, satnerf.py:138-143): gradients of sky0 (H2 x 3) and sky2 (3 x H2); block b owns hidden units n = b*blockDim + tid
-__global__ void sky_bwd_kernel(const float* __restrict__ d_head, int C, const float* __restrict__ rays, int ray_cols, const float* __restrict__ aux,
-                               int R, int S, int H2, const float* __restrict__ W, long long w0, long long b0, long long w2, float* __restrict__ G, long long gb2) {
+// sky_color MLP (per ray, satnerf.py:138-143): gradients of sky0 (H2 x 3) and sky2 (3 x H2) from the per-ray sums of the
+// sky channels; thread n owns hidden unit n and walks the rays in order (deterministic).
+__global__ void sky_bwd_kernel(const float* __restrict__ ray_sums, const float* __restrict__ rays, int ray_cols, const float* __restrict__ aux,
+                               int R, int H2, const float* __restrict__ W, long long w0, long long b0, long long w2, float* __restrict__ G) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool on = n < H2;
-    float w0x = 0, w0y = 0, w0z = 0, bb = 0, v0 = 0, v1 = 0, v2 = 0;
-    if (on) { w0x = W[w0 + n * 3]; w0y = W[w0 + n * 3 + 1]; w0z = W[w0 + n * 3 + 2]; bb = W[b0 + n]; v0 = W[w2 + n]; v1 = W[w2 + H2 + n]; v2 = W[w2 + 2 * H2 + n]; }
-    float gw2_0 = 0, gw2_1 = 0, gw2_2 = 0, gw0x = 0, gw0y = 0, gw0z = 0, gb0 = 0, gbias0 = 0, gbias1 = 0, gbias2 = 0;
+    if (n >= H2) return;
+    const float w0x = W[w0 + n * 3], w0y = W[w0 + n * 3 + 1], w0z = W[w0 + n * 3 + 2], bb = W[b0 + n];
+    const float v0 = W[w2 + n], v1 = W[w2 + H2 + n], v2 = W[w2 + 2 * H2 + n];
+    float gw2_0 = 0, gw2_1 = 0, gw2_2 = 0, gw0x = 0, gw0y = 0, gw0z = 0, gb0 = 0;
     for (int r = 0; r < R; ++r) {
-        float d0 = 0, d1 = 0, d2 = 0;
-        for (int i = 0; i < S; ++i) { const float* dh = d_head + ((size_t)r * S + i) * C; d0 += dh[5]; d1 += dh[6]; d2 += dh[7]; }
+        const float d0 = ray_sums[(size_t)r * 16 + 5], d1 = ray_sums[(size_t)r * 16 + 6], d2 = ray_sums[(size_t)r * 16 + 7];
         const float* sd = aux ? aux + (size_t)r * 3 : rays + (size_t)r * ray_cols + 8;
         float pre = fmaf(w0z, sd[2], fmaf(w0y, sd[1], fmaf(w0x, sd[0], bb)));
         float h = fmaxf(pre, 0.f);
         gw2_0 = fmaf(d0, h, gw2_0); gw2_1 = fmaf(d1, h, gw2_1); gw2_2 = fmaf(d2, h, gw2_2);
         float dh_ = pre > 0.f ? fmaf(d2, v2, fmaf(d1, v1, d0 * v0)) : 0.f;
         gw0x = fmaf(dh_, sd[0], gw0x); gw0y = fmaf(dh_, sd[1], gw0y); gw0z = fmaf(dh_, sd[2], gw0z); gb0 += dh_;
-        gbias0 += d0; gbias1 += d1; gbias2 += d2;
     }
-    if (on) {
-        G[w2 + n] += gw2_0; G[w2 + H2 + n] += gw2_1; G[w2 + 2 * H2 + n] += gw2_2;
-        G[w0 + n * 3] += gw0x; G[w0 + n * 3 + 1] += gw0y; G[w0 + n * 3 + 2] += gw0z; G[b0 + n] += gb0;
-    }
-    if (n == 0) { G[gb2] += gbias0; G[gb2 + 1] += gbias1; G[gb2 + 2] += gbias2; }
+    G[w2 + n] += gw2_0; G[w2 + H2 + n] += gw2_1; G[w2 + 2 * H2 + n] += gw2_2;
+    G[w0 + n * 3] += gw0x; G[w0 + n * 3 + 1] += gw0y; G[w0 + n * 3 + 2] += gw0z; G[b0 + n] += gb0;
 }
 
 __global__ void ray_sum_t_kernel(const float* __restrict__ per_point, float* __restrict__ per_ray, int n_rays, int S, int D) {
@@ -501,7 +501,7 @@ static void fwd_stash_layout(const FieldLayout& L, int n_tiles, int tpg, TcStash
 struct BwdPlan {
     int G, groups, tpg, n_tiles, ks, n_outs, n_items;
     TcBwdStash bs;
-    size_t off_dhead, off_absmax, off_dt, off_packed, packed_bytes, off_bstash, off_items, off_outs, off_partial, partial_floats, total;
+    size_t off_dhead, off_raysums, off_absmax, off_dt, off_packed, packed_bytes, off_bstash, off_items, off_outs, off_partial, partial_floats, total;
 };
 
 static void plan_bwd(const FieldLayout& L, const snb_pass_desc* p, const TcProgram& P, int n_tbl_floats, BwdPlan* B) {
@@ -528,6 +528,7 @@ static void plan_bwd(const FieldLayout& L, const snb_pass_desc* p, const TcProgr
     B->ks = ks; B->n_items = outs * ks;
     Arena ar(nullptr, 0);
     B->off_dhead = ar.off; ar.take<float>((size_t)p->n_rays * S * L.n_channels);
+    B->off_raysums = ar.off; ar.take<float>((size_t)p->n_rays * 16);
     B->off_absmax = ar.off; ar.take<float>(64);
     B->off_dt = ar.off; ar.take<float>((size_t)p->n_rays * S * (L.t_dims > 0 ? L.t_dims : 1));
     B->packed_bytes = (size_t)P.tables_base + (size_t)n_tbl_floats * 4 + 256;
@@ -578,7 +579,8 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     b.sky = io->sky; b.beta = io->beta; b.nerf_rgb = io->nerf_rgb;
     b.g_rgb = g->g_rgb; b.g_depth = g->g_depth; b.g_weights = g->g_weights; b.g_transparency = g->g_transparency;
     b.g_albedo = g->g_albedo; b.g_sun = g->g_sun; b.g_sky = g->g_sky; b.g_beta = g->g_beta; b.d_head = d_head;
-    SNB_TRY(launch_composite_bwd(b, st));
+    float* ray_sums = (float*)(ws + B.off_raysums);
+    SNB_TRY(launch_composite_bwd_warp(b, ray_sums, st));
     SNB_CUDA(cudaMemsetAsync(absmax, 0, 256, st));
     absmax_kernel<<<148, 256, 0, st>>>(d_head, Ptot * C, absmax);
     SNB_CHECK_LAUNCH();
@@ -662,14 +664,14 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     SNB_TRY(launch_dw(d_items, (int)items.size(), nullptr, partial, st));
 
     // 4. reductions / scatter into the flat gradient
-    dw_finalize_kernel<<<(unsigned)outs.size(), 256, 0, st>>>(d_outs, partial, absmax, g->g_params);
+    dw_finalize_kernel<<<dim3((unsigned)outs.size(), 8), 256, 0, st>>>(d_outs, partial, absmax, g->g_params);
     SNB_CHECK_LAUNCH();
-    head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, 3, g->g_params + L.sigma.b); SNB_CHECK_LAUNCH();
-    for (int c = 0; c < 3; ++c) { head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, c, g->g_params + L.rgb2.b + c); SNB_CHECK_LAUNCH(); }
-    head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, 4, g->g_params + L.sun[3].b); SNB_CHECK_LAUNCH();
-    if (L.variant == SNB_SATNERF) { head_bias_kernel<<<1, 256, 0, st>>>(d_head, Ptot, C, 8, g->g_params + L.beta2.b); SNB_CHECK_LAUNCH(); }
-    sky_bwd_kernel<<<(H2 + 63) / 64, 64, 0, st>>>(d_head, C, io->rays, p->ray_cols, io->aux_dir, R, S, H2, io->params, L.sky0.w, L.sky0.b, L.sky2.w,
-                                                   g->g_params, L.sky2.b);
+    BiasDst bd; for (int c = 0; c < 9; ++c) bd.off[c] = -1;
+    bd.off[0] = L.rgb2.b; bd.off[1] = L.rgb2.b + 1; bd.off[2] = L.rgb2.b + 2; bd.off[3] = L.sigma.b; bd.off[4] = L.sun[3].b;
+    bd.off[5] = L.sky2.b; bd.off[6] = L.sky2.b + 1; bd.off[7] = L.sky2.b + 2;
+    if (L.variant == SNB_SATNERF) bd.off[8] = L.beta2.b;
+    head_bias_kernel<<<9, 256, 0, st>>>(ray_sums, R, bd, g->g_params); SNB_CHECK_LAUNCH();
+    sky_bwd_kernel<<<(H2 + 63) / 64, 64, 0, st>>>(ray_sums, io->rays, p->ray_cols, io->aux_dir, R, H2, io->params, L.sky0.w, L.sky0.b, L.sky2.w, g->g_params);
     SNB_CHECK_LAUNCH();
     if (A.d_t) {
         ray_sum_t_kernel<<<(R * L.t_dims + 127) / 128, 128, 0, st>>>(d_t, g->g_t_emb, R, S, L.t_dims);

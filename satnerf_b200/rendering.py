@@ -53,7 +53,7 @@ class _Pass(torch.autograd.Function):
             stash["nerf_rgb"] = torch.empty(R, S, 3, device=dev, dtype=torch.float32)
         # training: the tensor-core forward stashes its activations for the tensor-core backward (the fp32 path recomputes)
         act_stash = None
-        if any(ctx.needs_input_grad) and cfg["precision"] == capi.FP16_TC:
+        if cfg["train"] and cfg["precision"] == capi.FP16_TC:
             nbytes = capi.render_stash_bytes(field.desc, pd)
             if nbytes:
                 act_stash = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -87,6 +87,7 @@ class _Pass(torch.autograd.Function):
         for k, g in zip(ctx.keys, gouts):
             grads["g_" + k] = None if g is None else g.to(torch.float32).contiguous()
         capi.render_backward(field.desc, ctx.pd, tensors, grads)
+        field._flat_grad = g_flat       # candidate flat gradient buffer (flat_grads() checks that .grad really aliases it)
         gp, off = [], 0
         for p in field.ordered_params():
             n = p.numel()
@@ -98,7 +99,9 @@ class _Pass(torch.autograd.Function):
 def _run_pass(field, args, rays, z, t_emb, noise, sc=False, xyz=None, aux_dir=None) -> Dict[str, torch.Tensor]:
     if not z.is_cuda:
         raise RuntimeError("satnerf_b200 renders CUDA tensors only (no CPU fallback); move rays and models to the GPU")
-    cfg = {"sc": sc, "precision": _precision(args), "noise_std": float(args.noise_std)}
+    # stash activations only when a backward can follow (Function.forward itself always runs with grad mode off)
+    train = torch.is_grad_enabled() and (any(p.requires_grad for p in field.parameters()) or (t_emb is not None and t_emb.requires_grad))
+    cfg = {"sc": sc, "precision": _precision(args), "noise_std": float(args.noise_std), "train": train}
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
     outs = _Pass.apply(field, cfg, f32(rays), f32(z), f32(t_emb), f32(noise), f32(xyz), f32(aux_dir), *field.ordered_params())
     return dict(zip(_out_shapes(field.variant, z.shape[0], z.shape[1]).keys(), outs))

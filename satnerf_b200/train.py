@@ -60,7 +60,8 @@ class NeRFSystem:
 
     def configure_optimizers(self):                                            # main.py:81-94, train_utils.py:24-53
         params = [p for m in self.models.values() for p in m.parameters()]
-        self.optimizer = torch.optim.Adam(params, lr=self.args.lr, weight_decay=0)
+        # same update rule as the reference (Adam, lr, no weight decay); the fused implementation is one launch on CUDA
+        self.optimizer = torch.optim.Adam(params, lr=self.args.lr, weight_decay=0, fused=params[0].is_cuda)
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=1, gamma=0.9)   # stepped per epoch
         return self.optimizer
 
@@ -92,13 +93,9 @@ class NeRFSystem:
 
     def optimization_step(self, batch):
         """zero grads -> training_step -> backward -> [all-reduce] -> Adam (what Lightning's fit loop does)."""
-        for m in self.models.values():
-            if hasattr(m, "flat_grads"):
-                m.flat_grads(zero=True)
-            else:
-                for p in m.parameters():
-                    if p.grad is not None:
-                        p.grad.zero_()
+        for m in self.models.values():          # grads are (re)assigned as slices of one flat buffer by the render backward
+            for p in m.parameters():
+                p.grad = None
         loss, info = self.training_step(batch)
         loss.backward()
         sdist.all_reduce_gradients(self.models)
