@@ -24,3 +24,4 @@ for g in range(12):
     tot_wait += wait; tot_epi += epi
     print(f"gemm {g:2d}: wait-for-acc {wait:7d}  epilogue {epi:7d}")
 print("sum wait", tot_wait, "sum epi", tot_epi, "composite", t[61, 1] - t[61, 0], "tile total", t[11, 2] - t[60, 0])
+

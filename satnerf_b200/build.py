@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsatnerf_b200.so")
-SOURCES = ["layout.cu", "sampling.cu", "composite.cu", "simt_field.cu", "tc_field.cu", "tc_backward.cu", "tc_bwd.cu", "capi.cu"]
+SOURCES = ["layout.cu", "sampling.cu", "composite.cu", "simt_field.cu", "tc_field.cu", "tc_backward.cu", "tc_bwd.cu", "mma_rate.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-I", os.path.join(ROOT, "include"), "-I", CSRC]
