@@ -371,9 +371,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         }
                     }
         } else {
-            // Issue is effectively blocking (~140 cycles per M128xN256xK16 instruction), so everything else the issuing
-            // thread does is exposed unless it overlaps an instruction in flight: the barrier of the NEXT stage is waited
-            // for right after the first MMA of the current stage has been issued, and descriptors are 64-bit adds.
+            // Single-thread issue: per stage wait for the weight tile, issue its K-steps (descriptors are 64-bit adds on
+            // precomputed bases), commit the stage back to the producer (and the accumulator to the epilogue at the end).
             const uint64_t a_desc0 = umma_desc_k_sw128(a_base), b_desc0 = umma_desc_k_sw128(b_base);
             for (int wk = unit; wk < n_work; wk += n_units) {
                 for (int t = 0; t < tiles_per_group; ++t) {
@@ -409,46 +408,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                             __syncwarp();
                             if (++st == P.n_stages) { st = 0; ph ^= 1; }
                             if (++s == g.k_slabs) { s = 0; ++j; }
-                        }
-                    }
-        } else {
-            // Issue is effectively blocking (~140 cycles per M128xN256xK16 instruction), so everything else the issuing
-            // thread does is exposed unless it overlaps an instruction in flight: the barrier of the NEXT stage is waited
-            // for right after the first MMA of the current stage has been issued, and descriptors are 64-bit adds.
-            const uint64_t a_desc0 = umma_desc_k_sw128(a_base), b_desc0 = umma_desc_k_sw128(b_base);
-            for (int wk = unit; wk < n_work; wk += n_units) {
-                for (int t = 0; t < tiles_per_group; ++t) {
-                    for (int gi = 0; gi < P.n_gemms; ++gi) {
-                        const TcGemm& g = P.g[gi];
-                        if (lane == 0) mbar_wait(sm.a_ready, ready_ph, 2);
-                        ready_ph ^= 1;
-                        __syncwarp();
-                        tc_fence_after();
-                        const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)g.chunk_n) : umma_idesc_f16((uint32_t)g.chunk_n);
-                        const int n_st = g.n_chunks * g.k_slabs;
-                        for (int i = 0; i < n_st; ++i) {
-                            const int j = i / g.k_slabs, s = i - j * g.k_slabs;
-                            int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
-                            const uint64_t da = a_desc0 + (uint64_t)((uint32_t)s * (kSlabBytes >> 4));
-                            const uint64_t db = umma_desc_k_sw128(b_base + (uint32_t)st * stage_bytes);
-                            const uint32_t d_tm = tmem + (uint32_t)(j * g.chunk_n);
-                            const bool last = i == n_st - 1;
-                            if (mdbg && lane == 0) g_tc_dbg[(16 + i) * 4 + 0] = clock64();
-                            mbar_wait(&sm.full[st], ph, 3);
-                            if (CG == 2) mbar_wait(&sm.peer_full[st], ph, 6);
-                            tc_fence_after();
-                            if (mdbg && lane == 0) g_tc_dbg[(16 + i) * 4 + 1] = clock64();
-                            if (lane == 0) {
-                                for (int k = 0; k < ksteps; ++k) {
-                                    if (CG == 2) umma_f16_ss_2cta(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
-                                    else umma_f16_ss(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
-                                }
-                                if (CG == 2) { umma_commit_2cta(&sm.empty[st], 3); if (last) umma_commit_2cta(sm.acc_full, 3); }
-                                else { umma_commit(&sm.empty[st]); if (last) umma_commit(sm.acc_full); }
-                                if (mdbg) g_tc_dbg[(16 + i) * 4 + 2] = clock64();
-                            }
-                            __syncwarp();
-                            if (++st == P.n_stages) { st = 0; ph ^= 1; }
                         }
                     }
                 }
