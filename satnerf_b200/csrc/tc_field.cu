@@ -210,7 +210,7 @@ __device__ __forceinline__ void sin32(int dbg, float* v, unsigned char* yarr, in
 }
 __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool skip, bool last, int has_beta, int n0, int H2, float* v,
                                           uint32_t a_base, int row, uint32_t tF, uint32_t tV, uint32_t sunb_row, uint32_t betab_row,
-                                          float px, float py, float pz, const EpiStash& es,
+                                          float px, float py, float pz, const EpiStash& es, bool do_park, uint32_t park,
                                           float& sig_dot, float& beta_dot, float& rgb0, float& rgb1, float& rgb2, float& sun_dot) {
     const int H = 2 * H2;
     if (kind == GK_TRUNK) {
@@ -236,14 +236,14 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
                 sig_dot = fmaf(w.z, v[i + 2], sig_dot); sig_dot = fmaf(w.w, v[i + 3], sig_dot);
             }
         }
-        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
+        if (!(dbg & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
     } else if (kind == GK_FEAT) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
-        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
+        if (!(dbg & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
     } else if (kind == GK_HEADA) {
         if (has_beta && n0 < H2) {
 #pragma unroll
@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
         // ================= MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =================
         int st = 0; uint32_t ph = 0, ready_ph = 0;
         const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
+        const uint32_t tmem = __shfl_sync(0xffffffffu, *sm.tmem_ptr, 0);      // provably warp-uniform copy of the TMEM base
         if (CG == 2 && cta_rank == 1) {
             // the leader's MMA reads this CTA's half of every weight tile: tell it when each stage has landed
             for (int wk = unit; wk < n_work; wk += n_units)
@@ -390,20 +391,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                             const uint64_t da = a_desc0 + (uint64_t)((uint32_t)s * (kSlabBytes >> 4));
                             const uint64_t db = b_desc0 + (uint64_t)((uint32_t)st * (uint32_t)(stage_bytes >> 4));
                             const uint32_t d_tm = tmem + (uint32_t)(j * g.chunk_n);
-                            const bool last = i == n_st - 1;
                             if (lane == 0) {          // one lane polls: 31 fewer pollers of the shared-memory barrier word
                                 mbar_wait(&sm.full[st], ph, 3);
                                 if (CG == 2) mbar_wait(&sm.peer_full[st], ph, 6);
                             }
                             __syncwarp();
                             tc_fence_after();
-                            if (lane == 0) {
+                            if (elect_one()) {        // warp-uniform operands + elect: UTCHMMA takes uniform registers directly
                                 for (int k = 0; k < ksteps; ++k) {
                                     if (CG == 2) umma_f16_ss_2cta(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
                                     else umma_f16_ss(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
                                 }
-                                if (CG == 2) { umma_commit_2cta(&sm.empty[st], 3); if (last) umma_commit_2cta(sm.acc_full, 3); }
-                                else { umma_commit(&sm.empty[st]); if (last) umma_commit(sm.acc_full); }
+                                const bool chunk_done = s == g.k_slabs - 1;      // accumulator of N-chunk j is complete
+                                if (CG == 2) { umma_commit_2cta(&sm.empty[st], 3); if (chunk_done) umma_commit_2cta(sm.acc_full, 3); }
+                                else { umma_commit(&sm.empty[st]); if (chunk_done) umma_commit(sm.acc_full); }
                             }
                             __syncwarp();
                             if (++st == P.n_stages) { st = 0; ph ^= 1; }
@@ -539,17 +540,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     if (sb && tid_e == 0) bulk_wait_read();      // the stash copy of the previous activation tile has left shared memory
                     named_bar_sync(1, kEpiThreads);              // tables of this GEMM are in shared memory
                     TC_MARK(gi, 0);
-                    // one thread polls the mbarrier; the other epilogue threads park in a hardware barrier instead of
-                    // spinning on shared memory while the tensor core streams its operands from it
-                    if (tid_e == 0) mbar_wait(sm.acc_full, acc_ph, 4);
-                    acc_ph ^= 1;
-                    named_bar_sync(2, kEpiThreads);
-                    tc_fence_after();
-                    const uint32_t tok = fresh_token((uint32_t)gi);
-                    TC_MARK(gi, 1);
-                    // this warp's 32-column blocks: n0 = 32*half, + 32*kEpiSub, ...
-                    const int kind = g.kind, N = g.N;
+                    // N-chunks (<=256 columns) complete one after the other: the epilogue of chunk 0 runs while the tensor core
+                    // works on chunk 1.  Its fp16 results cannot go to the A tile yet (the MMAs still read it), so they are
+                    // parked in the drained accumulator columns and moved once the last chunk has been committed.
+                    const int kind = g.kind, N = g.N, n_chunks = g.n_chunks, chunk_n = g.chunk_n;
                     const bool skip = g.skip != 0, last = g.last != 0;
+                    const bool stores = kind == GK_TRUNK || kind == GK_FEAT || kind == GK_SUN1 || kind == GK_SUN2;
                     EpiStash es; es.gt = gt; es.y0 = es.y1 = es.act0 = es.act1 = nullptr;
                     if (sb) {
                         if (kind == GK_TRUNK) es.y0 = sb + A.stash.y[gi + 1];
@@ -558,12 +554,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         else if (kind == GK_SUN2) es.y0 = sb + A.stash.s2y;
                         else if (kind == GK_SUN3) { es.y0 = sb + A.stash.s3y; es.act0 = sb + A.stash.s3; }
                     }
-                    for (int n0 = half * 32; n0 < N; n0 += 32 * kEpiSub) {
-                        float va[32];
-                        if (!(A.dbg & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
-                        else { for (int i = 0; i < 32; ++i) va[i] = 0.01f * i; }
-                        epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz, es,
-                                  sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
+                    uint32_t tok = 0;
+                    for (int ch = 0; ch < n_chunks; ++ch) {
+                        // one thread polls the mbarrier; the others park in a hardware barrier instead of spinning on shared memory
+                        if (tid_e == 0) mbar_wait(sm.acc_full, acc_ph, 4);
+                        acc_ph ^= 1;
+                        named_bar_sync(2, kEpiThreads);
+                        tc_fence_after();
+                        if (ch == 0) { tok = fresh_token((uint32_t)gi); TC_MARK(gi, 1); }
+                        const bool final_chunk = ch == n_chunks - 1;
+                        if (final_chunk && stores && n_chunks > 1) {
+                            for (int n0 = half * 32; n0 < ch * chunk_n; n0 += 32 * kEpiSub) unpark_act32(tm_row + (uint32_t)n0, a_base, row, n0);
+                        }
+                        for (int n0 = ch * chunk_n + half * 32; n0 < (ch + 1) * chunk_n && n0 < N; n0 += 32 * kEpiSub) {
+                            float va[32];
+                            if (!(A.dbg & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
+                            else { for (int i = 0; i < 32; ++i) va[i] = 0.01f * i; }
+                            epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz, es,
+                                      stores && !final_chunk, tm_row + (uint32_t)n0,
+                                      sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
+                        }
+                        if (!final_chunk) { tmem_st_wait(); tc_fence_before(); }
                     }
                     tc_fence_before();
                     fence_proxy_async_smem();
