@@ -399,25 +399,38 @@ __global__ void head_bias_kernel(const float* __restrict__ ray_sums, int R, Bias
 }
 
 // sky_color MLP (per ray, satnerf.py:138-143): gradients of sky0 (H2 x 3) and sky2 (3 x H2) from the per-ray sums of the
-// sky channels; thread n owns hidden unit n and walks the rays in order (deterministic).
+// sky channels.  One block per hidden unit n; its threads stride over the rays and a fixed-order tree combines them
+// (deterministic).
 __global__ void sky_bwd_kernel(const float* __restrict__ ray_sums, const float* __restrict__ rays, int ray_cols, const float* __restrict__ aux,
                                int R, int H2, const float* __restrict__ W, long long w0, long long b0, long long w2, float* __restrict__ G) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= H2) return;
+    __shared__ float sh[7][128];
+    const int n = blockIdx.x;
     const float w0x = W[w0 + n * 3], w0y = W[w0 + n * 3 + 1], w0z = W[w0 + n * 3 + 2], bb = W[b0 + n];
     const float v0 = W[w2 + n], v1 = W[w2 + H2 + n], v2 = W[w2 + 2 * H2 + n];
-    float gw2_0 = 0, gw2_1 = 0, gw2_2 = 0, gw0x = 0, gw0y = 0, gw0z = 0, gb0 = 0;
-    for (int r = 0; r < R; ++r) {
+    float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // gw2[0..2], gw0[x,y,z], gb0
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
         const float d0 = ray_sums[(size_t)r * 16 + 5], d1 = ray_sums[(size_t)r * 16 + 6], d2 = ray_sums[(size_t)r * 16 + 7];
         const float* sd = aux ? aux + (size_t)r * 3 : rays + (size_t)r * ray_cols + 8;
         float pre = fmaf(w0z, sd[2], fmaf(w0y, sd[1], fmaf(w0x, sd[0], bb)));
         float h = fmaxf(pre, 0.f);
-        gw2_0 = fmaf(d0, h, gw2_0); gw2_1 = fmaf(d1, h, gw2_1); gw2_2 = fmaf(d2, h, gw2_2);
+        acc[0] = fmaf(d0, h, acc[0]); acc[1] = fmaf(d1, h, acc[1]); acc[2] = fmaf(d2, h, acc[2]);
         float dh_ = pre > 0.f ? fmaf(d2, v2, fmaf(d1, v1, d0 * v0)) : 0.f;
-        gw0x = fmaf(dh_, sd[0], gw0x); gw0y = fmaf(dh_, sd[1], gw0y); gw0z = fmaf(dh_, sd[2], gw0z); gb0 += dh_;
+        acc[3] = fmaf(dh_, sd[0], acc[3]); acc[4] = fmaf(dh_, sd[1], acc[4]); acc[5] = fmaf(dh_, sd[2], acc[5]); acc[6] += dh_;
     }
-    G[w2 + n] += gw2_0; G[w2 + H2 + n] += gw2_1; G[w2 + 2 * H2 + n] += gw2_2;
-    G[w0 + n * 3] += gw0x; G[w0 + n * 3 + 1] += gw0y; G[w0 + n * 3 + 2] += gw0z; G[b0 + n] += gb0;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) sh[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    for (int st = 64; st; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        G[w2 + n] += sh[0][0]; G[w2 + H2 + n] += sh[1][0]; G[w2 + 2 * H2 + n] += sh[2][0];
+        G[w0 + n * 3] += sh[3][0]; G[w0 + n * 3 + 1] += sh[4][0]; G[w0 + n * 3 + 2] += sh[5][0]; G[b0 + n] += sh[6][0];
+    }
 }
 
 __global__ void ray_sum_t_kernel(const float* __restrict__ per_point, float* __restrict__ per_ray, int n_rays, int S, int D) {
@@ -609,17 +622,30 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     items.reserve(B.n_items); outs.reserve(B.n_outs);
     const unsigned char* fb = (const unsigned char*)io->stash; const unsigned char* bb = ws + B.off_bstash;
     const int fgH = H / 64, fg2 = H2 / 64;
+    // Work-list order matters for DRAM traffic: the output tiles of one layer share their operands (every N-chunk reads the
+    // same dY rows, every M-tile the same input columns), so all tiles of a layer for ONE split-K range are made adjacent in
+    // the list — they run concurrently on neighbouring CTAs and the second reader of an operand slab hits L2.
+    std::vector<DwItem> pend;              // split 0 items of the current layer, one per output tile
     auto add_out = [&](const unsigned char* a_arr, int a_fgs, int a_fg0, const unsigned char* b_arr, int b_fgs, int b_fg0, int b_nfg, DwOut o) {
-        o.N = b_nfg * 64; o.ks = B.ks; o.part_off = (long long)items.size() * 128 * 256; o.part_stride = 128 * 256;
-        for (int s = 0; s < B.ks; ++s) {
-            DwItem w; memset(&w, 0, sizeof(w));
-            w.a_off = (long long)(uintptr_t)a_arr; w.b_off = (long long)(uintptr_t)b_arr; w.a_fgs = a_fgs; w.b_fgs = b_fgs;
-            w.a_fg0 = a_fg0; w.b_fg0 = b_fg0; w.b_nfg = b_nfg;
-            w.k_tile0 = (int)((long long)B.n_tiles * s / B.ks); w.k_tiles = (int)((long long)B.n_tiles * (s + 1) / B.ks) - w.k_tile0;
-            w.out_off = (long long)items.size() * 128 * 256;
-            items.push_back(w);
-        }
+        o.N = b_nfg * 64; o.ks = B.ks;
+        DwItem w; memset(&w, 0, sizeof(w));
+        w.a_off = (long long)(uintptr_t)a_arr; w.b_off = (long long)(uintptr_t)b_arr; w.a_fgs = a_fgs; w.b_fgs = b_fgs;
+        w.a_fg0 = a_fg0; w.b_fg0 = b_fg0; w.b_nfg = b_nfg;
+        pend.push_back(w);
         outs.push_back(o);
+    };
+    auto flush_layer = [&]() {
+        const size_t n = pend.size(), first_out = outs.size() - n;
+        const long long base = (long long)items.size() * 128 * 256;
+        for (int sp = 0; sp < B.ks; ++sp)
+            for (size_t e = 0; e < n; ++e) {
+                DwItem w = pend[e];
+                w.k_tile0 = (int)((long long)B.n_tiles * sp / B.ks); w.k_tiles = (int)((long long)B.n_tiles * (sp + 1) / B.ks) - w.k_tile0;
+                w.out_off = base + (long long)(sp * n + e) * 128 * 256;
+                items.push_back(w);
+            }
+        for (size_t e = 0; e < n; ++e) { outs[first_out + e].part_off = base + (long long)e * 128 * 256; outs[first_out + e].part_stride = (long long)n * 128 * 256; }
+        pend.clear();
     };
     // one linear layer: dY (out features M, atoms dy_arr with dy_fgs groups) x [IN (in features Nin, atoms) | E]
     auto layer = [&](const Lin& l, const unsigned char* dy_arr, int dy_fgs, const unsigned char* in_arr, int in_fgs, int Nin, int col_off,
@@ -635,12 +661,14 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
             o.xcol = xcol; o.suncol = suncol; o.tcol = tcol; o.tau = L.t_dims;
             add_out(dy_arr, dy_fgs, 2 * m, fb + A.fs.e, 1, 0, 1, o);
         }
+        flush_layer();
     };
     auto tiny = [&](const Lin& l, const unsigned char* in_arr, int in_fgs, int hc0, int nhc) {     // W (nhc x n_in): rows = head columns
         for (int m = 0; m * 128 < l.n_in; ++m) {
             DwOut o; memset(&o, 0, sizeof(o)); o.kind = 2; o.w_off = l.w; o.ld = l.n_in; o.m0 = m * 128; o.M = l.n_in; o.hc0 = hc0; o.nhc = nhc;
             add_out(in_arr, in_fgs, 2 * m, bb + B.bs.dhead, 1, 0, 1, o);
         }
+        flush_layer();
     };
     for (int l = L.n_layers - 1; l >= 1; --l)
         layer(L.trunk[l], bb + B.bs.dy[l], fgH, fb + A.fs.a[l - 1], fgH, H, l == L.skip ? L.in_xyz : 0, l == L.skip ? 0 : -1, -1, -1);
@@ -657,9 +685,25 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     if (L.variant == SNB_SATNERF) tiny(L.beta2, fb + A.fs.b1, fg2, 5, 1);
     if ((int)items.size() > B.n_items || (int)outs.size() > B.n_outs) SNB_FAIL(-3, "internal: weight-gradient work list overflow (%zu/%d, %zu/%d)", items.size(), B.n_items, outs.size(), B.n_outs);
     DwItem* d_items = (DwItem*)(ws + B.off_items); DwOut* d_outs = (DwOut*)(ws + B.off_outs);
-    SNB_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(DwItem) * items.size(), cudaMemcpyHostToDevice, st));
-    SNB_CUDA(cudaMemcpyAsync(d_outs, outs.data(), sizeof(DwOut) * outs.size(), cudaMemcpyHostToDevice, st));
-    SNB_CUDA(cudaStreamSynchronize(st));          // the host vectors go out of scope; the copies are tiny
+    {
+        // Work lists go through a small ring of pinned staging buffers so the copies are truly asynchronous: no stream
+        // synchronisation in the middle of the step (a pageable copy would stall the CPU behind the chain kernel).
+        constexpr int kSlots = 8; constexpr size_t kSlotBytes = 256 * 1024;
+        static unsigned char* pinned = nullptr; static cudaEvent_t ev[kSlots]; static int slot = 0;
+        if (!pinned) {
+            SNB_CUDA(cudaHostAlloc((void**)&pinned, kSlots * kSlotBytes, cudaHostAllocDefault));
+            for (int i = 0; i < kSlots; ++i) SNB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        const size_t ib = sizeof(DwItem) * items.size(), ob = sizeof(DwOut) * outs.size();
+        if (ib + ob > kSlotBytes) SNB_FAIL(-3, "internal: weight-gradient work list too large (%zu bytes)", ib + ob);
+        slot = (slot + 1) % kSlots;
+        SNB_CUDA(cudaEventSynchronize(ev[slot]));          // slot was used 8 backward calls ago: already complete in practice
+        unsigned char* h = pinned + (size_t)slot * kSlotBytes;
+        memcpy(h, items.data(), ib); memcpy(h + ib, outs.data(), ob);
+        SNB_CUDA(cudaMemcpyAsync(d_items, h, ib, cudaMemcpyHostToDevice, st));
+        SNB_CUDA(cudaMemcpyAsync(d_outs, h + ib, ob, cudaMemcpyHostToDevice, st));
+        SNB_CUDA(cudaEventRecord(ev[slot], st));
+    }
     float* partial = (float*)(ws + B.off_partial);
     SNB_TRY(launch_dw(d_items, (int)items.size(), nullptr, partial, st));
 
@@ -671,7 +715,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     bd.off[5] = L.sky2.b; bd.off[6] = L.sky2.b + 1; bd.off[7] = L.sky2.b + 2;
     if (L.variant == SNB_SATNERF) bd.off[8] = L.beta2.b;
     head_bias_kernel<<<9, 256, 0, st>>>(ray_sums, R, bd, g->g_params); SNB_CHECK_LAUNCH();
-    sky_bwd_kernel<<<(H2 + 63) / 64, 64, 0, st>>>(ray_sums, io->rays, p->ray_cols, io->aux_dir, R, H2, io->params, L.sky0.w, L.sky0.b, L.sky2.w, g->g_params);
+    sky_bwd_kernel<<<H2, 128, 0, st>>>(ray_sums, io->rays, p->ray_cols, io->aux_dir, R, H2, io->params, L.sky0.w, L.sky0.b, L.sky2.w, g->g_params);
     SNB_CHECK_LAUNCH();
     if (A.d_t) {
         ray_sum_t_kernel<<<(R * L.t_dims + 127) / 128, 128, 0, st>>>(d_t, g->g_t_emb, R, S, L.t_dims);
