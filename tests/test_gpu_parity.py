@@ -192,7 +192,7 @@ def test_field_forward_matches_oracle():
     assert sig.shape == (333, 1) and rel_err(sig.cpu(), want[:, 3:4]) < 2e-5
 
 
-@pytest.mark.parametrize("model,h,n_rays,S", [("sat-nerf", 128, 50, 64), ("sat-nerf", 256, 33, 96), ("s-nerf", 128, 20, 64)])
+@pytest.mark.parametrize("model,h,n_rays,S", [("sat-nerf", 128, 50, 64), ("sat-nerf", 256, 33, 96), ("s-nerf", 128, 20, 64), ("sat-nerf", 384, 17, 48)])
 def test_tc_backward_matches_fp64_oracle(model, h, n_rays, S):
     """Tensor-core backward (fused input-gradient chain + split-K weight-gradient GEMMs, fp16 gradients with a loss scale)
     against float64 autograd of the oracle.  Tolerance 2e-2 of each tensor's max |grad| (north_star gives no gradient
@@ -219,7 +219,9 @@ def test_tc_backward_matches_fp64_oracle(model, h, n_rays, S):
     worst = 0.0
     for name, prm in ms["coarse"].named_parameters():
         ref = P["coarse"][name].grad
-        err = rel_err(prm.grad.cpu(), ref, floor=1e-12)
+        # a bias gradient is a signed sum over all points and can cancel to ~0: measure it on the scale of its layer's weight gradient
+        floor = float(P["coarse"][name.replace(".bias", ".weight")].grad.abs().max()) if name.endswith(".bias") else 1e-12
+        err = rel_err(prm.grad.cpu(), ref, floor=floor)
         worst = max(worst, err)
         assert err < 2e-2, (name, err)
     if model == "sat-nerf":
