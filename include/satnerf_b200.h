@@ -113,6 +113,8 @@ SNB_API int         snb_debug_dw_gemm(const float* xa, const float* xb, int P, i
 /* developer microbenchmark: cycles for `iters` back-to-back tcgen05.mma (M=128 or 256, K=16) on n_blocks CTAs;
  * mode 0 SS cg1, 1 TS cg1 (A in TMEM), 2 SS cg2, 3 SS cg1 MN-major; host_out[0] = cycles, host_out[1] = iters */
 SNB_API int         snb_debug_mma_rate(int mode, int N, int iters, int n_blocks, long long* host_out);
+SNB_API int         snb_debug_mma_ring2(int N, int depth, int groups, int flags, int n_blocks, long long* host_out);
+SNB_API int         snb_debug_mma_ring(int N, int kstage, int depth, int groups, int flags, int n_blocks, long long* host_out);
 /* 1 when the device of the current context can run the tcgen05 path (compute capability 10.x). */
 SNB_API int         snb_device_supports_tc(void);
 

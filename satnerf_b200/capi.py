@@ -52,6 +52,8 @@ _SIGNATURES = {
     "snb_launch_count": (C.c_int64, [C.c_int]),
     "snb_debug_read": (C.c_int, [C.c_void_p, C.c_size_t]),
     "snb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "snb_debug_mma_ring2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "snb_debug_mma_ring": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "snb_debug_dw_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_param_layout": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),

@@ -24,6 +24,8 @@ enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
 
 struct TcGemm {
     int kind, N, K, n_chunks, chunk_n, k_slabs, skip, last, fmt, has_vec;
+    int k_early;                     // K-slabs of the input tile that are valid (and chunk-0 accumulator columns free) at the FIRST
+                                     // ready signal; the rest needs the second one (forward kernel only)
     int tbl_off, vec_off;            // float offsets into the packed table area
     // weight sources (flat fp32 params): rows [0,rows0) from src0, the rest from src1
     long long src0, src1; int ld0, ld1, col0, col1, rows0;
@@ -73,7 +75,7 @@ struct Smem {
     float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
     float* skyc;             // [kMaxGroupRays][4]
     float* consts;           // 8 floats
-    uint64_t *full, *empty, *peer_full, *acc_full, *a_ready;
+    uint64_t *full, *empty, *peer_full, *acc_full, *a_ready, *a_ready2;
     uint32_t* tmem_ptr;
 };
 
@@ -96,6 +98,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, i
     s.peer_full = (uint64_t*)p; p += 8 * 8;
     s.acc_full = (uint64_t*)p; p += 8;
     s.a_ready = (uint64_t*)p; p += 8;
+    s.a_ready2 = (uint64_t*)p; p += 8;
     s.tmem_ptr = (uint32_t*)p;
     return s;
 }

@@ -65,6 +65,18 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
     { TcGemm& g = add(GK_SUN2, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 0); }
     { TcGemm& g = add(GK_SUN3, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 1); }
     P->n_gemms = ng;
+    // Early start of a GEMM's first K-slabs (see the kernel): after layer 0 / a two-chunk producer the low half of the
+    // input tile is published before the high half; HEADA leaves the tile untouched, so SUN1 may start on all of it.
+    P->g[0].k_early = (H % 128 == 0) ? H / 128 : 0;
+    for (int i = 1; i < ng; ++i) {
+        const TcGemm& pr = P->g[i - 1];
+        const bool pr_stores = pr.kind == GK_TRUNK || pr.kind == GK_FEAT || pr.kind == GK_SUN1 || pr.kind == GK_SUN2;
+        if (pr.n_chunks == 2 && pr_stores && pr.chunk_n % 64 == 0) P->g[i].k_early = pr.chunk_n / 64;
+        else if (pr.n_chunks == 2 && pr.kind == GK_HEADA) P->g[i].k_early = P->g[i].k_slabs;
+        else P->g[i].k_early = 0;
+        if (P->g[i].k_early > P->g[i].k_slabs) P->g[i].k_early = P->g[i].k_slabs;
+    }
+    { const char* e = getenv("SNB_TC_NO_EARLY"); if (e && atoi(e)) for (int i = 0; i < ng; ++i) P->g[i].k_early = 0; }
     P->consts = tbl; tbl += 8;
     P->sunw = tbl; tbl += 4 * H2;                 // [3][H2] weights + [H2] bias
     P->betaw = tbl; tbl += (L.t_dims + 1) * H2;   // [tau][H2] weights + [H2] bias
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); mbar_init(&sm.peer_full[i], 1); }
-        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, CG);     // one elected arrival per CTA of the pair
+        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, CG); mbar_init(sm.a_ready2, CG);     // one elected arrival per CTA of the pair
         fence_barrier_init();
     }
     if (CG == 2) { __syncthreads(); cluster_sync_all(); }       // both CTAs of the pair are running and their barriers are initialised
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =================
-        int st = 0; uint32_t ph = 0, ready_ph = 0;
+        int st = 0; uint32_t ph = 0, ready_ph = 0, ready2_ph = 0;
         const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
         const uint32_t tmem = __shfl_sync(0xffffffffu, *sm.tmem_ptr, 0);      // provably warp-uniform copy of the TMEM base
         if (CG == 2 && cta_rank == 1) {
@@ -386,7 +398,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)g.chunk_n) : umma_idesc_f16((uint32_t)g.chunk_n);
                         const int n_st = g.n_chunks * g.k_slabs;
                         int j = 0, s = 0;
+                        int n_early = g.k_early;          // stages (all of N-chunk 0) that only need the first ready signal
                         for (int i = 0; i < n_st; ++i) {
+                            if (i == n_early) {           // the rest of the input tile / the accumulator columns of the later chunks
+                                if (lane == 0) mbar_wait(sm.a_ready2, ready2_ph, 7);
+                                ready2_ph ^= 1; n_early = -1;
+                                __syncwarp();
+                                tc_fence_after();
+                            }
                             int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
                             const uint64_t da = a_desc0 + (uint64_t)((uint32_t)s * (kSlabBytes >> 4));
                             const uint64_t db = b_desc0 + (uint64_t)((uint32_t)st * (uint32_t)(stage_bytes >> 4));
@@ -410,6 +429,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                             if (++st == P.n_stages) { st = 0; ph ^= 1; }
                             if (++s == g.k_slabs) { s = 0; ++j; }
                         }
+                        if (n_early >= 0) {               // every stage was an early one: still consume the second signal
+                            if (lane == 0) mbar_wait(sm.a_ready2, ready2_ph, 7);
+                            ready2_ph ^= 1;
+                            __syncwarp();
+                        }
                     }
                 }
             }
@@ -428,7 +452,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
         uint32_t acc_ph = 0;
         const int aux_col = 8;
         int tile_counter = 0;
-        const uint32_t ready_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready), 0) : 0u;     // the leader's a_ready barrier
+        const uint32_t ready_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready), 0) : 0u;     // the leader's a_ready barriers
+        const uint32_t ready2_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready2), 0) : 0u;
+        auto signal_ready = [&](int which) {          // one elected arrival per CTA
+            if (tid_e == 0) {
+                if (CG == 2) mbar_arrive_cluster(which ? ready2_bar : ready_bar);
+                else mbar_arrive(which ? sm.a_ready2 : sm.a_ready);
+            }
+        };
         for (int wk = unit; wk < n_work; wk += n_units) {
             const int grp = CG == 2 ? 2 * wk + (int)cta_rank : wk;
             const int r0 = grp * A.G;
@@ -511,18 +542,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 cp_async_wait_all();
                 named_bar_sync(1, kEpiThreads);
                 const uint32_t tok0 = fresh_token(0xffffu);
-                for (int n0 = half * 32; n0 < H; n0 += 32 * kEpiSub) {
-                    float v[32];
+                const int l0_split = P.g[0].k_early * 64;         // columns published with the first ready signal (0: none)
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int c_lo = pass ? l0_split : 0, c_hi = pass ? H : l0_split;
+                    for (int n0 = c_lo + half * 32; n0 < c_hi; n0 += 32 * kEpiSub) {
+                        float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok0);
-                        float y = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
-                        v[i] = __fmul_rn(30.0f, y);
+                        for (int i = 0; i < 32; ++i) {
+                            float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok0);
+                            float y = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
+                            v[i] = __fmul_rn(30.0f, y);
+                        }
+                        if (sb) yb_store32(yb_slot(sb + A.stash.y[0], gt, H, n0, row), v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i]);
+                        store_act32(a_base, row, n0, v);
                     }
-                    if (sb) yb_store32(yb_slot(sb + A.stash.y[0], gt, H, n0, row), v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i]);
-                    store_act32(a_base, row, n0, v);
+                    if (pass == 0 && l0_split > 0) {              // low K-slabs of the first GEMM's input are in place
+                        fence_proxy_async_smem();
+                        named_bar_sync(1, kEpiThreads);
+                        signal_ready(0);
+                    }
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, kEpiThreads);                  // everyone is done with the layer-0 table
@@ -530,7 +570,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 {   const TcGemm& g0 = P.g[0];
                     if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
                     if (g0.has_vec) table_copy(sm.tblV, T + g0.vec_off, g0.N * 4, tid_e); }
-                if (tid_e == 0) { if (CG == 2) mbar_arrive_cluster(ready_bar); else mbar_arrive(sm.a_ready); }
+                if (l0_split == 0) signal_ready(0);
+                signal_ready(1);
                 TC_MARK(60, 1);
 
                 float sig_dot = 0.f, beta_dot = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f, sun_dot = 0.f;
@@ -555,6 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         else if (kind == GK_SUN3) { es.y0 = sb + A.stash.s3y; es.act0 = sb + A.stash.s3; }
                     }
                     uint32_t tok = 0;
+                    const bool next_early = gi + 1 < P.n_gemms && n_chunks > 1 && P.g[gi + 1].k_early > 0;
+                    bool early_signaled = false;
                     for (int ch = 0; ch < n_chunks; ++ch) {
                         // one thread polls the mbarrier; the others park in a hardware barrier instead of spinning on shared memory
                         if (tid_e == 0) mbar_wait(sm.acc_full, acc_ph, 4);
@@ -565,6 +608,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         const bool final_chunk = ch == n_chunks - 1;
                         if (final_chunk && stores && n_chunks > 1) {
                             for (int n0 = half * 32; n0 < ch * chunk_n; n0 += 32 * kEpiSub) unpark_act32(tm_row + (uint32_t)n0, a_base, row, n0);
+                        }
+                        if (final_chunk && next_early) {
+                            // Every MMA of this GEMM has completed and the earlier chunks are drained: the low K-slabs of the next
+                            // GEMM's input (or, after HEADA, the untouched tile) and the accumulator columns of its chunk 0 are
+                            // ready, so its MMAs run underneath the epilogue of this last chunk.
+                            tc_fence_before();
+                            fence_proxy_async_smem();
+                            named_bar_sync(1, kEpiThreads);
+                            signal_ready(0);
+                            early_signaled = true;
                         }
                         for (int n0 = ch * chunk_n + half * 32; n0 < (ch + 1) * chunk_n && n0 < N; n0 += 32 * kEpiSub) {
                             float va[32];
@@ -591,7 +644,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         const TcGemm& gn = P.g[gi + 1];
                         if (gn.fmt != TF_NONE) table_copy(sm.tblF, T + gn.tbl_off, gn.N * gn.fmt * 4, tid_e);
                         if (gn.has_vec) table_copy(sm.tblV, T + gn.vec_off, gn.N * 4, tid_e);
-                        if (tid_e == 0) { if (CG == 2) mbar_arrive_cluster(ready_bar); else mbar_arrive(sm.a_ready); }
+                        if (!early_signaled) signal_ready(0);
+                        signal_ready(1);
                     }
                 }
                 // ---- head outputs of this point: combine the partial dot products of the kEpiSub column interleaves.
