@@ -106,6 +106,8 @@ SNB_API const char* snb_last_error(void);
 SNB_API int64_t     snb_launch_count(int reset);
 /* developer aid: copies the fused kernel's phase timestamps (int64 clock64 values) to a HOST buffer */
 SNB_API int         snb_debug_read(void* host_dst, size_t bytes);
+/* with SNB_TC_HANG_MIRROR set: 16 x [code, block, thread, parity] of the bounded barrier waits that trapped, by wait code (0xffffffff: none) */
+SNB_API int         snb_debug_hang_info(unsigned int* out64);
 /* developer / test entry: out (Fa x Fb) = Xa^T Xb through the point-atom packing and the tensor-core
  * weight-gradient kernel (csrc/tc_backward.cu); Xa (P x Fa), Xb (P x Fb) fp32 row-major, Fa % 128 == 0, Fb % 64 == 0 */
 SNB_API int         snb_debug_dw_gemm(const float* xa, const float* xb, int P, int Fa, int Fb, int k_splits, float* out,

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "snb_device_supports_tc": (C.c_int, []),
     "snb_launch_count": (C.c_int64, [C.c_int]),
     "snb_debug_read": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "snb_debug_hang_info": (C.c_int, [C.POINTER(C.c_uint)]),
     "snb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "snb_debug_mma_ring2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "snb_debug_mma_ring": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),

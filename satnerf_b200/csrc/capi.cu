@@ -183,3 +183,4 @@ extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* p
 
 // Developer aid: phase timestamps recorded by the fused kernel (see tc_field.cu); host buffer of int64.
 extern "C" SNB_API int snb_debug_read(void* host_dst, size_t bytes) { return tc_debug_read(host_dst, bytes); }
+extern "C" SNB_API int snb_debug_hang_info(unsigned int* out4) { return tc_debug_hang_info(out4); }

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128, 1) mma_ring2_kernel(int N, int depth, int
         int st = 0; uint32_t ph = 0;
         for (int i = 0; i < groups; ++i) {
             mbar_wait(&full[st], ph, 5);
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&peer_full[st]), 0));
+            if (lane == 0) { if (flags & 1024) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&peer_full[st]), 0)); else mbar_arrive_cluster(mapa_u32(smem_u32(&peer_full[st]), 0)); }
             __syncwarp();
             if (++st == depth) { st = 0; ph ^= 1; }
         }

@@ -36,13 +36,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 
 // debug record written before a timeout trap: [0]=code, [1]=block, [2]=thread, [3]=aux
 __device__ unsigned int g_hang_info[8];
+__device__ unsigned int* g_hang_host = nullptr;      // optional pinned host mirror (survives the trap): see snb_debug_hang_info
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {         // ~2 s at 2 GHz: far beyond any legitimate wait
+        if (clock64() - t0 > ((code == 1 || code == 4 || code == 5) ? 3000000000LL : 1000000000LL)) {    // 0.5 s (issuer) / 1.5 s (others) at 2 GHz: far beyond any
+                                                                                                    // legitimate wait; the issuer's record comes first
             g_hang_info[0] = code; g_hang_info[1] = blockIdx.x; g_hang_info[2] = threadIdx.x; g_hang_info[3] = parity;
+            if (g_hang_host) { unsigned int* h = g_hang_host + (code & 15) * 4; h[0] = code; h[1] = blockIdx.x; h[2] = threadIdx.x; h[3] = parity; }
             __threadfence_system();
             asm volatile("trap;");
         }
@@ -138,6 +141,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");

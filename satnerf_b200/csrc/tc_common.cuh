@@ -75,7 +75,7 @@ struct Smem {
     float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
     float* skyc;             // [kMaxGroupRays][4]
     float* consts;           // 8 floats
-    uint64_t *full, *empty, *peer_full, *acc_full, *a_ready, *a_ready2;
+    uint64_t *full, *empty, *peer_full, *acc_full, *acc_full2, *a_ready, *a_ready2;
     uint32_t* tmem_ptr;
 };
 
@@ -97,6 +97,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, i
     s.empty = (uint64_t*)p; p += 8 * 8;
     s.peer_full = (uint64_t*)p; p += 8 * 8;
     s.acc_full = (uint64_t*)p; p += 8;
+    s.acc_full2 = (uint64_t*)p; p += 8;
     s.a_ready = (uint64_t*)p; p += 8;
     s.a_ready2 = (uint64_t*)p; p += 8;
     s.tmem_ptr = (uint32_t*)p;

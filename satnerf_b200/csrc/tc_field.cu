@@ -67,14 +67,16 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
     P->n_gemms = ng;
     // Early start of a GEMM's first K-slabs (see the kernel): after layer 0 / a two-chunk producer the low half of the
     // input tile is published before the high half; HEADA leaves the tile untouched, so SUN1 may start on all of it.
-    P->g[0].k_early = (H % 128 == 0) ? H / 128 : 0;
+    P->g[0].k_early = (H % 128 == 0 && H >= 256) ? H / 128 : 0;
     for (int i = 1; i < ng; ++i) {
         const TcGemm& pr = P->g[i - 1];
         const bool pr_stores = pr.kind == GK_TRUNK || pr.kind == GK_FEAT || pr.kind == GK_SUN1 || pr.kind == GK_SUN2;
         if (pr.n_chunks == 2 && pr_stores && pr.chunk_n % 64 == 0) P->g[i].k_early = pr.chunk_n / 64;
-        else if (pr.n_chunks == 2 && pr.kind == GK_HEADA) P->g[i].k_early = P->g[i].k_slabs;
+        else if (pr.n_chunks == 2 && pr.kind == GK_HEADA) P->g[i].k_early = P->g[i].k_slabs - 1;
         else P->g[i].k_early = 0;
-        if (P->g[i].k_early > P->g[i].k_slabs) P->g[i].k_early = P->g[i].k_slabs;
+        // At least one stage of every GEMM waits for the second signal of BOTH CTAs of a pair: otherwise a fast CTA could
+        // send the second signal of the following GEMM before its partner has sent this one's (barrier phase aliasing).
+        if (P->g[i].k_early > P->g[i].k_slabs - 1) P->g[i].k_early = P->g[i].k_slabs - 1;
     }
     { const char* e = getenv("SNB_TC_NO_EARLY"); if (e && atoi(e)) for (int i = 0; i < ng; ++i) P->g[i].k_early = 0; }
     P->consts = tbl; tbl += 8;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); mbar_init(&sm.peer_full[i], 1); }
-        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, CG); mbar_init(sm.a_ready2, CG);     // one elected arrival per CTA of the pair
+        mbar_init(sm.acc_full, 1); mbar_init(sm.acc_full2, 1); mbar_init(sm.a_ready, CG); mbar_init(sm.a_ready2, CG);     // one elected arrival per CTA of the pair
         fence_barrier_init();
     }
     if (CG == 2) { __syncthreads(); cluster_sync_all(); }       // both CTAs of the pair are running and their barriers are initialised
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
                         for (int i = 0; i < n; ++i) {
                             mbar_wait(&sm.full[st], ph, 5);
-                            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.peer_full[st]), 0));
+                            if (lane == 0) { if (A.dbg & 64) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.peer_full[st]), 0)); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sm.peer_full[st]), 0)); }   // a release here costs ~1000 cycles per stage
                             __syncwarp();
                             if (++st == P.n_stages) { st = 0; ph ^= 1; }
                         }
@@ -391,48 +393,71 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 for (int t = 0; t < tiles_per_group; ++t) {
                     for (int gi = 0; gi < P.n_gemms; ++gi) {
                         const TcGemm& g = P.g[gi];
-                        if (lane == 0) mbar_wait(sm.a_ready, ready_ph, 2);
+#ifdef SNB_TC_PROGRESS
+                        if (g_hang_host && blockIdx.x < 16 && lane == 0) ((volatile unsigned int*)g_hang_host)[64 + blockIdx.x * 8 + 3] = (unsigned)(wk << 16 | t << 8 | gi);
+#endif
+                        mbar_wait(sm.a_ready, ready_ph, 2);
                         ready_ph ^= 1;
-                        __syncwarp();
                         tc_fence_after();
                         const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)g.chunk_n) : umma_idesc_f16((uint32_t)g.chunk_n);
                         const int n_st = g.n_chunks * g.k_slabs;
                         int j = 0, s = 0;
                         int n_early = g.k_early;          // stages (all of N-chunk 0) that only need the first ready signal
-                        for (int i = 0; i < n_st; ++i) {
+                        // Every lane polls the barriers (a lane-0 poll + __syncwarp costs ~100 cycles per stage) and, when the ring
+                        // is deep enough, one elected region issues TWO stages (8 MMAs): the per-region issue overhead (~400 cycles,
+                        // profiles/mma_ring_probe*.py) then stays below the 2 x 512 tensor cycles it feeds.
+                        for (int i = 0; i < n_st;) {
                             if (i == n_early) {           // the rest of the input tile / the accumulator columns of the later chunks
-                                if (lane == 0) mbar_wait(sm.a_ready2, ready2_ph, 7);
+                                mbar_wait(sm.a_ready2, ready2_ph, 7);
                                 ready2_ph ^= 1; n_early = -1;
-                                __syncwarp();
                                 tc_fence_after();
                             }
+                            const bool pair = P.n_stages >= 4 && s + 1 < g.k_slabs && i + 1 != n_early && !(A.dbg & 32);
+                            int st1 = st + 1; uint32_t ph1 = ph; if (st1 == P.n_stages) { st1 = 0; ph1 ^= 1; }
                             int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
+                            int ksteps1 = g.K - (s + 1) * 64; ksteps1 = (ksteps1 > 64 ? 64 : ksteps1) / 16;
                             const uint64_t da = a_desc0 + (uint64_t)((uint32_t)s * (kSlabBytes >> 4));
                             const uint64_t db = b_desc0 + (uint64_t)((uint32_t)st * (uint32_t)(stage_bytes >> 4));
+                            const uint64_t da1 = da + (uint64_t)(kSlabBytes >> 4);
+                            const uint64_t db1 = b_desc0 + (uint64_t)((uint32_t)st1 * (uint32_t)(stage_bytes >> 4));
                             const uint32_t d_tm = tmem + (uint32_t)(j * g.chunk_n);
-                            if (lane == 0) {          // one lane polls: 31 fewer pollers of the shared-memory barrier word
-                                mbar_wait(&sm.full[st], ph, 3);
-                                if (CG == 2) mbar_wait(&sm.peer_full[st], ph, 6);
+                            mbar_wait(&sm.full[st], ph, 3);
+                            if (CG == 2) mbar_wait(&sm.peer_full[st], ph, 6);
+                            if (pair) {
+                                mbar_wait(&sm.full[st1], ph1, 3);
+                                if (CG == 2) mbar_wait(&sm.peer_full[st1], ph1, 6);
                             }
-                            __syncwarp();
+                            __syncwarp();             // lanes may leave the polling loops at different times: elect.sync needs them converged
                             tc_fence_after();
                             if (elect_one()) {        // warp-uniform operands + elect: UTCHMMA takes uniform registers directly
                                 for (int k = 0; k < ksteps; ++k) {
                                     if (CG == 2) umma_f16_ss_2cta(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
                                     else umma_f16_ss(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
                                 }
-                                const bool chunk_done = s == g.k_slabs - 1;      // accumulator of N-chunk j is complete
-                                if (CG == 2) { umma_commit_2cta(&sm.empty[st], 3); if (chunk_done) umma_commit_2cta(sm.acc_full, 3); }
-                                else { umma_commit(&sm.empty[st]); if (chunk_done) umma_commit(sm.acc_full); }
+                                if (CG == 2) umma_commit_2cta(&sm.empty[st], 3); else umma_commit(&sm.empty[st]);
+                                if (pair) {
+                                    for (int k = 0; k < ksteps1; ++k) {
+                                        if (CG == 2) umma_f16_ss_2cta(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
+                                        else umma_f16_ss(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
+                                    }
+                                    if (CG == 2) umma_commit_2cta(&sm.empty[st1], 3); else umma_commit(&sm.empty[st1]);
+                                }
+                                const bool chunk_done = s + (pair ? 1 : 0) == g.k_slabs - 1;      // accumulator of N-chunk j is complete
+                                // one barrier per N-chunk index: two commits of one GEMM on a single barrier could both land before the
+                                // epilogue looks at it (it may still be draining its stash copy), and the parity wait would miss a phase
+                                if (chunk_done) { uint64_t* ab = j == 0 ? sm.acc_full : sm.acc_full2; if (CG == 2) umma_commit_2cta(ab, 3); else umma_commit(ab); }
                             }
                             __syncwarp();
-                            if (++st == P.n_stages) { st = 0; ph ^= 1; }
-                            if (++s == g.k_slabs) { s = 0; ++j; }
+                            const int adv = pair ? 2 : 1;
+                            i += adv;
+                            for (int q = 0; q < adv; ++q) {
+                                if (++st == P.n_stages) { st = 0; ph ^= 1; }
+                                if (++s == g.k_slabs) { s = 0; ++j; }
+                            }
                         }
                         if (n_early >= 0) {               // every stage was an early one: still consume the second signal
-                            if (lane == 0) mbar_wait(sm.a_ready2, ready2_ph, 7);
+                            mbar_wait(sm.a_ready2, ready2_ph, 7);
                             ready2_ph ^= 1;
-                            __syncwarp();
                         }
                     }
                 }
@@ -449,14 +474,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
         const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
         const uint32_t tF = smem_u32(sm.tblF), tV = smem_u32(sm.tblV);
         const int H = P.H, H2 = P.H2, S = A.S;
-        uint32_t acc_ph = 0;
+        uint32_t acc_ph = 0, acc_ph2 = 0;
         const int aux_col = 8;
         int tile_counter = 0;
         const uint32_t ready_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready), 0) : 0u;     // the leader's a_ready barriers
         const uint32_t ready2_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready2), 0) : 0u;
+#ifdef SNB_TC_PROGRESS      // deadlock diagnosis: per-block progress words in the pinned hang mirror (SNB_TC_HANG_MIRROR=1)
+        unsigned int n_sig[2] = {0u, 0u};
+#endif
         auto signal_ready = [&](int which) {          // one elected arrival per CTA
             if (tid_e == 0) {
-                if (CG == 2) mbar_arrive_cluster(which ? ready2_bar : ready_bar);
+#ifdef SNB_TC_PROGRESS
+                if (g_hang_host && blockIdx.x < 16) { ++n_sig[which]; ((volatile unsigned int*)g_hang_host)[64 + blockIdx.x * 8 + which] = n_sig[which]; }
+#endif
+                // (the writes this publishes were fenced into the async proxy and ordered by the named barrier before this point;
+                //  the tensor core that reads them is this CTA's own, so the remote arrival needs no cluster-scope release)
+                if (CG == 2 && cta_rank != 0) { if (A.dbg & 64) mbar_arrive_cluster(which ? ready2_bar : ready_bar); else mbar_arrive_cluster_relaxed(which ? ready2_bar : ready_bar); }
                 else mbar_arrive(which ? sm.a_ready2 : sm.a_ready);
             }
         };
@@ -515,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     }
                 }
                 const int gt = grp * tiles_per_group + t;         // global tile id (stash index)
-                unsigned char* const sb = TRAIN ? A.stash_base : nullptr;     // compile-time null in the inference instantiation
+                unsigned char* const sb = (TRAIN && grp < A.n_groups) ? A.stash_base : nullptr;     // compile-time null in the inference instantiation; the idle half of an odd pair stashes nothing
                 if (sb && half == 0) {
                     // extra input block of the weight-gradient GEMMs: [x y z | sun_d | t_emb | 1 | 0 ...] (64 fp16 per point)
                     float e[16];
@@ -577,6 +610,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 float sig_dot = 0.f, beta_dot = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f, sun_dot = 0.f;
                 for (int gi = 0; gi < P.n_gemms; ++gi) {
                     const TcGemm& g = P.g[gi];
+#ifdef SNB_TC_PROGRESS
+                    if (g_hang_host && blockIdx.x < 16 && tid_e == 0) ((volatile unsigned int*)g_hang_host)[64 + blockIdx.x * 8 + 2] = (unsigned)(wk << 16 | t << 8 | gi);
+#endif
                     cp_async_wait_all();
                     if (sb && tid_e == 0) bulk_wait_read();      // the stash copy of the previous activation tile has left shared memory
                     named_bar_sync(1, kEpiThreads);              // tables of this GEMM are in shared memory
@@ -600,8 +636,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     bool early_signaled = false;
                     for (int ch = 0; ch < n_chunks; ++ch) {
                         // one thread polls the mbarrier; the others park in a hardware barrier instead of spinning on shared memory
-                        if (tid_e == 0) mbar_wait(sm.acc_full, acc_ph, 4);
-                        acc_ph ^= 1;
+                        if (tid_e == 0) mbar_wait(ch == 0 ? sm.acc_full : sm.acc_full2, ch == 0 ? acc_ph : acc_ph2, 4);
+                        if (ch == 0) acc_ph ^= 1; else acc_ph2 ^= 1;
                         named_bar_sync(2, kEpiThreads);
                         tc_fence_after();
                         if (ch == 0) { tok = fresh_token((uint32_t)gi); TC_MARK(gi, 1); }
@@ -752,6 +788,21 @@ int tc_workspace(const FieldLayout& L, const snb_pass_desc* p, bool backward, si
     return 0;
 }
 
+static unsigned int* g_hang_pinned = nullptr;
+static int hang_mirror_init() {
+    if (g_hang_pinned) return 0;
+    SNB_CUDA(cudaHostAlloc((void**)&g_hang_pinned, 1024, cudaHostAllocMapped));
+    memset(g_hang_pinned, 0xff, 1024);
+    unsigned int* dptr = nullptr;
+    SNB_CUDA(cudaHostGetDevicePointer((void**)&dptr, g_hang_pinned, 0));
+    SNB_CUDA(cudaMemcpyToSymbol(g_hang_host, &dptr, sizeof(dptr)));
+    return 0;
+}
+int tc_debug_hang_info(unsigned int* out) {
+    for (int i = 0; i < 192; ++i) out[i] = g_hang_pinned ? g_hang_pinned[i] : 0xffffffffu;
+    return 0;
+}
+
 int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_render_io* io, void* workspace, size_t workspace_bytes,
                       cudaStream_t st) {
     if (!tc_supported(L, p)) return 1;
@@ -763,15 +814,18 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         SNB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         SNB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
+    if (getenv("SNB_TC_HANG_MIRROR")) { int rc = hang_mirror_init(); if (rc) return rc; }
     TcArgs A; memset(&A, 0, sizeof(A));
     int nfl = build_program(L, &A.prog);
     TcProgram& P = A.prog;
     size_t need = (size_t)P.tables_base + (size_t)nfl * 4;
     if (need > workspace_bytes) SNB_FAIL(-4, "tensor-core path: workspace too small (%zu < %zu)", workspace_bytes, need);
-    // CTA pairs (SNB_TC_CG=2) are functional but measured no faster: the tensor pipe, not the weight stream, bounds
-    // the MMA phase (profiles/r1_phase_probe.md), so the simpler single-CTA form is the default.
-    int cg = 1;
-    { const char* e = getenv("SNB_TC_CG"); if (e && atoi(e) == 2) cg = 2; }
+    // CTA pairs (cta_group::2) are the default: each CTA streams and buffers only half of every weight tile, so the ring is
+    // 4 x 16 KB deep instead of 2 x 32 KB and the L2 -> shared-memory stream per SM halves; a single CTA is bound by the
+    // refill latency of its 2-stage ring (profiles/r1_phase_probe.md, mma_ring*_probe.py).  SNB_TC_CG=1 forces single CTAs.
+    const int G_ = choose_group(p->n_samples);
+    int cg = (p->n_rays + G_ - 1) / G_ >= 2 ? 2 : 1;
+    { const char* e = getenv("SNB_TC_CG"); if (e && atoi(e) == 2) cg = 2; if (e && atoi(e) == 1) cg = 1; }
     size_t fixed = (size_t)P.a_slabs * kSlabBytes + smem_fixed_bytes() + 1024;
     int ns = (int)(((size_t)max_smem - fixed) / (P.stage_bytes / cg)); if (ns > 8) ns = 8;
     if (ns < 2) SNB_FAIL(-6, "tensor-core path: not enough shared memory for the weight ring");

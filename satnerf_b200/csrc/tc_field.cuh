@@ -13,6 +13,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
                        const snb_render_grads* g, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 int tc_debug_read(void* dst, size_t bytes);
+int tc_debug_hang_info(unsigned int* out4);
 int tc_bwd_workspace(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes);
 int tc_stash_bytes(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes);
 
