@@ -12,7 +12,7 @@ from typing import Dict, Optional
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsatnerf_b200.so")
+_LIB_PATH = os.environ.get("SNB_LIBRARY_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsatnerf_b200.so")   # (override: developer A/B builds)
 
 NERF, SNERF, SATNERF = 0, 1, 2
 FP32_SIMT, FP16_TC = 0, 1

@@ -38,17 +38,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ unsigned int g_hang_info[8];
 __device__ unsigned int* g_hang_host = nullptr;      // optional pinned host mirror (survives the trap): see snb_debug_hang_info
 
+// slow path of a bounded wait, kept out of line so that the polling loops stay small
+static __device__ __noinline__ void mbar_hang_trap(int code, uint32_t parity) {
+    g_hang_info[0] = code; g_hang_info[1] = blockIdx.x; g_hang_info[2] = threadIdx.x; g_hang_info[3] = parity;
+    if (g_hang_host) { unsigned int* h = g_hang_host + (code & 15) * 4; h[0] = code; h[1] = blockIdx.x; h[2] = threadIdx.x; h[3] = parity; }
+    __threadfence_system();
+    asm volatile("trap;");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
+    // 0.5 s (MMA issuer) / 1.5 s (others) at 2 GHz: far beyond any legitimate wait; the issuer's record comes first
+    const long long limit = (code == 1 || code == 4 || code == 5) ? 3000000000LL : 1000000000LL;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > ((code == 1 || code == 4 || code == 5) ? 3000000000LL : 1000000000LL)) {    // 0.5 s (issuer) / 1.5 s (others) at 2 GHz: far beyond any
-                                                                                                    // legitimate wait; the issuer's record comes first
-            g_hang_info[0] = code; g_hang_info[1] = blockIdx.x; g_hang_info[2] = threadIdx.x; g_hang_info[3] = parity;
-            if (g_hang_host) { unsigned int* h = g_hang_host + (code & 15) * 4; h[0] = code; h[1] = blockIdx.x; h[2] = threadIdx.x; h[3] = parity; }
-            __threadfence_system();
-            asm volatile("trap;");
-        }
+        if (clock64() - t0 > limit) mbar_hang_trap(code, parity);
     }
 }
 

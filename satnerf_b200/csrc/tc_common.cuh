@@ -24,6 +24,7 @@ enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
 
 struct TcGemm {
     int kind, N, K, n_chunks, chunk_n, k_slabs, skip, last, fmt, has_vec;
+    int two_idx;                     // number of two-chunk GEMMs before this one in the program
     int k_early;                     // K-slabs of the input tile that are valid (and chunk-0 accumulator columns free) at the FIRST
                                      // ready signal; the rest needs the second one (forward kernel only)
     int tbl_off, vec_off;            // float offsets into the packed table area
@@ -32,7 +33,7 @@ struct TcGemm {
 };
 
 struct TcProgram {
-    int H, H2, n_gemms, tau, has_beta, a_slabs, stage_bytes, n_stages;
+    int H, H2, n_gemms, n_two, tau, has_beta, a_slabs, stage_bytes, n_stages;
     int l0_tbl, consts, sunw, betaw, sky;        // float offsets in the table area
     long long l0_w, l0_b;                        // flat param offsets of trunk layer 0
     long long tables_base;                       // byte offset of the table area in the packed buffer

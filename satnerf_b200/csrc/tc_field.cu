@@ -65,6 +65,8 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
     { TcGemm& g = add(GK_SUN2, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 0); }
     { TcGemm& g = add(GK_SUN3, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 1); }
     P->n_gemms = ng;
+    P->n_two = 0;
+    for (int i = 0; i < ng; ++i) { P->g[i].two_idx = P->n_two; if (P->g[i].n_chunks == 2) ++P->n_two; }
     // Early start of a GEMM's first K-slabs (see the kernel): after layer 0 / a two-chunk producer the low half of the
     // input tile is published before the high half; HEADA leaves the tile untouched, so SUN1 may start on all of it.
     P->g[0].k_early = (H % 128 == 0 && H >= 256) ? H / 128 : 0;
@@ -76,6 +78,9 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
         else P->g[i].k_early = 0;
         // At least one stage of every GEMM waits for the second signal of BOTH CTAs of a pair: otherwise a fast CTA could
         // send the second signal of the following GEMM before its partner has sent this one's (barrier phase aliasing).
+#ifdef SNB_V_SUN1_ALL
+        if (pr.n_chunks == 2 && pr.kind == GK_HEADA) P->g[i].k_early = P->g[i].k_slabs; else
+#endif
         if (P->g[i].k_early > P->g[i].k_slabs - 1) P->g[i].k_early = P->g[i].k_slabs - 1;
     }
     { const char* e = getenv("SNB_TC_NO_EARLY"); if (e && atoi(e)) for (int i = 0; i < ng; ++i) P->g[i].k_early = 0; }
@@ -208,7 +213,15 @@ __global__ void tc_pack_misc_kernel(TcProgram P, MiscOffsets M, const float* __r
 // Phase timestamps (clock64) of block 0's second tile, read back through snb_debug_read: per GEMM
 // [wait-for-accumulator start, accumulator ready, epilogue done]; slot 60.. = layer-0 / compositing marks.
 __device__ long long g_tc_dbg[64 * 4];
+// The marks and the SNB_TC_DBG knobs exist only in probe builds (-DSNB_TC_PROBE, profiles/dev/build_variant.sh): the
+// production kernel is register-bound (112 per thread) and every extra live value in the epilogue spills.
+#ifdef SNB_TC_PROBE
 #define TC_MARK(slot, k) do { if (dbg_on && tid_e == 0) g_tc_dbg[(slot) * 4 + (k)] = clock64(); } while (0)
+#define TC_DBG(x) (x)
+#else
+#define TC_MARK(slot, k) do { (void)dbg_on; } while (0)
+#define TC_DBG(x) 0
+#endif
 
 // Epilogue of one 32-column block of one row: v = fp32 accumulators of columns n0..n0+31.
 // Tables live in shared memory (32-bit addresses): tF = [N] floats (F1) or [N][4] (F4), tV = [N] extra vector.
@@ -216,7 +229,7 @@ __device__ long long g_tc_dbg[64 * 4];
 // registers (first layers of the rgb / beta heads, last sun layer) go to their atoms stash.
 struct EpiStash { unsigned char *y0, *y1, *act0, *act1; int gt; };     // 0: first column half of HEADA (beta) / every other kind
 
-#define SIN_(x) ((dbg & 1) ? (x) : __sinf(x))
+#define SIN_(x) ((TC_DBG(dbg) & 1) ? (x) : __sinf(x))
 __device__ __forceinline__ void sin32(int dbg, float* v, unsigned char* yarr, int gt, int F, int n0, int row) {
     if (yarr) yb_store32(yb_slot(yarr, gt, F, n0, row), v);
 #pragma unroll
@@ -250,14 +263,14 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
                 sig_dot = fmaf(w.z, v[i + 2], sig_dot); sig_dot = fmaf(w.w, v[i + 3], sig_dot);
             }
         }
-        if (!(dbg & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
+        if (!(TC_DBG(dbg) & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
     } else if (kind == GK_FEAT) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
             float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
-        if (!(dbg & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
+        if (!(TC_DBG(dbg) & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
     } else if (kind == GK_HEADA) {
         if (has_beta && n0 < H2) {
 #pragma unroll
@@ -288,7 +301,7 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
         sin32(dbg, v, es.y0, es.gt, H2, n0, row);
-        if (!(dbg & 4)) store_act32(a_base, row, n0, v);
+        if (!(TC_DBG(dbg) & 4)) store_act32(a_base, row, n0, v);
     } else {   // GK_SUN2 / GK_SUN3
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -296,7 +309,7 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
         sin32(dbg, v, es.y0, es.gt, H2, n0, row);
-        if (kind == GK_SUN2) { if (!(dbg & 4)) store_act32(a_base, row, n0, v); }
+        if (kind == GK_SUN2) { if (!(TC_DBG(dbg) & 4)) store_act32(a_base, row, n0, v); }
         else {
             if (es.act0) atom_store32(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
 #pragma unroll
@@ -354,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     for (int i = 0; i < n; ++i) {
                         if (lane == 0) {
                             mbar_wait(&sm.empty[st], ph ^ 1, 1);
-                            if (A.dbg & 16) mbar_arrive(&sm.full[st]);        // knob: no copy (tensor pipe alone)
+                            if (TC_DBG(A.dbg) & 16) mbar_arrive(&sm.full[st]);        // knob: no copy (tensor pipe alone)
                             else {
                                 mbar_arrive_expect_tx(&sm.full[st], bytes);
                                 bulk_g2s(sm.b + (size_t)st * stage_bytes, src + cta_rank * bytes, bytes, &sm.full[st]);   // this CTA's rows of the tile
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
                         for (int i = 0; i < n; ++i) {
                             mbar_wait(&sm.full[st], ph, 5);
-                            if (lane == 0) { if (A.dbg & 64) mbar_arrive_cluster(mapa_u32(smem_u32(&sm.peer_full[st]), 0)); else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sm.peer_full[st]), 0)); }   // a release here costs ~1000 cycles per stage
+                            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sm.peer_full[st]), 0));   // a release here costs ~1000 cycles per stage
                             __syncwarp();
                             if (++st == P.n_stages) { st = 0; ph ^= 1; }
                         }
@@ -412,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 ready2_ph ^= 1; n_early = -1;
                                 tc_fence_after();
                             }
-                            const bool pair = P.n_stages >= 4 && s + 1 < g.k_slabs && i + 1 != n_early && !(A.dbg & 32);
+                            const bool pair = P.n_stages >= 4 && s + 1 < g.k_slabs && i + 1 != n_early;
                             int st1 = st + 1; uint32_t ph1 = ph; if (st1 == P.n_stages) { st1 = 0; ph1 ^= 1; }
                             int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
                             int ksteps1 = g.K - (s + 1) * 64; ksteps1 = (ksteps1 > 64 ? 64 : ksteps1) / 16;
@@ -427,7 +440,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 mbar_wait(&sm.full[st1], ph1, 3);
                                 if (CG == 2) mbar_wait(&sm.peer_full[st1], ph1, 6);
                             }
-                            __syncwarp();             // lanes may leave the polling loops at different times: elect.sync needs them converged
                             tc_fence_after();
                             if (elect_one()) {        // warp-uniform operands + elect: UTCHMMA takes uniform registers directly
                                 for (int k = 0; k < ksteps; ++k) {
@@ -445,7 +457,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 const bool chunk_done = s + (pair ? 1 : 0) == g.k_slabs - 1;      // accumulator of N-chunk j is complete
                                 // one barrier per N-chunk index: two commits of one GEMM on a single barrier could both land before the
                                 // epilogue looks at it (it may still be draining its stash copy), and the parity wait would miss a phase
-                                if (chunk_done) { uint64_t* ab = j == 0 ? sm.acc_full : sm.acc_full2; if (CG == 2) umma_commit_2cta(ab, 3); else umma_commit(ab); }
+                                if (chunk_done) {
+#ifdef SNB_V_ONE_ACC
+                                    if (CG == 2) umma_commit_2cta(sm.acc_full, 3); else umma_commit(sm.acc_full);
+#else
+                                    if (j == 0) { if (CG == 2) umma_commit_2cta(sm.acc_full, 3); else umma_commit(sm.acc_full); }
+                                    else { if (CG == 2) umma_commit_2cta(sm.acc_full2, 3); else umma_commit(sm.acc_full2); }
+#endif
+                                }
                             }
                             __syncwarp();
                             const int adv = pair ? 2 : 1;
@@ -474,7 +493,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
         const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
         const uint32_t tF = smem_u32(sm.tblF), tV = smem_u32(sm.tblV);
         const int H = P.H, H2 = P.H2, S = A.S;
-        uint32_t acc_ph = 0, acc_ph2 = 0;
         const int aux_col = 8;
         int tile_counter = 0;
         const uint32_t ready_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready), 0) : 0u;     // the leader's a_ready barriers
@@ -489,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 #endif
                 // (the writes this publishes were fenced into the async proxy and ordered by the named barrier before this point;
                 //  the tensor core that reads them is this CTA's own, so the remote arrival needs no cluster-scope release)
-                if (CG == 2 && cta_rank != 0) { if (A.dbg & 64) mbar_arrive_cluster(which ? ready2_bar : ready_bar); else mbar_arrive_cluster_relaxed(which ? ready2_bar : ready_bar); }
+                if (CG == 2 && cta_rank != 0) mbar_arrive_cluster_relaxed(which ? ready2_bar : ready_bar);
                 else mbar_arrive(which ? sm.a_ready2 : sm.a_ready);
             }
         };
@@ -528,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 }
             }
             for (int t = 0; t < n_tiles; ++t) {
-                const bool dbg_on = blockIdx.x == 0 && (tile_counter++ == 1);
+                const bool dbg_on = TC_DBG(blockIdx.x == 0 && tile_counter == 1); ++tile_counter;
                 TC_MARK(60, 0);
                 // ---- sample position of this thread's point ----
                 const int p = t * kTile + row;
@@ -636,8 +654,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     bool early_signaled = false;
                     for (int ch = 0; ch < n_chunks; ++ch) {
                         // one thread polls the mbarrier; the others park in a hardware barrier instead of spinning on shared memory
-                        if (tid_e == 0) mbar_wait(ch == 0 ? sm.acc_full : sm.acc_full2, ch == 0 ? acc_ph : acc_ph2, 4);
-                        if (ch == 0) acc_ph ^= 1; else acc_ph2 ^= 1;
+#ifdef SNB_V_ONE_ACC
+#error "SNB_V_ONE_ACC is no longer supported"
+#else
+                        // barrier phases follow from the tile / GEMM counters (no per-thread parity registers):
+                        // chunk 0 flips acc_full once per GEMM, chunk 1 flips acc_full2 once per two-chunk GEMM
+                        if (tid_e == 0) {
+                            const int tile_seq = tile_counter - 1;
+                            if (ch == 0) mbar_wait(sm.acc_full, (uint32_t)(tile_seq * P.n_gemms + gi) & 1u, 4);
+                            else mbar_wait(sm.acc_full2, (uint32_t)(tile_seq * P.n_two + g.two_idx) & 1u, 4);
+                        }
+#endif
                         named_bar_sync(2, kEpiThreads);
                         tc_fence_after();
                         if (ch == 0) { tok = fresh_token((uint32_t)gi); TC_MARK(gi, 1); }
@@ -657,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         }
                         for (int n0 = ch * chunk_n + half * 32; n0 < (ch + 1) * chunk_n && n0 < N; n0 += 32 * kEpiSub) {
                             float va[32];
-                            if (!(A.dbg & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
+                            if (!(TC_DBG(A.dbg) & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
                             else { for (int i = 0; i < 32; ++i) va[i] = 0.01f * i; }
                             epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz, es,
                                       stores && !final_chunk, tm_row + (uint32_t)n0,
@@ -707,7 +734,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 named_bar_sync(1, kEpiThreads);                  // scratch reads done before the next tile's layer 0 overwrites A
             }
             named_bar_sync(1, kEpiThreads);
-            { const bool dbg_on = blockIdx.x == 0 && tile_counter == 2; TC_MARK(61, 0); }
+            { const bool dbg_on = TC_DBG(blockIdx.x == 0 && tile_counter == 2); TC_MARK(61, 0); }
             // ---- alpha compositing: one warp per ray, transmittance by warp scan (satnerf.py:52-70) ----
             for (int gr = warp - 2; gr < n_rays; gr += kEpiWarps) {
                 const int ray = r0 + gr;
@@ -757,7 +784,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 }
             }
             named_bar_sync(1, kEpiThreads);                      // group tables are reused by the next group
-            { const bool dbg_on = blockIdx.x == 0 && tile_counter == 2; TC_MARK(61, 1); }
+            { const bool dbg_on = TC_DBG(blockIdx.x == 0 && tile_counter == 2); TC_MARK(61, 1); }
         }
     }
     tc_fence_before();
