@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 1
+#define SNB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SNB_API __attribute__((visibility("default")))
@@ -63,6 +63,10 @@ typedef struct snb_pass_desc {
     int32_t march_along_sun; /* 1 = solar-correction pass, points = o + sun_d*z (rendering.py:104) */
     int32_t precision;       /* SNB_FP32_SIMT | SNB_FP16_TC                                     */
     float   noise_std;       /* args.noise_std; multiplies `noise` (satnerf.py:57-58)           */
+    int32_t weights_packed;  /* SNB_FP16_TC forward only: 1 = `workspace` still holds the packed fp16 weight tiles this
+                                library wrote there on an earlier call with the SAME parameter values (the caller
+                                guarantees both): the per-call repacking (two small kernels) is skipped.  Evaluation
+                                loops (batched_inference, eval_satnerf.py:46-66) render many batches per weight set. */
 } snb_pass_desc;
 
 typedef struct snb_render_io {

@@ -28,7 +28,7 @@ class FieldDesc(C.Structure):
 
 class PassDesc(C.Structure):
     _fields_ = [("n_rays", C.c_int32), ("n_samples", C.c_int32), ("ray_cols", C.c_int32),
-                ("march_along_sun", C.c_int32), ("precision", C.c_int32), ("noise_std", C.c_float)]
+                ("march_along_sun", C.c_int32), ("precision", C.c_int32), ("noise_std", C.c_float), ("weights_packed", C.c_int32)]
 
 
 _IO_FIELDS = ["params", "rays", "z_vals", "t_emb", "noise", "xyz", "aux_dir", "rgb", "depth", "weights", "transparency",
@@ -88,7 +88,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.snb_abi_version() != 1:
+        if handle.snb_abi_version() != 2:
             raise RuntimeError("libsatnerf_b200.so ABI version mismatch")
         _lib = handle
     return _lib
@@ -233,15 +233,25 @@ def _fill(struct, names, tensors: Dict[str, Optional[torch.Tensor]]):
     return struct
 
 
-def render_forward(desc: FieldDesc, pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]]):
+def render_forward(desc: FieldDesc, pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]], workspace: Optional[torch.Tensor] = None):
+    """`workspace`: a caller-owned uint8 buffer of render_workspace_bytes() bytes (needed for pd.weights_packed, which relies
+    on the buffer's contents surviving between calls); default: the shared per-device scratch."""
     dev = tensors["rays"].device if tensors.get("rays") is not None else tensors["xyz"].device
     io = _fill(RenderIO(), _IO_FIELDS, tensors)
     n = C.c_size_t(0)
     with torch.cuda.device(dev):
         _check(lib().snb_render_workspace(C.byref(desc), C.byref(pd), 0, C.byref(n)), "snb_render_workspace")
-        ws = _workspace(dev, n.value)
+        ws = workspace if workspace is not None else _workspace(dev, n.value)
+        if ws.numel() < n.value:
+            raise RuntimeError(f"render_forward: workspace of {ws.numel()} bytes given, {n.value} needed")
         _check(lib().snb_render_forward(C.byref(desc), C.byref(pd), C.byref(io), C.c_void_p(ws.data_ptr()), ws.numel(), _stream(dev)),
                "snb_render_forward")
+
+
+def render_workspace_bytes(desc: FieldDesc, pd: PassDesc, backward: bool = False) -> int:
+    n = C.c_size_t(0)
+    _check(lib().snb_render_workspace(C.byref(desc), C.byref(pd), int(backward), C.byref(n)), "snb_render_workspace")
+    return int(n.value)
 
 
 def render_backward(desc: FieldDesc, pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]], grads: Dict[str, Optional[torch.Tensor]]):

@@ -24,6 +24,7 @@ enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
 
 struct TcGemm {
     int kind, N, K, n_chunks, chunk_n, k_slabs, skip, last, fmt, has_vec;
+    int free_slabs, store2_idx;      // two-chunk GEMMs that write the tile: K-slabs the last chunk's MMAs release one by one; sequence index
     int two_idx;                     // number of two-chunk GEMMs before this one in the program
     int k_early;                     // K-slabs of the input tile that are valid (and chunk-0 accumulator columns free) at the FIRST
                                      // ready signal; the rest needs the second one (forward kernel only)
@@ -33,7 +34,7 @@ struct TcGemm {
 };
 
 struct TcProgram {
-    int H, H2, n_gemms, n_two, tau, has_beta, a_slabs, stage_bytes, n_stages;
+    int H, H2, n_gemms, n_two, n_store2, tau, has_beta, a_slabs, stage_bytes, n_stages;
     int l0_tbl, consts, sunw, betaw, sky;        // float offsets in the table area
     long long l0_w, l0_b;                        // flat param offsets of trunk layer 0
     long long tables_base;                       // byte offset of the table area in the packed buffer
@@ -76,7 +77,7 @@ struct Smem {
     float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
     float* skyc;             // [kMaxGroupRays][4]
     float* consts;           // 8 floats
-    uint64_t *full, *empty, *peer_full, *acc_full, *acc_full2, *a_ready, *a_ready2;
+    uint64_t *full, *empty, *peer_full, *acc_full, *acc_full2, *a_ready, *a_ready2, *slab_free;
     uint32_t* tmem_ptr;
 };
 
@@ -101,6 +102,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, i
     s.acc_full2 = (uint64_t*)p; p += 8;
     s.a_ready = (uint64_t*)p; p += 8;
     s.a_ready2 = (uint64_t*)p; p += 8;
+    s.slab_free = (uint64_t*)p; p += 4 * 8;
     s.tmem_ptr = (uint32_t*)p;
     return s;
 }

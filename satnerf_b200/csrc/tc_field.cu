@@ -65,8 +65,16 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
     { TcGemm& g = add(GK_SUN2, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 0); }
     { TcGemm& g = add(GK_SUN3, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 1); }
     P->n_gemms = ng;
-    P->n_two = 0;
-    for (int i = 0; i < ng; ++i) { P->g[i].two_idx = P->n_two; if (P->g[i].n_chunks == 2) ++P->n_two; }
+    P->n_two = 0; P->n_store2 = 0;
+    for (int i = 0; i < ng; ++i) {
+        TcGemm& g = P->g[i];
+        g.two_idx = P->n_two; if (g.n_chunks == 2) ++P->n_two;
+        // chunk 0 of a two-chunk GEMM that writes the tile stores its results straight into the K-slabs the MMAs of chunk 1
+        // have finished with (released slab by slab through slab_free[])
+        const bool st = g.kind == GK_TRUNK || g.kind == GK_FEAT;
+        g.store2_idx = P->n_store2; g.free_slabs = 0;
+        if (st && g.n_chunks == 2) { g.free_slabs = (g.chunk_n + 63) / 64; ++P->n_store2; }
+    }
     // Early start of a GEMM's first K-slabs (see the kernel): after layer 0 / a two-chunk producer the low half of the
     // input tile is published before the high half; HEADA leaves the tile untouched, so SUN1 may start on all of it.
     P->g[0].k_early = (H % 128 == 0 && H >= 256) ? H / 128 : 0;
@@ -235,22 +243,23 @@ __device__ __forceinline__ void sin32(int dbg, float* v, unsigned char* yarr, in
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = SIN_(v[i]);
 }
+#define LDS_T(addr) ((TC_DBG(dbg) & 64) ? make_float4(0.f, 0.f, 0.f, 0.f) : lds128(addr, tok))
 __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool skip, bool last, int has_beta, int n0, int H2, float* v,
                                           uint32_t a_base, int row, uint32_t tF, uint32_t tV, uint32_t sunb_row, uint32_t betab_row,
-                                          float px, float py, float pz, const EpiStash& es, bool do_park, uint32_t park,
+                                          float px, float py, float pz, const EpiStash& es, uint64_t* slab_bar, uint32_t slab_par,
                                           float& sig_dot, float& beta_dot, float& rgb0, float& rgb1, float& rgb2, float& sun_dot) {
     const int H = 2 * H2;
     if (kind == GK_TRUNK) {
         if (skip) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
+                float4 w = LDS_T(tF + (uint32_t)(n0 + i) * 16u);
                 v[i] += fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x)));
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+                float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
                 v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
         }
@@ -258,46 +267,46 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
         if (last) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                float4 w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
+                float4 w = LDS_T(tV + (uint32_t)(n0 + i) * 4u);
                 sig_dot = fmaf(w.x, v[i], sig_dot); sig_dot = fmaf(w.y, v[i + 1], sig_dot);
                 sig_dot = fmaf(w.z, v[i + 2], sig_dot); sig_dot = fmaf(w.w, v[i + 3], sig_dot);
             }
         }
-        if (!(TC_DBG(dbg) & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
+        if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act32(a_base, row, n0, v); }
     } else if (kind == GK_FEAT) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-            float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+            float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
-        if (!(TC_DBG(dbg) & 4)) { if (do_park) park_act32(park, v); else store_act32(a_base, row, n0, v); }
+        if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act32(a_base, row, n0, v); }
     } else if (kind == GK_HEADA) {
         if (has_beta && n0 < H2) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                float4 b = lds128(betab_row + (uint32_t)(n0 + i) * 4u, tok);
+                float4 b = LDS_T(betab_row + (uint32_t)(n0 + i) * 4u);
                 v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
             sin32(dbg, v, es.y0, es.gt, H2, n0, row);
             if (es.act0) atom_store32(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) beta_dot = fmaf(lds128(tF + (uint32_t)(n0 + i) * 16u, tok).y, v[i], beta_dot);
+            for (int i = 0; i < 32; ++i) beta_dot = fmaf(LDS_T(tF + (uint32_t)(n0 + i) * 16u).y, v[i], beta_dot);
         } else {
             const int m0 = has_beta ? n0 - H2 : n0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += lds128(tF + (uint32_t)(n0 + i) * 16u, tok).x;
+            for (int i = 0; i < 32; ++i) v[i] += LDS_T(tF + (uint32_t)(n0 + i) * 16u).x;
             sin32(dbg, v, es.y1, es.gt, H2, m0, row);
             if (es.act1) atom_store32(es.act1, es.gt, (H2 + 63) >> 6, row, m0, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
+                float4 w = LDS_T(tF + (uint32_t)(n0 + i) * 16u);
                 rgb0 = fmaf(w.y, v[i], rgb0); rgb1 = fmaf(w.z, v[i], rgb1); rgb2 = fmaf(w.w, v[i], rgb2);
             }
         }
     } else if (kind == GK_SUN1) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-            float4 b = lds128(sunb_row + (uint32_t)(n0 + i) * 4u, tok);
+            float4 b = LDS_T(sunb_row + (uint32_t)(n0 + i) * 4u);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
         sin32(dbg, v, es.y0, es.gt, H2, n0, row);
@@ -305,7 +314,7 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
     } else {   // GK_SUN2 / GK_SUN3
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-            float4 b = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
+            float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
         sin32(dbg, v, es.y0, es.gt, H2, n0, row);
@@ -314,13 +323,14 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
             if (es.act0) atom_store32(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                float4 w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
+                float4 w = LDS_T(tV + (uint32_t)(n0 + i) * 4u);
                 sun_dot = fmaf(w.x, v[i], sun_dot); sun_dot = fmaf(w.y, v[i + 1], sun_dot);
                 sun_dot = fmaf(w.z, v[i + 2], sun_dot); sun_dot = fmaf(w.w, v[i + 3], sun_dot);
             }
         }
     }
 }
+#undef LDS_T
 #undef SIN_
 // CG = 1: one CTA per 128-point tile.  CG = 2: CTA pair (cta_group::2): two SMs run two tiles in lockstep, the
 // leader issues M=256 MMAs that read each CTA's own activation tile and HALF of every weight tile from each
@@ -339,8 +349,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
     const float* T = reinterpret_cast<const float*>(A.packed + P.tables_base);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); mbar_init(&sm.peer_full[i], 1); }
-        mbar_init(sm.acc_full, 1); mbar_init(sm.acc_full2, 1); mbar_init(sm.a_ready, CG); mbar_init(sm.a_ready2, CG);     // one elected arrival per CTA of the pair
+        // leader of a pair: a stage is full when its own copy has landed AND the peer has reported its half (relay arrival)
+        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], (CG == 2 && cta_rank == 0) ? 2 : 1); mbar_init(&sm.empty[i], 1); mbar_init(&sm.peer_full[i], 1); }
+        mbar_init(sm.acc_full, 1); mbar_init(sm.acc_full2, 1); mbar_init(sm.a_ready, CG); mbar_init(sm.a_ready2, CG);
+        for (int i = 0; i < 4; ++i) mbar_init(&sm.slab_free[i], 1);     // one elected arrival per CTA of the pair
         fence_barrier_init();
     }
     if (CG == 2) { __syncthreads(); cluster_sync_all(); }       // both CTAs of the pair are running and their barriers are initialised
@@ -382,102 +394,118 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA) / weight-arrival relay (peer CTA) =================
-        int st = 0; uint32_t ph = 0, ready_ph = 0, ready2_ph = 0;
+        int st = 0; uint32_t ph = 0, ready_ph = 0;
         const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
         const uint32_t tmem = __shfl_sync(0xffffffffu, *sm.tmem_ptr, 0);      // provably warp-uniform copy of the TMEM base
         if (CG == 2 && cta_rank == 1) {
-            // the leader's MMA reads this CTA's half of every weight tile: tell it when each stage has landed
+            // The leader's MMA reads this CTA's half of every weight tile: when a stage has landed here, arrive on the LEADER's
+            // full barrier of that stage (count 2 there: its own copy + this arrival).  Relaxed: a cluster-scope release costs
+            // ~1000 cycles per arrival and the data were delivered by the async proxy before this CTA's barrier completed.
+            const uint32_t leader_full = mapa_u32(smem_u32(sm.full), 0);
             for (int wk = unit; wk < n_work; wk += n_units)
                 for (int t = 0; t < tiles_per_group; ++t)
                     for (int gi = 0; gi < P.n_gemms; ++gi) {
                         const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
                         for (int i = 0; i < n; ++i) {
                             mbar_wait(&sm.full[st], ph, 5);
-                            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sm.peer_full[st]), 0));   // a release here costs ~1000 cycles per stage
+                            if (lane == 0) mbar_arrive_cluster_relaxed(leader_full + (uint32_t)st * 8u);
                             __syncwarp();
                             if (++st == P.n_stages) { st = 0; ph ^= 1; }
                         }
                     }
         } else {
-            // Single-thread issue: per stage wait for the weight tile, issue its K-steps (descriptors are 64-bit adds on
-            // precomputed bases), commit the stage back to the producer (and the accumulator to the epilogue at the end).
+            // Single-thread issue.  The loop is latency-critical: one elected region issues up to two weight stages (8 MMAs,
+            // 1024 tensor cycles) and must cost less than that -- every lane polls the barriers (no lane-0 block + __syncwarp),
+            // the GEMM's fields live in registers, descriptors are 64-bit adds on precomputed bases.
             const uint64_t a_desc0 = umma_desc_k_sw128(a_base), b_desc0 = umma_desc_k_sw128(b_base);
+            const uint32_t stage_desc = (uint32_t)(stage_bytes >> 4);
+            const bool deep = P.n_stages >= 4;
+#ifdef SNB_TC_PROBE
+            int itile = 0;
+#endif
             for (int wk = unit; wk < n_work; wk += n_units) {
                 for (int t = 0; t < tiles_per_group; ++t) {
+#ifdef SNB_TC_PROBE
+                    const bool trace_tile = blockIdx.x == 0 && itile++ == 1; int trace_n = 0;
+#endif
                     for (int gi = 0; gi < P.n_gemms; ++gi) {
-                        const TcGemm& g = P.g[gi];
+                        const int k_slabs = P.g[gi].k_slabs, n_chunks = P.g[gi].n_chunks, chunk_n = P.g[gi].chunk_n, K = P.g[gi].K;
+                        const int k_early = P.g[gi].k_early, free_slabs = P.g[gi].free_slabs;
+                        const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)chunk_n) : umma_idesc_f16((uint32_t)chunk_n);
 #ifdef SNB_TC_PROGRESS
                         if (g_hang_host && blockIdx.x < 16 && lane == 0) ((volatile unsigned int*)g_hang_host)[64 + blockIdx.x * 8 + 3] = (unsigned)(wk << 16 | t << 8 | gi);
 #endif
-                        mbar_wait(sm.a_ready, ready_ph, 2);
-                        ready_ph ^= 1;
-                        tc_fence_after();
-                        const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)g.chunk_n) : umma_idesc_f16((uint32_t)g.chunk_n);
-                        const int n_st = g.n_chunks * g.k_slabs;
-                        int j = 0, s = 0;
-                        int n_early = g.k_early;          // stages (all of N-chunk 0) that only need the first ready signal
-                        // Every lane polls the barriers (a lane-0 poll + __syncwarp costs ~100 cycles per stage) and, when the ring
-                        // is deep enough, one elected region issues TWO stages (8 MMAs): the per-region issue overhead (~400 cycles,
-                        // profiles/mma_ring_probe*.py) then stays below the 2 x 512 tensor cycles it feeds.
-                        for (int i = 0; i < n_st;) {
-                            if (i == n_early) {           // the rest of the input tile / the accumulator columns of the later chunks
-                                mbar_wait(sm.a_ready2, ready2_ph, 7);
-                                ready2_ph ^= 1; n_early = -1;
-                                tc_fence_after();
-                            }
-                            const bool pair = P.n_stages >= 4 && s + 1 < g.k_slabs && i + 1 != n_early;
-                            int st1 = st + 1; uint32_t ph1 = ph; if (st1 == P.n_stages) { st1 = 0; ph1 ^= 1; }
-                            int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
-                            int ksteps1 = g.K - (s + 1) * 64; ksteps1 = (ksteps1 > 64 ? 64 : ksteps1) / 16;
-                            const uint64_t da = a_desc0 + (uint64_t)((uint32_t)s * (kSlabBytes >> 4));
-                            const uint64_t db = b_desc0 + (uint64_t)((uint32_t)st * (uint32_t)(stage_bytes >> 4));
-                            const uint64_t da1 = da + (uint64_t)(kSlabBytes >> 4);
-                            const uint64_t db1 = b_desc0 + (uint64_t)((uint32_t)st1 * (uint32_t)(stage_bytes >> 4));
-                            const uint32_t d_tm = tmem + (uint32_t)(j * g.chunk_n);
-                            mbar_wait(&sm.full[st], ph, 3);
-                            if (CG == 2) mbar_wait(&sm.peer_full[st], ph, 6);
-                            if (pair) {
-                                mbar_wait(&sm.full[st1], ph1, 3);
-                                if (CG == 2) mbar_wait(&sm.peer_full[st1], ph1, 6);
-                            }
-                            tc_fence_after();
-                            if (elect_one()) {        // warp-uniform operands + elect: UTCHMMA takes uniform registers directly
-                                for (int k = 0; k < ksteps; ++k) {
-                                    if (CG == 2) umma_f16_ss_2cta(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
-                                    else umma_f16_ss(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
-                                }
-                                if (CG == 2) umma_commit_2cta(&sm.empty[st], 3); else umma_commit(&sm.empty[st]);
-                                if (pair) {
-                                    for (int k = 0; k < ksteps1; ++k) {
-                                        if (CG == 2) umma_f16_ss_2cta(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
-                                        else umma_f16_ss(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
-                                    }
-                                    if (CG == 2) umma_commit_2cta(&sm.empty[st1], 3); else umma_commit(&sm.empty[st1]);
-                                }
-                                const bool chunk_done = s + (pair ? 1 : 0) == g.k_slabs - 1;      // accumulator of N-chunk j is complete
-                                // one barrier per N-chunk index: two commits of one GEMM on a single barrier could both land before the
-                                // epilogue looks at it (it may still be draining its stash copy), and the parity wait would miss a phase
-                                if (chunk_done) {
-#ifdef SNB_V_ONE_ACC
-                                    if (CG == 2) umma_commit_2cta(sm.acc_full, 3); else umma_commit(sm.acc_full);
-#else
-                                    if (j == 0) { if (CG == 2) umma_commit_2cta(sm.acc_full, 3); else umma_commit(sm.acc_full); }
-                                    else { if (CG == 2) umma_commit_2cta(sm.acc_full2, 3); else umma_commit(sm.acc_full2); }
+                        mbar_wait(sm.a_ready, ready_ph, 2);          // (both ready barriers flip once per GEMM: one parity)
+                        for (int j = 0; j < n_chunks; ++j) {
+                            const uint32_t d_tm = tmem + (uint32_t)(j * chunk_n);
+                            for (int s = 0; s < k_slabs;) {
+                                if (j == 0 && s == k_early) mbar_wait(sm.a_ready2, ready_ph, 7);     // the rest of the input tile / accumulator columns of the later chunks
+                                const bool pair = deep && s + 1 < k_slabs && !(j == 0 && s + 1 == k_early);
+                                int st1 = st + 1; uint32_t ph1 = ph; if (st1 == P.n_stages) { st1 = 0; ph1 ^= 1; }
+                                const uint64_t da = a_desc0 + (uint64_t)((uint32_t)s * (kSlabBytes >> 4));
+                                const uint64_t db = b_desc0 + (uint64_t)((uint32_t)st * stage_desc);
+                                const uint64_t db1 = b_desc0 + (uint64_t)((uint32_t)st1 * stage_desc);
+                                int ksteps = K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) >> 4;
+                                int ksteps1 = K - (s + 1) * 64; ksteps1 = (ksteps1 > 64 ? 64 : ksteps1) >> 4;
+#ifdef SNB_TC_PROBE
+                                const bool tr = trace_tile && (gi == 1 || gi == 2) && trace_n < 40 && lane == 0;
+                                if (tr) g_tc_dbg[(20 + trace_n) * 4 + 0] = clock64();
 #endif
+                                mbar_wait(&sm.full[st], ph, 3);           // (pair mode: this CTA's copy and the peer's relay arrival)
+                                if (pair) mbar_wait(&sm.full[st1], ph1, 3);
+                                tc_fence_after();
+#ifdef SNB_TC_PROBE
+                                if (tr) g_tc_dbg[(20 + trace_n) * 4 + 1] = clock64();
+#endif
+                                if (elect_one()) {        // warp-uniform operands + elect: UTCHMMA takes uniform registers directly
+                                    if (ksteps == 4) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            if (CG == 2) umma_f16_ss_2cta(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
+                                            else umma_f16_ss(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
+                                        }
+                                    } else {
+                                        for (int k = 0; k < ksteps; ++k) {
+                                            if (CG == 2) umma_f16_ss_2cta(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
+                                            else umma_f16_ss(d_tm, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (s | k) != 0);
+                                        }
+                                    }
+                                    if (CG == 2) umma_commit_2cta(&sm.empty[st], 3); else umma_commit(&sm.empty[st]);
+                                    if (j >= 1 && s < free_slabs) { if (CG == 2) umma_commit_2cta(&sm.slab_free[s], 3); else umma_commit(&sm.slab_free[s]); }
+                                    if (pair) {
+                                        const uint64_t da1 = da + (uint64_t)(kSlabBytes >> 4);
+                                        if (ksteps1 == 4) {
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k) {
+                                                if (CG == 2) umma_f16_ss_2cta(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
+                                                else umma_f16_ss(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
+                                            }
+                                        } else {
+                                            for (int k = 0; k < ksteps1; ++k) {
+                                                if (CG == 2) umma_f16_ss_2cta(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
+                                                else umma_f16_ss(d_tm, da1 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), idesc, 1);
+                                            }
+                                        }
+                                        if (CG == 2) umma_commit_2cta(&sm.empty[st1], 3); else umma_commit(&sm.empty[st1]);
+                                        if (j >= 1 && s + 1 < free_slabs) { if (CG == 2) umma_commit_2cta(&sm.slab_free[s + 1], 3); else umma_commit(&sm.slab_free[s + 1]); }
+                                    }
+                                    // one barrier per N-chunk index: two commits of one GEMM on a single barrier could both land before the
+                                    // epilogue looks at it (it may still be draining its stash copy), and the parity wait would miss a phase
+                                    if (s + (pair ? 2 : 1) == k_slabs) {
+                                        if (j == 0) { if (CG == 2) umma_commit_2cta(sm.acc_full, 3); else umma_commit(sm.acc_full); }
+                                        else { if (CG == 2) umma_commit_2cta(sm.acc_full2, 3); else umma_commit(sm.acc_full2); }
+                                    }
                                 }
-                            }
-                            __syncwarp();
-                            const int adv = pair ? 2 : 1;
-                            i += adv;
-                            for (int q = 0; q < adv; ++q) {
-                                if (++st == P.n_stages) { st = 0; ph ^= 1; }
-                                if (++s == g.k_slabs) { s = 0; ++j; }
+                                __syncwarp();
+#ifdef SNB_TC_PROBE
+                                if (tr) { g_tc_dbg[(20 + trace_n) * 4 + 2] = clock64(); g_tc_dbg[(20 + trace_n) * 4 + 3] = (long long)(gi << 16 | (j * k_slabs + s) << 8 | (pair ? 1 : 0)); }
+                                if (trace_tile && (gi == 1 || gi == 2)) ++trace_n;
+#endif
+                                if (pair) { s += 2; st = st1 + 1; ph = ph1; if (st == P.n_stages) { st = 0; ph ^= 1; } }
+                                else { s += 1; st = st1; ph = ph1; }
                             }
                         }
-                        if (n_early >= 0) {               // every stage was an early one: still consume the second signal
-                            mbar_wait(sm.a_ready2, ready2_ph, 7);
-                            ready2_ph ^= 1;
-                        }
+                        ready_ph ^= 1;
                     }
                 }
             }
@@ -616,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, kEpiThreads);                  // everyone is done with the layer-0 table
+                named_bar_sync(1, kEpiThreads);                  // the whole input tile of the first GEMM is in place
                 if (sb && tid_e == 0) { bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
                 {   const TcGemm& g0 = P.g[0];
                     if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
@@ -636,8 +664,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     named_bar_sync(1, kEpiThreads);              // tables of this GEMM are in shared memory
                     TC_MARK(gi, 0);
                     // N-chunks (<=256 columns) complete one after the other: the epilogue of chunk 0 runs while the tensor core
-                    // works on chunk 1.  Its fp16 results cannot go to the A tile yet (the MMAs still read it), so they are
-                    // parked in the drained accumulator columns and moved once the last chunk has been committed.
+                    // works on chunk 1.  Chunk 1's MMAs walk the K-slabs in order and release each one (slab_free[]) as soon as
+                    // they are done with it, so chunk 0's fp16 results go straight into the low K-slabs of the tile.
                     const int kind = g.kind, N = g.N, n_chunks = g.n_chunks, chunk_n = g.chunk_n;
                     const bool skip = g.skip != 0, last = g.last != 0;
                     const bool stores = kind == GK_TRUNK || kind == GK_FEAT || kind == GK_SUN1 || kind == GK_SUN2;
@@ -665,35 +693,58 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                             else mbar_wait(sm.acc_full2, (uint32_t)(tile_seq * P.n_two + g.two_idx) & 1u, 4);
                         }
 #endif
+#ifdef SNB_TC_PROBE
+                        if (gi == 1 && ch == 1) TC_MARK(53, 0);
+#endif
                         named_bar_sync(2, kEpiThreads);
+#ifdef SNB_TC_PROBE
+                        if (gi == 1 && ch == 1) TC_MARK(53, 1);
+#endif
                         tc_fence_after();
-                        if (ch == 0) { tok = fresh_token((uint32_t)gi); TC_MARK(gi, 1); }
+                        if (ch == 0) { tok = fresh_token((uint32_t)gi); TC_MARK(gi, 1); } else { TC_MARK(gi, 3); }
                         const bool final_chunk = ch == n_chunks - 1;
-                        if (final_chunk && stores && n_chunks > 1) {
-                            for (int n0 = half * 32; n0 < ch * chunk_n; n0 += 32 * kEpiSub) unpark_act32(tm_row + (uint32_t)n0, a_base, row, n0);
-                        }
-                        if (final_chunk && next_early) {
-                            // Every MMA of this GEMM has completed and the earlier chunks are drained: the low K-slabs of the next
-                            // GEMM's input (or, after HEADA, the untouched tile) and the accumulator columns of its chunk 0 are
-                            // ready, so its MMAs run underneath the epilogue of this last chunk.
-                            tc_fence_before();
-                            fence_proxy_async_smem();
-                            named_bar_sync(1, kEpiThreads);
-                            signal_ready(0);
-                            early_signaled = true;
-                        }
                         for (int n0 = ch * chunk_n + half * 32; n0 < (ch + 1) * chunk_n && n0 < N; n0 += 32 * kEpiSub) {
                             float va[32];
+#ifdef SNB_TC_PROBE
+                            const int it_ = (n0 - ch * chunk_n) >> 7;
+                            if (gi == 1 && ch == 1 && it_ < 2) TC_MARK(54 + it_, 0);
+#endif
                             if (!(TC_DBG(A.dbg) & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
                             else { for (int i = 0; i < 32; ++i) va[i] = 0.01f * i; }
+#ifdef SNB_TC_PROBE
+                            if (gi == 1 && ch == 1 && it_ < 2) TC_MARK(54 + it_, 1);
+#endif
                             epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz, es,
-                                      stores && !final_chunk, tm_row + (uint32_t)n0,
+                                      (stores && !final_chunk) ? sm.slab_free : nullptr, (uint32_t)((tile_counter - 1) * P.n_store2 + g.store2_idx) & 1u,
                                       sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
+#ifdef SNB_TC_PROBE
+                            if (gi == 1 && ch == 1 && it_ < 2) TC_MARK(54 + it_, 2);
+#endif
                         }
-                        if (!final_chunk) { tmem_st_wait(); tc_fence_before(); }
+                        if (!final_chunk) {
+                            tc_fence_before();
+                            if (next_early) {
+                                // Chunk 0 is drained and its results sit (fenced) in the low K-slabs: the next GEMM's first MMAs may be
+                                // queued right behind this GEMM's chunk 1 -- they touch neither its accumulator columns nor the high
+                                // K-slabs the last chunk's epilogue is about to write -- so the tensor pipe never drains between layers.
+                                if (!(TC_DBG(A.dbg) & 32)) fence_proxy_async_smem();
+                                named_bar_sync(1, kEpiThreads);
+                                signal_ready(0);
+                                early_signaled = true;
+                            }
+                        }
                     }
+#ifdef SNB_TC_PROBE
+                    if (gi == 1) TC_MARK(52, 0);
+#endif
                     tc_fence_before();
-                    fence_proxy_async_smem();
+#ifdef SNB_TC_PROBE
+                    if (gi == 1) TC_MARK(52, 1);
+#endif
+                    if (!(TC_DBG(A.dbg) & 32)) fence_proxy_async_smem();
+#ifdef SNB_TC_PROBE
+                    if (gi == 1) TC_MARK(52, 2);
+#endif
                     named_bar_sync(1, kEpiThreads);              // all TMEM reads / A writes / table reads of this GEMM done
                     TC_MARK(gi, 2);
                     if (sb && tid_e == 0) {                      // dump the activation tile this GEMM produced (A-tile image = atoms)
@@ -876,10 +927,12 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     M.sky0_w = L.sky0.w; M.sky0_b = L.sky0.b; M.sky2_w = L.sky2.w; M.sky2_b = L.sky2.b;
     M.beta0_w = L.beta0.w; M.beta0_b = L.beta0.b; M.beta0_ld = L.beta0.n_in; M.beta2_w = L.beta2.w; M.beta2_b = L.beta2.b;
 
-    tc_pack_kernel<<<dim3(64, P.n_gemms), 256, 0, st>>>(P, io->params, A.packed);
-    SNB_CHECK_LAUNCH();
-    tc_pack_misc_kernel<<<8, 256, 0, st>>>(P, M, io->params, A.packed);
-    SNB_CHECK_LAUNCH();
+    if (!p->weights_packed) {      // (caller's promise otherwise: same parameter values, workspace untouched since we packed them)
+        tc_pack_kernel<<<dim3(64, P.n_gemms), 256, 0, st>>>(P, io->params, A.packed);
+        SNB_CHECK_LAUNCH();
+        tc_pack_misc_kernel<<<8, 256, 0, st>>>(P, M, io->params, A.packed);
+        SNB_CHECK_LAUNCH();
+    }
     const bool train = A.stash_base != nullptr;
     if (cg == 2) {
         auto kern = train ? tc_render_kernel<2, true> : tc_render_kernel<2, false>;

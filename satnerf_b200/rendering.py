@@ -46,7 +46,7 @@ class _Pass(torch.autograd.Function):
         variant = field.variant
         R, S = z.shape
         dev = z.device
-        pd = capi.PassDesc(R, S, rays.shape[1] if rays is not None else 0, int(cfg["sc"]), cfg["precision"], float(cfg["noise_std"]))
+        pd = capi.PassDesc(R, S, rays.shape[1] if rays is not None else 0, int(cfg["sc"]), cfg["precision"], float(cfg["noise_std"]), 0)
         outs = {k: torch.empty(s, device=dev, dtype=torch.float32) for k, s in _out_shapes(variant, R, S).items()}
         stash = {"sigma": torch.empty(R, S, device=dev, dtype=torch.float32)}
         if variant == "nerf":
@@ -59,7 +59,25 @@ class _Pass(torch.autograd.Function):
                 act_stash = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         tensors = dict(params=field.flat_params(), rays=rays, z_vals=z, t_emb=t_emb,
                        noise=noise if cfg["noise_std"] != 0 else None, xyz=xyz, aux_dir=aux_dir, stash=act_stash, **outs, **stash)
-        capi.render_forward(field.desc, pd, tensors)
+        # Inference on the tensor-core path: the packed fp16 weight tiles are kept in a buffer owned by the field and
+        # reused while the parameters are untouched (their autograd version counter and storage are unchanged) --
+        # batched_inference / DSM extraction render many ray batches per weight set.
+        ws = None
+        if not cfg["train"] and cfg["precision"] == capi.FP16_TC:
+            flat = tensors["params"]
+            # (the parameters alias `flat` through `.data`, so each keeps its own version counter)
+            key = (flat.data_ptr(), flat._version, tuple(p._version for p in params), str(dev))
+            need = capi.render_workspace_bytes(field.desc, pd)
+            cache = getattr(field, "_tc_packed", None)
+            if cache is None or cache[0].device != dev or cache[0].numel() < need:
+                cache = [torch.empty(max(need, 1), dtype=torch.uint8, device=dev), None]
+                field._tc_packed = cache
+            ws = cache[0]
+            if need and cache[1] == key:
+                pd.weights_packed = 1
+            cache[1] = key
+        capi.render_forward(field.desc, pd, tensors, workspace=ws)
+        pd.weights_packed = 0
         ctx.act_stash = act_stash
         ctx.field, ctx.pd, ctx.variant = field, pd, variant
         ctx.keys = list(outs)

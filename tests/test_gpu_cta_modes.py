@@ -42,3 +42,29 @@ def test_cta_pair_equals_single_cta(monkeypatch, h, n_rays, S, train):
         for n in ga:
             assert torch.isfinite(ga[n]).all()
             assert torch.equal(ga[n], gb[n]), n
+
+
+def test_packed_weight_cache_follows_parameter_updates():
+    """Inference keeps the packed fp16 weight tiles between calls (snb_pass_desc.weights_packed); an in-place parameter
+    update (optimizer step, load_state_dict) must invalidate them."""
+    import copy
+
+    import satnerf_b200 as sb
+    args = make_args(fc_units=256, n_samples=64, precision="tc")
+    torch.manual_seed(11)
+    ms = {"coarse": sb.load_model(args).cuda(), "t": torch.nn.Embedding(30, 4).cuda()}
+    rays, ts = orc.synthetic_sat_rays(300, seed=12)
+    g = torch.Generator().manual_seed(13)
+    draws = [torch.rand(300, 64, generator=g), torch.randn(300, 64, generator=g)]
+    with torch.no_grad():
+        a = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
+        b = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)          # served from the cached tiles
+        assert all(torch.equal(a[k], b[k]) for k in a)
+        for p in ms["coarse"].parameters():
+            p.mul_(1.05)                                                             # in-place update: version counter moves
+        c = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
+        fresh = {"coarse": sb.load_model(args).cuda(), "t": ms["t"]}
+        fresh["coarse"].load_state_dict(copy.deepcopy(ms["coarse"].state_dict()))
+        d = sb.render_rays(fresh, args, rays.cuda(), ts.cuda(), _draws=draws)
+    assert not torch.equal(a["rgb_coarse"], c["rgb_coarse"])
+    assert all(torch.equal(c[k], d[k]) for k in c)

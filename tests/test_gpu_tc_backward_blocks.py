@@ -49,7 +49,7 @@ def test_forward_stash_matches_oracle_activations():
         h = torch.sin(y); acts.append(h); pres.append(y)
     feat = F.linear(h, p["feats_from_xyz.weight"], p["feats_from_xyz.bias"])
     field = field.cuda()
-    pd = capi.PassDesc(R, S, 11, 0, capi.FP16_TC, 0.0)
+    pd = capi.PassDesc(R, S, 11, 0, capi.FP16_TC, 0.0, 0)
     nbytes = capi.render_stash_bytes(field.desc, pd)
     stash = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     outs = {k: torch.empty(s, device="cuda") for k, s in dict(rgb=(R, 3), depth=(R,), weights=(R, S), transparency=(R, S), albedo=(R, S, 3),

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(capi.exported_symbols())
-    assert lib.snb_abi_version() == 1
+    assert lib.snb_abi_version() == 2
 
 
 @pytest.mark.parametrize("model,h", [("sat-nerf", 64), ("sat-nerf", 512), ("s-nerf", 256), ("nerf", 256)])
