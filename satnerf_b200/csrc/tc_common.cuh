@@ -72,7 +72,7 @@ struct Smem {
     unsigned char* b;        // weight ring: n_stages x stage_bytes
     float* tblF;             // [N][4] or [N]
     float* tblV;             // [N]
-    float *z, *sg, *al0, *al1, *al2, *sn, *bt, *wt;   // per-point tables of the current group (kMaxGroupPts each)
+    float *z, *sg, *al0, *al1, *al2, *sn, *bt, *wt;   // per-point tables of the current group (kMaxGroupPts each); wt = xyz scratch of the tile [3][128]
     float* sunb;             // [kMaxGroupRays][H2] per-ray bias of sun_v_net.0 (bias + W[:,H:H+3] sun_d)
     float* betab;            // [kMaxGroupRays][H2] per-ray bias of beta_from_xyz.0
     float* skyc;             // [kMaxGroupRays][4]
@@ -145,6 +145,11 @@ __device__ __forceinline__ void yb_store32(unsigned char* slot, const float* y) 
         d[c] = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
                           pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
     }
+}
+// 8 consecutive pre-activations (16 bytes of a yb slot)
+__device__ __forceinline__ void yb_store8(unsigned char* p16, const float* x) {
+    *reinterpret_cast<uint4*>(p16) = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
+                                                 pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
 }
 // address of the 16-byte chunk (features k..k+7, k % 8 == 0) of point `row` of tile gt in an atoms array with `fgs` groups
 __device__ __forceinline__ unsigned char* atom_chunk(unsigned char* arr, int gt, int fgs, int row, int k) {

@@ -617,25 +617,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 const uint32_t sunb_row = smem_u32(sm.sunb) + (uint32_t)(rl * H2) * 4u;
                 const uint32_t betab_row = smem_u32(sm.betab) + (uint32_t)(rl * H2) * 4u;
                 // ---- trunk layer 0 on CUDA cores: sin(30 (W0 x + b0)), K = 3 (satnerf.py:105-106) ----
+                if (half == 0) { sm.wt[row] = px; sm.wt[kTile + row] = py; sm.wt[2 * kTile + row] = pz; }     // positions of the tile's points
                 table_copy(sm.tblF, T + P.l0_tbl, H * 16, tid_e);
                 cp_async_wait_all();
                 named_bar_sync(1, kEpiThreads);
                 const uint32_t tok0 = fresh_token(0xffffu);
                 const int l0_split = P.g[0].k_early * 64;         // columns published with the first ready signal (0: none)
+                // Thread mapping of this layer: 4 rows (lane + 32k) x 8 columns per step, so that one 16-byte table read
+                // ([wx wy wz b] of a column: a 512-byte register fill per warp) feeds 4 outputs instead of 1 -- with one row per
+                // thread the table reads alone took ~8 000 cycles of the shared-memory pipe per tile.
+                float rx[4], ry[4], rz[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { rx[k] = sm.wt[lane + 32 * k]; ry[k] = sm.wt[kTile + lane + 32 * k]; rz[k] = sm.wt[2 * kTile + lane + 32 * k]; }
                 for (int pass = 0; pass < 2; ++pass) {
                     const int c_lo = pass ? l0_split : 0, c_hi = pass ? H : l0_split;
-                    for (int n0 = c_lo + half * 32; n0 < c_hi; n0 += 32 * kEpiSub) {
-                        float v[32];
+                    for (int n0 = c_lo + (warp - 2) * 8; n0 < c_hi; n0 += 8 * kEpiWarps) {
+                        float4 w[8];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok0);
-                            float y = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
-                            v[i] = __fmul_rn(30.0f, y);
+                        for (int i = 0; i < 8; ++i) w[i] = lds128(tF + (uint32_t)(n0 + i) * 16u, tok0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int r = lane + 32 * k;
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float y = fmaf(w[i].z, rz[k], fmaf(w[i].y, ry[k], fmaf(w[i].x, rx[k], w[i].w)));
+                                v[i] = __fmul_rn(30.0f, y);
+                            }
+                            if (sb) yb_store8(yb_slot(sb + A.stash.y[0], gt, H, n0, r) + (n0 & 31) * 2, v);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = __sinf(v[i]);
+                            sts128(a_chunk_addr(a_base, r, n0), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
                         }
-                        if (sb) yb_store32(yb_slot(sb + A.stash.y[0], gt, H, n0, row), v);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __sinf(v[i]);
-                        store_act32(a_base, row, n0, v);
                     }
                     if (pass == 0 && l0_split > 0) {              // low K-slabs of the first GEMM's input are in place
                         fence_proxy_async_smem();
