@@ -10,9 +10,10 @@ a = argparse.Namespace(model="sat-nerf", n_samples=64, n_importance=0, noise_std
                        fc_units=int(sys.argv[1]) if len(sys.argv) > 1 else 512, t_embbeding_tau=4, t_embbeding_vocab=30, precision="tc")
 torch.manual_seed(0)
 ms = {"coarse": sb.load_model(a).cuda(), "t": torch.nn.Embedding(30, 4).cuda()}
-rays, ts = orc.synthetic_sat_rays(4096, seed=1)
+train = len(sys.argv) > 2 and sys.argv[2] == "train"      # training-mode forward (activation stash) on 1024 rays
+rays, ts = orc.synthetic_sat_rays(1024 if train else 4096, seed=1)
 rays, ts = rays.cuda(), ts.cuda()
-with torch.no_grad():
+with torch.enable_grad() if train else torch.no_grad():
     for _ in range(3):
         sb.render_rays(ms, a, rays, ts)
 torch.cuda.synchronize()

@@ -126,6 +126,15 @@ __device__ __forceinline__ void store_act32(uint32_t a_base, int row, int k0, co
         sts128(a_chunk_addr(a_base, row, k0 + c * 8), pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
     }
 }
+// NC (multiple of 8) consecutive activations of one row as fp16 into the swizzled A tile
+template <int NC>
+__device__ __forceinline__ void store_act_cols(uint32_t a_base, int row, int k0, const float* v) {
+#pragma unroll
+    for (int c = 0; c < NC / 8; ++c) {
+        const float* x = v + c * 8;
+        sts128(a_chunk_addr(a_base, row, k0 + c * 8), pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
+    }
+}
 // ---- training stash helpers -------------------------------------------------------------------------------
 // pre-activations are stashed as fp16 revolutions r = frac(y / 2pi) in [-0.5, 0.5]: cos(2 pi r) = cos(y) with a uniform
 // absolute error (fp16 ulp 2.4e-4 rev = 1.5e-3 rad) whatever |y| is (first layer: y = 30 (W0 x + b0) reaches +-50 rad)
@@ -146,6 +155,16 @@ __device__ __forceinline__ void yb_store32(unsigned char* slot, const float* y) 
                           pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
     }
 }
+template <int NC>
+__device__ __forceinline__ void yb_store_cols(unsigned char* p, const float* y) {      // p: 16-byte aligned position inside a yb slot
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int c = 0; c < NC / 8; ++c) {
+        const float* x = y + c * 8;
+        d[c] = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
+                          pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
+    }
+}
 // 8 consecutive pre-activations (16 bytes of a yb slot)
 __device__ __forceinline__ void yb_store8(unsigned char* p16, const float* x) {
     *reinterpret_cast<uint4*>(p16) = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
@@ -154,6 +173,15 @@ __device__ __forceinline__ void yb_store8(unsigned char* p16, const float* x) {
 // address of the 16-byte chunk (features k..k+7, k % 8 == 0) of point `row` of tile gt in an atoms array with `fgs` groups
 __device__ __forceinline__ unsigned char* atom_chunk(unsigned char* arr, int gt, int fgs, int row, int k) {
     return arr + (((size_t)gt * fgs + (k >> 6)) * 16 + (row >> 3)) * 1024 + (size_t)(row & 7) * 128 + (size_t)((((k >> 3) & 7) ^ (row & 7)) << 4);
+}
+template <int NC>
+__device__ __forceinline__ void atom_store_cols(unsigned char* arr, int gt, int fgs, int row, int k0, const float* v) {
+#pragma unroll
+    for (int c = 0; c < NC / 8; ++c) {
+        const float* x = v + c * 8;
+        *reinterpret_cast<uint4*>(atom_chunk(arr, gt, fgs, row, k0 + c * 8)) =
+            make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
+    }
 }
 __device__ __forceinline__ void atom_store32(unsigned char* arr, int gt, int fgs, int row, int k0, const float* v) {
 #pragma unroll

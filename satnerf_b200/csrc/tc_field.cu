@@ -231,20 +231,22 @@ __device__ long long g_tc_dbg[64 * 4];
 #define TC_DBG(x) 0
 #endif
 
-// Epilogue of one 32-column block of one row: v = fp32 accumulators of columns n0..n0+31.
+// Epilogue of NC (16) consecutive columns of one row: v = fp32 accumulators of columns n0..n0+NC-1.
 // Tables live in shared memory (32-bit addresses): tF = [N] floats (F1) or [N][4] (F4), tV = [N] extra vector.
 // Training mode (ys != nullptr): the pre-activations go to the yb stash and activations that are consumed in
 // registers (first layers of the rgb / beta heads, last sun layer) go to their atoms stash.
 struct EpiStash { unsigned char *y0, *y1, *act0, *act1; int gt; };     // 0: first column half of HEADA (beta) / every other kind
 
 #define SIN_(x) ((TC_DBG(dbg) & 1) ? (x) : __sinf(x))
-__device__ __forceinline__ void sin32(int dbg, float* v, unsigned char* yarr, int gt, int F, int n0, int row) {
-    if (yarr) yb_store32(yb_slot(yarr, gt, F, n0, row), v);
+template <int NC>
+__device__ __forceinline__ void sin_cols(int dbg, float* v, unsigned char* yarr, int gt, int F, int n0, int row) {
+    if (yarr) yb_store_cols<NC>(yb_slot(yarr, gt, F, n0, row) + (n0 & 31) * 2, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = SIN_(v[i]);
+    for (int i = 0; i < NC; ++i) v[i] = SIN_(v[i]);
 }
 #define LDS_T(addr) ((TC_DBG(dbg) & 64) ? make_float4(0.f, 0.f, 0.f, 0.f) : lds128(addr, tok))
-__device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool skip, bool last, int has_beta, int n0, int H2, float* v,
+template <int NC>
+__device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool skip, bool last, int has_beta, int n0, int H2, float* v,
                                           uint32_t a_base, int row, uint32_t tF, uint32_t tV, uint32_t sunb_row, uint32_t betab_row,
                                           float px, float py, float pz, const EpiStash& es, uint64_t* slab_bar, uint32_t slab_par,
                                           float& sig_dot, float& beta_dot, float& rgb0, float& rgb1, float& rgb2, float& sun_dot) {
@@ -252,77 +254,77 @@ __device__ __forceinline__ void epi_block(uint32_t tok, int dbg, int kind, bool 
     if (kind == GK_TRUNK) {
         if (skip) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < NC; ++i) {
                 float4 w = LDS_T(tF + (uint32_t)(n0 + i) * 16u);
                 v[i] += fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x)));
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < NC; i += 4) {
                 float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
                 v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
         }
-        sin32(dbg, v, es.y0, es.gt, H, n0, row);
+        sin_cols<NC>(dbg, v, es.y0, es.gt, H, n0, row);
         if (last) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < NC; i += 4) {
                 float4 w = LDS_T(tV + (uint32_t)(n0 + i) * 4u);
                 sig_dot = fmaf(w.x, v[i], sig_dot); sig_dot = fmaf(w.y, v[i + 1], sig_dot);
                 sig_dot = fmaf(w.z, v[i + 2], sig_dot); sig_dot = fmaf(w.w, v[i + 3], sig_dot);
             }
         }
-        if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act32(a_base, row, n0, v); }
+        if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act_cols<NC>(a_base, row, n0, v); }
     } else if (kind == GK_FEAT) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < NC; i += 4) {
             float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
-        if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act32(a_base, row, n0, v); }
+        if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act_cols<NC>(a_base, row, n0, v); }
     } else if (kind == GK_HEADA) {
         if (has_beta && n0 < H2) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < NC; i += 4) {
                 float4 b = LDS_T(betab_row + (uint32_t)(n0 + i) * 4u);
                 v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
-            sin32(dbg, v, es.y0, es.gt, H2, n0, row);
-            if (es.act0) atom_store32(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
+            sin_cols<NC>(dbg, v, es.y0, es.gt, H2, n0, row);
+            if (es.act0) atom_store_cols<NC>(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) beta_dot = fmaf(LDS_T(tF + (uint32_t)(n0 + i) * 16u).y, v[i], beta_dot);
+            for (int i = 0; i < NC; ++i) beta_dot = fmaf(LDS_T(tF + (uint32_t)(n0 + i) * 16u).y, v[i], beta_dot);
         } else {
             const int m0 = has_beta ? n0 - H2 : n0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += LDS_T(tF + (uint32_t)(n0 + i) * 16u).x;
-            sin32(dbg, v, es.y1, es.gt, H2, m0, row);
-            if (es.act1) atom_store32(es.act1, es.gt, (H2 + 63) >> 6, row, m0, v);
+            for (int i = 0; i < NC; ++i) v[i] += LDS_T(tF + (uint32_t)(n0 + i) * 16u).x;
+            sin_cols<NC>(dbg, v, es.y1, es.gt, H2, m0, row);
+            if (es.act1) atom_store_cols<NC>(es.act1, es.gt, (H2 + 63) >> 6, row, m0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < NC; ++i) {
                 float4 w = LDS_T(tF + (uint32_t)(n0 + i) * 16u);
                 rgb0 = fmaf(w.y, v[i], rgb0); rgb1 = fmaf(w.z, v[i], rgb1); rgb2 = fmaf(w.w, v[i], rgb2);
             }
         }
     } else if (kind == GK_SUN1) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < NC; i += 4) {
             float4 b = LDS_T(sunb_row + (uint32_t)(n0 + i) * 4u);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
-        sin32(dbg, v, es.y0, es.gt, H2, n0, row);
-        if (!(TC_DBG(dbg) & 4)) store_act32(a_base, row, n0, v);
+        sin_cols<NC>(dbg, v, es.y0, es.gt, H2, n0, row);
+        if (!(TC_DBG(dbg) & 4)) store_act_cols<NC>(a_base, row, n0, v);
     } else {   // GK_SUN2 / GK_SUN3
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < NC; i += 4) {
             float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
             v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
-        sin32(dbg, v, es.y0, es.gt, H2, n0, row);
-        if (kind == GK_SUN2) { if (!(TC_DBG(dbg) & 4)) store_act32(a_base, row, n0, v); }
+        sin_cols<NC>(dbg, v, es.y0, es.gt, H2, n0, row);
+        if (kind == GK_SUN2) { if (!(TC_DBG(dbg) & 4)) store_act_cols<NC>(a_base, row, n0, v); }
         else {
-            if (es.act0) atom_store32(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
+            if (es.act0) atom_store_cols<NC>(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < NC; i += 4) {
                 float4 w = LDS_T(tV + (uint32_t)(n0 + i) * 4u);
                 sun_dot = fmaf(w.x, v[i], sun_dot); sun_dot = fmaf(w.y, v[i + 1], sun_dot);
                 sun_dot = fmaf(w.z, v[i + 2], sun_dot); sun_dot = fmaf(w.w, v[i + 3], sun_dot);
@@ -716,23 +718,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         tc_fence_after();
                         if (ch == 0) { tok = fresh_token((uint32_t)gi); TC_MARK(gi, 1); } else { TC_MARK(gi, 3); }
                         const bool final_chunk = ch == n_chunks - 1;
-                        for (int n0 = ch * chunk_n + half * 32; n0 < (ch + 1) * chunk_n && n0 < N; n0 += 32 * kEpiSub) {
-                            float va[32];
-#ifdef SNB_TC_PROBE
-                            const int it_ = (n0 - ch * chunk_n) >> 7;
-                            if (gi == 1 && ch == 1 && it_ < 2) TC_MARK(54 + it_, 0);
-#endif
-                            if (!(TC_DBG(A.dbg) & 2)) { tmem_ld32(tm_row + (uint32_t)n0, va); tmem_ld_wait(); }
-                            else { for (int i = 0; i < 32; ++i) va[i] = 0.01f * i; }
-#ifdef SNB_TC_PROBE
-                            if (gi == 1 && ch == 1 && it_ < 2) TC_MARK(54 + it_, 1);
-#endif
-                            epi_block(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, va, a_base, row, tF, tV, sunb_row, betab_row, px, py, pz, es,
-                                      (stores && !final_chunk) ? sm.slab_free : nullptr, (uint32_t)((tile_counter - 1) * P.n_store2 + g.store2_idx) & 1u,
-                                      sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
-#ifdef SNB_TC_PROBE
-                            if (gi == 1 && ch == 1 && it_ < 2) TC_MARK(54 + it_, 2);
-#endif
+                        // 32-column blocks in two 16-column halves: the TMEM load of one half is in flight while the other half goes
+                        // through bias / sin / pack / store (a block-wide load + wait cost ~200 exposed cycles per block)
+                        {
+                            const int n_end = min((ch + 1) * chunk_n, N);
+                            int n0 = ch * chunk_n + half * 32;
+                            bool have = n0 < n_end;
+                            uint32_t va[16], vb[16];
+                            uint64_t* const slab_bar = (stores && !final_chunk) ? sm.slab_free : nullptr;
+                            const uint32_t slab_par = (uint32_t)((tile_counter - 1) * P.n_store2 + g.store2_idx) & 1u;
+                            if (have) tmem_ld16(tm_row + (uint32_t)n0, va);
+                            while (have) {
+                                tmem_ld_wait16(va);
+                                tmem_ld16(tm_row + (uint32_t)(n0 + 16), vb);
+                                epi_cols<16>(tok, A.dbg, kind, skip, last, P.has_beta, n0, H2, reinterpret_cast<float*>(va), a_base, row, tF, tV, sunb_row, betab_row,
+                                             px, py, pz, es, slab_bar, slab_par, sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
+                                tmem_ld_wait16(vb);
+                                const int n1 = n0 + 32 * kEpiSub;
+                                const bool more = n1 < n_end;
+                                if (more) tmem_ld16(tm_row + (uint32_t)n1, va);
+                                epi_cols<16>(tok, A.dbg, kind, skip, last, P.has_beta, n0 + 16, H2, reinterpret_cast<float*>(vb), a_base, row, tF, tV, sunb_row, betab_row,
+                                             px, py, pz, es, slab_bar, slab_par, sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);
+                                n0 = n1; have = more;
+                            }
                         }
                         if (!final_chunk) {
                             tc_fence_before();
