@@ -101,6 +101,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                              // layout: SWIZZLE_128B [61,64)
     return d;
 }
+// K-major operand tile that is ONE K-step (16 fp16 = 32 bytes) wide, 32-byte swizzle: rows of 32 B, 8-row groups 256 B apart
+// (SBO), the two 16-byte chunks of a row swapped when bit 2 of the row is set (address bit 4 ^= bit 7).  Base 256 B aligned.
+__device__ __forceinline__ uint64_t umma_desc_k_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                              // layout: SWIZZLE_32B
+    return d;
+}
 // kind::f16 instruction descriptor: A,B = fp16 (K-major), D = fp32, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);

@@ -25,6 +25,7 @@ enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
 struct TcGemm {
     int kind, N, K, n_chunks, chunk_n, k_slabs, skip, last, fmt, has_vec;
     int free_slabs, store2_idx;      // two-chunk GEMMs that write the tile: K-slabs the last chunk's MMAs release one by one; sequence index
+    int aux;                         // 1: bias (2: + the skip layer's xyz term) comes from one extra K-step on the aux operand tiles
     int two_idx;                     // number of two-chunk GEMMs before this one in the program
     int k_early;                     // K-slabs of the input tile that are valid (and chunk-0 accumulator columns free) at the FIRST
                                      // ready signal; the rest needs the second one (forward kernel only)
@@ -70,6 +71,7 @@ struct TcArgs {
 struct Smem {
     unsigned char* a;        // activation tile: a_slabs x [128 rows x 128 B], 128B-swizzled, K-major
     unsigned char* b;        // weight ring: n_stages x stage_bytes
+    unsigned char* a_aux;    // [128 rows][16 fp16] 32B-swizzled: [1 1 | xyz hi | xyz lo | xyz hi | 0..] (aliases the upper half of tblF)
     float* tblF;             // [N][4] or [N]
     float* tblV;             // [N]
     float *z, *sg, *al0, *al1, *al2, *sn, *bt, *wt;   // per-point tables of the current group (kMaxGroupPts each); wt = xyz scratch of the tile [3][128]
@@ -85,7 +87,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, i
     Smem s; unsigned char* p = base;
     s.a = p; p += (size_t)P.a_slabs * kSlabBytes;
     s.b = p; p += (size_t)P.n_stages * (P.stage_bytes / cg);
-    s.tblF = (float*)p; p += kTblF;
+    s.tblF = (float*)p; s.a_aux = p + kTblF - kTile * 32; p += kTblF;
     s.tblV = (float*)p; p += kTblV;
     float* f = (float*)p;
     s.z = f; s.sg = f + kMaxGroupPts; s.al0 = f + 2 * kMaxGroupPts; s.al1 = f + 3 * kMaxGroupPts; s.al2 = f + 4 * kMaxGroupPts;
@@ -106,6 +108,10 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const TcProgram& P, i
     s.tmem_ptr = (uint32_t*)p;
     return s;
 }
+
+// bytes of one N-chunk of a GEMM in the packed weight stream: k_slabs 128B-swizzled tiles [+ one 32B-swizzled aux tile]
+__host__ __device__ __forceinline__ long long chunk_stream_bytes(const TcGemm& g) { return (long long)g.k_slabs * g.chunk_n * 128 + (g.aux ? g.chunk_n * 32 : 0); }
+__host__ __device__ __forceinline__ long long gemm_stream_bytes(const TcGemm& g) { return g.n_chunks * chunk_stream_bytes(g); }
 
 __device__ __forceinline__ int group_points(const TcArgs& A, int grp) {
     int r0 = grp * A.G; int n = A.R - r0; if (n > A.G) n = A.G; return n * A.S;

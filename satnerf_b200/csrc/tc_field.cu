@@ -53,9 +53,10 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
         TcGemm& g = add(GK_TRUNK, H, H);
         g.skip = i == L.skip; g.last = i == L.n_layers - 1;
         g.src0 = L.trunk[i].w; g.ld0 = L.trunk[i].n_in; g.col0 = g.skip ? L.in_xyz : 0; g.rows0 = H;
-        tables(g, g.skip ? TF_F4 : TF_F1, g.last);
+        g.aux = g.skip ? 2 : 1;                  // bias (+ xyz term of the skip layer) ride on the aux K-step: no epilogue table
+        tables(g, TF_NONE, g.last);
     }
-    { TcGemm& g = add(GK_FEAT, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; tables(g, TF_F1, 0); }
+    { TcGemm& g = add(GK_FEAT, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; g.aux = 1; tables(g, TF_NONE, 0); }
     { int nb = P->has_beta ? H2 : 0;
       TcGemm& g = add(GK_HEADA, nb + H2, H);
       g.src0 = P->has_beta ? L.beta0.w : L.rgb0.w; g.ld0 = P->has_beta ? L.beta0.n_in : L.rgb0.n_in; g.rows0 = P->has_beta ? nb : H2;
@@ -98,7 +99,7 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
     P->sky = tbl; tbl += 4 * H2 + 3 * H2 + 4;     // sky0 [H2][3]+b[H2] as [H2][4]; sky2 [3][H2]; b2[3]
     long long wbytes = 0; int max_stage = 0;
     for (int i = 0; i < ng; ++i) {
-        wbytes += (long long)P->g[i].n_chunks * P->g[i].k_slabs * P->g[i].chunk_n * 128;
+        wbytes += gemm_stream_bytes(P->g[i]);
         if (P->g[i].chunk_n * 128 > max_stage) max_stage = P->g[i].chunk_n * 128;
     }
     P->stage_bytes = max_stage;
@@ -137,8 +138,9 @@ __global__ void tc_pack_kernel(TcProgram P, const float* __restrict__ W, unsigne
     if (gi < P.n_gemms) {
         const TcGemm g = P.g[gi];
         long long base = 0;
-        for (int i = 0; i < gi; ++i) base += (long long)P.g[i].n_chunks * P.g[i].k_slabs * P.g[i].chunk_n * 128;
+        for (int i = 0; i < gi; ++i) base += gemm_stream_bytes(P.g[i]);
         __half* out = reinterpret_cast<__half*>(packed + base);
+        const size_t chunk_halves = (size_t)(chunk_stream_bytes(g) / 2);
         // B tiles: for chunk j, slab s: [chunk_n rows][64 k] fp16, 128-byte swizzle
         const long long total = (long long)g.n_chunks * g.k_slabs * g.chunk_n * 64;
         for (long long e = tid; e < total; e += nthr) {
@@ -149,21 +151,32 @@ __global__ void tc_pack_kernel(TcProgram P, const float* __restrict__ W, unsigne
             float v = 0.f;
             if (k < g.K) v = n < g.rows0 ? W[g.src0 + (long long)n * g.ld0 + g.col0 + k]
                                          : W[g.src1 + (long long)(n - g.rows0) * g.ld1 + g.col1 + k];
-            size_t tile = (size_t)(j * g.k_slabs + s) * g.chunk_n * 64;
+            size_t tile = (size_t)j * chunk_halves + (size_t)s * g.chunk_n * 64;
             size_t off = tile + (size_t)nl * 64 + ((((kk >> 3) ^ (nl & 7)) << 3) | (kk & 7));
             out[off] = __float2half_rn(v);
+        }
+        // aux tile of every chunk: [chunk_n rows][16 k] fp16, 32-byte swizzle.  k = 0,1: bias hi, lo (fp16 pair: exact to 2^-22);
+        // skip layer: k = 2..4 W_xyz hi (x A's xyz hi), 5..7 W_xyz hi (x xyz lo), 8..10 W_xyz lo (x xyz hi); the rest 0
+        if (g.aux) {
+            const long long boff = g.kind == GK_FEAT ? g.src0 + (long long)g.N * g.ld0 : g.src0 + (long long)H * g.ld0;   // bias follows the weight block
+            for (int e = tid; e < g.N * 16; e += nthr) {
+                const int n = e >> 4, k = e & 15, j = n / g.chunk_n, nl = n - j * g.chunk_n;
+                float v = 0.f;
+                if (k < 2) { float b = W[boff + n]; float hi = __half2float(__float2half_rn(b)); v = k == 0 ? hi : b - hi; }
+                else if (g.aux == 2 && k < 11) {
+                    float w = W[g.src0 + (long long)n * g.ld0 + (k - 2) % 3]; float hi = __half2float(__float2half_rn(w));
+                    v = k < 8 ? hi : w - hi;
+                }
+                size_t off = (size_t)j * chunk_halves + (size_t)g.k_slabs * g.chunk_n * 64
+                           + (size_t)(nl >> 3) * 128 + (size_t)(nl & 7) * 16 + (size_t)((((k >> 3) ^ ((nl >> 2) & 1)) << 3) | (k & 7));
+                out[off] = __float2half_rn(v);
+            }
         }
         // epilogue tables
         for (int n = tid; n < g.N; n += nthr) {
             float* t4 = T + g.tbl_off;
             switch (g.kind) {
-                case GK_TRUNK: {
-                    // which trunk layer: recover from the weight offset (bias follows the weight block)
-                    long long boff = g.src0 + (long long)H * g.ld0;
-                    if (g.fmt == TF_F4) { t4[n * 4] = W[boff + n]; for (int c = 0; c < 3; ++c) t4[n * 4 + 1 + c] = W[g.src0 + (long long)n * g.ld0 + c]; }
-                    else t4[n] = W[boff + n];
-                    break; }
-                case GK_FEAT: case GK_SUN2: case GK_SUN3: t4[n] = W[g.src0 + (long long)g.N * g.ld0 + n]; break;
+                case GK_SUN2: case GK_SUN3: t4[n] = W[g.src0 + (long long)g.N * g.ld0 + n]; break;
                 default: break;      // HEADA / per-ray tables are written by tc_pack_misc_kernel
             }
         }
@@ -251,20 +264,7 @@ __device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool s
                                           float px, float py, float pz, const EpiStash& es, uint64_t* slab_bar, uint32_t slab_par,
                                           float& sig_dot, float& beta_dot, float& rgb0, float& rgb1, float& rgb2, float& sun_dot) {
     const int H = 2 * H2;
-    if (kind == GK_TRUNK) {
-        if (skip) {
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                float4 w = LDS_T(tF + (uint32_t)(n0 + i) * 16u);
-                v[i] += fmaf(w.w, pz, fmaf(w.z, py, fmaf(w.y, px, w.x)));
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < NC; i += 4) {
-                float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-            }
-        }
+    if (kind == GK_TRUNK) {          // bias (and the skip layer's xyz term) are already in the accumulator (aux K-step)
         sin_cols<NC>(dbg, v, es.y0, es.gt, H, n0, row);
         if (last) {
 #pragma unroll
@@ -276,11 +276,6 @@ __device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool s
         }
         if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act_cols<NC>(a_base, row, n0, v); }
     } else if (kind == GK_FEAT) {
-#pragma unroll
-        for (int i = 0; i < NC; i += 4) {
-            float4 b = LDS_T(tF + (uint32_t)(n0 + i) * 4u);
-            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-        }
         if (!(TC_DBG(dbg) & 4)) { if (slab_bar) mbar_wait(slab_bar + (n0 >> 6), slab_par, 8); store_act_cols<NC>(a_base, row, n0, v); }
     } else if (kind == GK_HEADA) {
         if (has_beta && n0 < H2) {
@@ -376,9 +371,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
             for (int t = 0; t < tiles_per_group; ++t) {
                 const unsigned char* src = A.packed;
                 for (int gi = 0; gi < P.n_gemms; ++gi) {
-                    const uint32_t tile_bytes = (uint32_t)P.g[gi].chunk_n * 128u, bytes = tile_bytes / CG;
-                    const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
-                    for (int i = 0; i < n; ++i) {
+                    const int per_chunk = P.g[gi].k_slabs + (P.g[gi].aux ? 1 : 0);       // the aux tile (one K-step wide) closes every chunk
+                    const int n = P.g[gi].n_chunks * per_chunk;
+                    for (int i = 0, sc = 0; i < n; ++i) {
+                        const uint32_t tile_bytes = (uint32_t)P.g[gi].chunk_n * (sc < P.g[gi].k_slabs ? 128u : 32u), bytes = tile_bytes / CG;
                         if (lane == 0) {
                             mbar_wait(&sm.empty[st], ph ^ 1, 1);
                             if (TC_DBG(A.dbg) & 16) mbar_arrive(&sm.full[st]);        // knob: no copy (tensor pipe alone)
@@ -389,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         }
                         __syncwarp();
                         src += tile_bytes;
+                        if (++sc == per_chunk) sc = 0;
                         if (++st == P.n_stages) { st = 0; ph ^= 1; }
                     }
                 }
@@ -407,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
             for (int wk = unit; wk < n_work; wk += n_units)
                 for (int t = 0; t < tiles_per_group; ++t)
                     for (int gi = 0; gi < P.n_gemms; ++gi) {
-                        const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
+                        const int n = P.g[gi].n_chunks * (P.g[gi].k_slabs + (P.g[gi].aux ? 1 : 0));
                         for (int i = 0; i < n; ++i) {
                             mbar_wait(&sm.full[st], ph, 5);
                             if (lane == 0) mbar_arrive_cluster_relaxed(leader_full + (uint32_t)st * 8u);
@@ -421,6 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
             // the GEMM's fields live in registers, descriptors are 64-bit adds on precomputed bases.
             const uint64_t a_desc0 = umma_desc_k_sw128(a_base), b_desc0 = umma_desc_k_sw128(b_base);
             const uint32_t stage_desc = (uint32_t)(stage_bytes >> 4);
+            const uint64_t aux_a_desc = umma_desc_k_sw32(smem_u32(sm.a_aux)), aux_b_desc0 = umma_desc_k_sw32(b_base);
             const bool deep = P.n_stages >= 4;
 #ifdef SNB_TC_PROBE
             int itile = 0;
@@ -432,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 #endif
                     for (int gi = 0; gi < P.n_gemms; ++gi) {
                         const int k_slabs = P.g[gi].k_slabs, n_chunks = P.g[gi].n_chunks, chunk_n = P.g[gi].chunk_n, K = P.g[gi].K;
-                        const int k_early = P.g[gi].k_early, free_slabs = P.g[gi].free_slabs;
+                        const int k_early = P.g[gi].k_early, free_slabs = P.g[gi].free_slabs, aux = P.g[gi].aux;
                         const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)chunk_n) : umma_idesc_f16((uint32_t)chunk_n);
 #ifdef SNB_TC_PROGRESS
                         if (g_hang_host && blockIdx.x < 16 && lane == 0) ((volatile unsigned int*)g_hang_host)[64 + blockIdx.x * 8 + 3] = (unsigned)(wk << 16 | t << 8 | gi);
@@ -493,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                     }
                                     // one barrier per N-chunk index: two commits of one GEMM on a single barrier could both land before the
                                     // epilogue looks at it (it may still be draining its stash copy), and the parity wait would miss a phase
-                                    if (s + (pair ? 2 : 1) == k_slabs) {
+                                    if (!aux && s + (pair ? 2 : 1) == k_slabs) {
                                         if (j == 0) { if (CG == 2) umma_commit_2cta(sm.acc_full, 3); else umma_commit(sm.acc_full); }
                                         else { if (CG == 2) umma_commit_2cta(sm.acc_full2, 3); else umma_commit(sm.acc_full2); }
                                     }
@@ -505,6 +503,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 #endif
                                 if (pair) { s += 2; st = st1 + 1; ph = ph1; if (st == P.n_stages) { st = 0; ph ^= 1; } }
                                 else { s += 1; st = st1; ph = ph1; }
+                            }
+                            if (aux) {
+                                // the chunk's last K-step: [1 1 | xyz..] x [bias hi lo | W_xyz..] adds the bias (and the skip layer's
+                                // xyz term) inside the accumulator, so the epilogue needs no per-column table
+                                mbar_wait(&sm.full[st], ph, 3);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint64_t dbx = aux_b_desc0 + (uint64_t)((uint32_t)st * stage_desc);
+                                    if (CG == 2) umma_f16_ss_2cta(d_tm, aux_a_desc, dbx, idesc, 1); else umma_f16_ss(d_tm, aux_a_desc, dbx, idesc, 1);
+                                    if (CG == 2) umma_commit_2cta(&sm.empty[st], 3); else umma_commit(&sm.empty[st]);
+                                    if (j == 0) { if (CG == 2) umma_commit_2cta(sm.acc_full, 3); else umma_commit(sm.acc_full); }
+                                    else { if (CG == 2) umma_commit_2cta(sm.acc_full2, 3); else umma_commit(sm.acc_full2); }
+                                }
+                                __syncwarp();
+                                if (++st == P.n_stages) { st = 0; ph ^= 1; }
                             }
                         }
                         ready_ph ^= 1;
@@ -659,7 +672,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, kEpiThreads);                  // the whole input tile of the first GEMM is in place
+                named_bar_sync(1, kEpiThreads);                  // the whole input tile of the first GEMM is in place; layer-0 table dead
+                if (half == 0) {                                 // aux operand row of this point: [1 1 | xyz hi | xyz lo | xyz hi | 0..] (fp16 hi/lo pairs)
+                    const __half xh = __float2half_rn(px), yh = __float2half_rn(py), zh = __float2half_rn(pz);
+                    const uint32_t one = 0x3c003c00u;
+                    const uint32_t w1 = pack_half2(__half2float(xh), __half2float(yh));
+                    const uint32_t w2 = pack_half2(__half2float(zh), px - __half2float(xh));
+                    const uint32_t w3 = pack_half2(py - __half2float(yh), pz - __half2float(zh));
+                    const uint32_t w4 = pack_half2(__half2float(xh), __half2float(yh));
+                    const uint32_t w5 = pack_half2(__half2float(zh), 0.f);
+                    const uint32_t base_aux = smem_u32(sm.a_aux) + (uint32_t)(row >> 3) * 256u + (uint32_t)(row & 7) * 32u;
+                    const uint32_t sw = ((uint32_t)(row >> 2) & 1u) << 4;
+                    sts128(base_aux + (0u ^ sw), one, w1, w2, w3);          // k 0..7 : 1 1 | x y z hi | x y z lo
+                    sts128(base_aux + (16u ^ sw), w4, w5, 0u, 0u);          // k 8..15: x y z hi | 0
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, kEpiThreads);                  // aux rows in place before the second ready signal
                 if (sb && tid_e == 0) { bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
                 {   const TcGemm& g0 = P.g[0];
                     if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
