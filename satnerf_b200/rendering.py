@@ -46,6 +46,7 @@ class _Pass(torch.autograd.Function):
         variant = field.variant
         R, S = z.shape
         dev = z.device
+        ctx.set_materialize_grads(False)       # outputs the loss does not touch arrive as None in backward (no zero-filled (R,S,.) tensors)
         pd = capi.PassDesc(R, S, rays.shape[1] if rays is not None else 0, int(cfg["sc"]), cfg["precision"], float(cfg["noise_std"]), 0)
         outs = {k: torch.empty(s, device=dev, dtype=torch.float32) for k, s in _out_shapes(variant, R, S).items()}
         stash = {"sigma": torch.empty(R, S, device=dev, dtype=torch.float32)}
@@ -166,6 +167,18 @@ def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
     return b0 + (u - c0) / den * (b1 - b0)
 
 
+_LINSPACE = {}
+
+
+def _linspace01(S: int, dev) -> torch.Tensor:
+    """torch.linspace(0, 1, S) of rendering.py:65 — deterministic, so one tensor per (S, device) serves every call."""
+    key = (S, str(dev))
+    t = _LINSPACE.get(key)
+    if t is None:
+        t = _LINSPACE[key] = torch.linspace(0, 1, S, device=dev)
+    return t
+
+
 def render_rays(models, args, rays, ts, _draws: Optional[List[torch.Tensor]] = None):
     """rendering.py:52-158.  Same arguments and result dict as the reference.
 
@@ -194,7 +207,7 @@ def render_rays(models, args, rays, ts, _draws: Optional[List[torch.Tensor]] = N
     if variant == "sat-nerf" and ts is None:
         raise TypeError("sat-nerf needs ts (the reference fails in torch.cat at models/satnerf.py:204)")
     t_emb = models["t"](ts) if variant == "sat-nerf" else None                    # rendering.py:100
-    steps = torch.linspace(0, 1, S, device=dev)                                   # :65
+    steps = _linspace01(S, dev)                                                   # :65
     z = capi.stratified_depths(rays, steps, draw("u", R, S).contiguous())         # :67-78
 
     def level(name, zz):

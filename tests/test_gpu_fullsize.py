@@ -82,6 +82,29 @@ def test_config3_coarse_fine_tc_vs_fp32():
         assert rel_err(a[k], b[k]) < 5e-3, (k, rel_err(a[k], b[k]))
 
 
+def test_config4_snerf_solar_correction_tc_vs_fp32():
+    """BASELINE.json configs[3]: s-nerf with the solar-correction pass (rendering.py:90-96), 4096 rays x 64 samples, h=512:
+    two field passes per call (points along the ray and along the sun direction); draws: rand_like, randn, randn(SC)."""
+    import satnerf_b200 as sb
+    args = make_args(model="s-nerf", sc_lambda=0.05)
+    torch.manual_seed(9)
+    ms = {"coarse": sb.load_model(args).cuda()}
+    rays, _ = orc.synthetic_sat_rays(4096, seed=10)
+    rays = rays.cuda()
+    g = torch.Generator().manual_seed(11)
+    draws = [torch.rand(4096, 64, generator=g), torch.randn(4096, 64, generator=g), torch.randn(4096, 64, generator=g)]
+    with torch.no_grad():
+        args.precision = "tc"
+        a = sb.render_rays(ms, args, rays, None, _draws=draws)
+        args.precision = "fp32"
+        b = sb.render_rays(ms, args, rays, None, _draws=draws)
+    assert {"weights_sc_coarse", "transparency_sc_coarse", "sun_sc_coarse"} <= set(a) and "beta_coarse" not in a
+    assert a["sun_sc_coarse"].shape == (4096, 64, 1)
+    for k in a:
+        assert rel_err(a[k], b[k]) < 1e-3, (k, rel_err(a[k], b[k]))
+    assert (a["weights_sc_coarse"].sum(-1) - 1).abs().max() < 1e-4
+
+
 def test_training_gradients_tc_vs_fp32_fullsize():
     import satnerf_b200 as sb
     args = make_args()

@@ -101,3 +101,34 @@ def test_bad_descriptors_are_rejected():
     d = capi.field_desc("sat-nerf", 8, 63, [4], 4)
     with pytest.raises(RuntimeError, match="fc_units"):
         capi.param_count(d)
+
+
+def test_device_ray_sampler_has_dataloader_semantics():
+    """satnerf_b200.data.DeviceRaySampler == DataLoader(dataset, shuffle=True, batch_size=B) of main.py:96-110: every ray once per
+    epoch, batches of B with a short last one, the keys and dtypes of SatelliteDataset.__getitem__ (datasets/satellite.py:347-350)."""
+    import torch
+    from satnerf_b200.data import DeviceRaySampler, combined_loader
+    N, B = 1000, 256
+    rays = torch.arange(N, dtype=torch.float32)[:, None].repeat(1, 11)
+    data = {"rays": rays, "rgbs": torch.rand(N, 3), "ts": torch.randint(0, 17, (N, 1)).float()}
+    sm = DeviceRaySampler(data, B, device="cpu", generator=torch.Generator().manual_seed(3))
+    assert len(sm) == 4
+    seen = []
+    for b in sm:
+        assert set(b) == {"rays", "rgbs", "ts"} and b["ts"].dtype == torch.int64 and b["rays"].shape[1] == 11
+        assert torch.equal(b["rgbs"], data["rgbs"][b["rays"][:, 0].long()])        # rows stay aligned across the tensors
+        seen.append(b["rays"][:, 0].long())
+    assert [len(s) for s in seen] == [256, 256, 256, 232]
+    assert torch.equal(torch.sort(torch.cat(seen)).values, torch.arange(N))         # a permutation: every ray exactly once
+    assert not torch.equal(torch.cat(seen), torch.arange(N))
+    second = torch.cat([b["rays"][:, 0].long() for b in sm])
+    assert not torch.equal(second, torch.cat(seen))                                # reshuffled every epoch
+    # rank shards of one global batch are disjoint and cover it
+    parts = [next(iter(DeviceRaySampler(data, B, device="cpu", generator=torch.Generator().manual_seed(5), rank=r, world=2))) for r in (0, 1)]
+    whole = next(iter(DeviceRaySampler(data, B, device="cpu", generator=torch.Generator().manual_seed(5))))
+    assert torch.equal(torch.cat([p["rays"] for p in parts]), whole["rays"])
+    # dict of loaders: one epoch = the longest loader, the shorter one restarts
+    depth = DeviceRaySampler({"rays": rays[:300], "depths": torch.rand(300, 2), "ts": data["ts"][:300]}, B, device="cpu")
+    batches = list(combined_loader({"color": sm, "depth": depth}))
+    assert len(batches) == 4 and all(set(b) == {"color", "depth"} for b in batches)
+    assert "depths" in batches[0]["depth"] and batches[2]["depth"]["rays"].shape[0] == 256
