@@ -61,7 +61,7 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
       TcGemm& g = add(GK_HEADA, nb + H2, H);
       g.src0 = P->has_beta ? L.beta0.w : L.rgb0.w; g.ld0 = P->has_beta ? L.beta0.n_in : L.rgb0.n_in; g.rows0 = P->has_beta ? nb : H2;
       g.src1 = L.rgb0.w; g.ld1 = L.rgb0.n_in;
-      tables(g, TF_F4, 0); }
+      tables(g, TF_F4, P->has_beta ? 1 : 0); }       // extra vector: beta_from_xyz.2 weights (one float per column of the beta half)
     { TcGemm& g = add(GK_SUN1, H2, H); g.src0 = L.sun[0].w; g.ld0 = L.sun[0].n_in; g.rows0 = H2; tables(g, TF_NONE, 0); }
     { TcGemm& g = add(GK_SUN2, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 0); }
     { TcGemm& g = add(GK_SUN3, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 1); }
@@ -204,7 +204,7 @@ __global__ void tc_pack_misc_kernel(TcProgram P, MiscOffsets M, const float* __r
             int nb = P.has_beta ? H2 : 0;
             for (int n = tid; n < g.N; n += nthr) {
                 float* t = T + g.tbl_off + n * 4;
-                if (n < nb) { t[0] = 0.f; t[1] = W[M.beta2_w + n]; t[2] = 0.f; t[3] = 0.f; }
+                if (n < nb) { t[0] = 0.f; t[1] = W[M.beta2_w + n]; t[2] = 0.f; t[3] = 0.f; T[g.vec_off + n] = W[M.beta2_w + n]; }
                 else { int m = n - nb; t[0] = W[M.rgb0_b + m]; t[1] = W[M.rgb2_w + m]; t[2] = W[M.rgb2_w + H2 + m]; t[3] = W[M.rgb2_w + 2 * H2 + m]; }
             }
         }
@@ -287,7 +287,11 @@ __device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool s
             sin_cols<NC>(dbg, v, es.y0, es.gt, H2, n0, row);
             if (es.act0) atom_store_cols<NC>(es.act0, es.gt, (H2 + 63) >> 6, row, n0, v);
 #pragma unroll
-            for (int i = 0; i < NC; ++i) beta_dot = fmaf(LDS_T(tF + (uint32_t)(n0 + i) * 16u).y, v[i], beta_dot);
+            for (int i = 0; i < NC; i += 4) {
+                float4 w = LDS_T(tV + (uint32_t)(n0 + i) * 4u);
+                beta_dot = fmaf(w.x, v[i], beta_dot); beta_dot = fmaf(w.y, v[i + 1], beta_dot);
+                beta_dot = fmaf(w.z, v[i + 2], beta_dot); beta_dot = fmaf(w.w, v[i + 3], beta_dot);
+            }
         } else {
             const int m0 = has_beta ? n0 - H2 : n0;
 #pragma unroll
@@ -830,6 +834,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     sm.al2[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb2 + sm.consts[3]), 1.002f), 0.001f);
                     sm.sn[p] = sigmoid_f(sun_dot + sm.consts[4]);                                      // :200
                     sm.bt[p] = P.has_beta ? softplus_f(beta_dot + sm.consts[5]) : 0.f;                 // :205
+                    // per-sample outputs that do not depend on the transmittance scan leave from here (128 threads) instead of
+                    // from the one warp per ray that composites
+                    const size_t gp = (size_t)r0 * S + p;
+                    if (A.sigma) A.sigma[gp] = sm.sg[p];
+                    if (A.sun) A.sun[gp] = sm.sn[p];
+                    if (A.beta && P.has_beta) A.beta[gp] = sm.bt[p];
+                    if (A.albedo) { A.albedo[gp * 3] = sm.al0[p]; A.albedo[gp * 3 + 1] = sm.al1[p]; A.albedo[gp * 3 + 2] = sm.al2[p]; }
+                    if (A.sky) { A.sky[gp * 3] = sm.skyc[rl * 4]; A.sky[gp * 3 + 1] = sm.skyc[rl * 4 + 1]; A.sky[gp * 3 + 2] = sm.skyc[rl * 4 + 2]; }
                 }
                 named_bar_sync(1, kEpiThreads);                  // scratch reads done before the next tile's layer 0 overwrites A
             }
@@ -861,16 +873,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         const size_t gp = (size_t)ray * S + i;
                         if (A.weights) A.weights[gp] = w;
                         if (A.transparency) A.transparency[gp] = Tr;
-                        if (A.sigma) A.sigma[gp] = sm.sg[p];
                         const float s = sm.sn[p];
                         depth = fmaf(w, zi, depth);
                         c0 += w * sm.al0[p] * (s + (1.f - s) * k0);
                         c1 += w * sm.al1[p] * (s + (1.f - s) * k1);
                         c2 += w * sm.al2[p] * (s + (1.f - s) * k2);
-                        if (A.sun) A.sun[gp] = s;
-                        if (A.beta && P.has_beta) A.beta[gp] = sm.bt[p];
-                        if (A.albedo) { A.albedo[gp * 3] = sm.al0[p]; A.albedo[gp * 3 + 1] = sm.al1[p]; A.albedo[gp * 3 + 2] = sm.al2[p]; }
-                        if (A.sky) { A.sky[gp * 3] = k0; A.sky[gp * 3 + 1] = k1; A.sky[gp * 3 + 2] = k2; }
                     }
                 }
 #pragma unroll
