@@ -198,22 +198,6 @@ __device__ __forceinline__ void atom_store32(unsigned char* arr, int gt, int fgs
     }
 }
 
-// park 32 activations as fp16 in 16 TMEM columns of this thread's lane (columns n0..n0+15 of its quadrant), and the
-// reverse: fetch them and store them into the swizzled A tile (columns k0..k0+31 of `row`)
-__device__ __forceinline__ void park_act32(uint32_t taddr, const float* v) {
-    uint32_t r[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = pack_half2(v[2 * i], v[2 * i + 1]);
-    tmem_st16(taddr, r);
-}
-__device__ __forceinline__ void unpark_act32(uint32_t taddr, uint32_t a_base, int row, int k0) {
-    uint32_t r[16];
-    tmem_ld16(taddr, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sts128(a_chunk_addr(a_base, row, k0 + c * 8), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-}
-
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 

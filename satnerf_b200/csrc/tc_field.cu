@@ -1,20 +1,30 @@
 // Fused tensor-core render pass for sm_100a (SNB_FP16_TC): one persistent, warp-specialised kernel
 // evaluates the whole field (SatNeRF / ShadowNeRF forward, models/satnerf.py:156-208) on 128-point
 // tiles and alpha-composites the rays of the tile group (satnerf.py:43-78) without activations ever
-// leaving the SM:
+// leaving the SM.  CTAs run as pairs (cta_group::2; template CG = 1: single CTAs): each CTA owns one
+// tile, the pair's leader issues M = 256 MMAs, each CTA streams and buffers half of every weight tile.
 //
-//   warp 0      weight producer: streams pre-swizzled fp16 weight tiles (L2-resident, ~5 MB) into a
-//               shared-memory ring with 1-D bulk async copies (TMA engine) + mbarrier transactions
-//   warp 1      MMA issuer: tcgen05.mma (M=128 points, N<=256 features, K=16) with the activation tile
-//               as the K-major A operand in shared memory, accumulators in TMEM (all 512 columns)
+//   warp 0      weight producer: streams this CTA's half of the pre-swizzled fp16 weight tiles
+//               (L2-resident, ~5 MB) into a 4-deep shared-memory ring with 1-D bulk async copies
+//               (TMA engine) + mbarrier transactions
+//   warp 1      leader: MMA issuer -- tcgen05.mma (M = 2 x 128 points, N <= 256 features, K = 16), the
+//               activation tile as the K-major A operand in shared memory, accumulators in TMEM (all 512
+//               columns), two weight stages (8 MMAs) per elected region;  peer: relay that reports
+//               "my half of the stage has landed" to the leader's stage barrier
 //   warps 2-17  epilogue: sample positions and the K=3 first layer in fp32 on CUDA cores, then per
-//               layer TMEM -> registers, bias (+ fp32 skip / per-ray terms), sin, fp16 pack into the
-//               swizzled A tile of the next layer; the tiny output heads (sigma, rgb, sun, beta) are
-//               dot products folded into the epilogue of the layer that feeds them; finally a
-//               warp-scan transmittance product composites each ray and writes the result dict.
+//               layer TMEM -> registers (16-column halves, next load in flight), sin, fp16 pack into the
+//               swizzled A tile of the next layer; biases and the skip layer's xyz term arrive inside
+//               the accumulator through one extra K = 16 step on 32B-swizzled aux operand tiles; the
+//               tiny output heads (sigma, rgb, sun, beta) are dot products folded into the epilogue of
+//               the layer that feeds them; finally a warp-scan transmittance product composites each ray.
 //
-// Arithmetic: fp16 operands / fp32 accumulation for the h x h contractions; first layer, skip term,
-// per-ray sun / embedding terms, heads and compositing in fp32 (SURVEY.md §7 "Precision").
+// Layer pipeline: N in two 256-column chunks with one accumulator barrier each; chunk 0's
+// epilogue runs under chunk 1's MMAs and stores into the K-slabs chunk 1 has released (slab_free); the
+// next layer's MMAs on those slabs are queued as soon as chunk 0 is stored (first ready signal), the
+// rest after chunk 1's epilogue (second ready signal).
+//
+// Arithmetic: fp16 operands / fp32 accumulation for the h x h contractions; first layer, per-ray sun /
+// embedding terms, heads and compositing in fp32; bias / skip terms as fp16 hi+lo pairs (exact to 2^-22).
 #include "tc_field.cuh"
 #include "tc_common.cuh"
 
@@ -351,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         // leader of a pair: a stage is full when its own copy has landed AND the peer has reported its half (relay arrival)
-        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], (CG == 2 && cta_rank == 0) ? 2 : 1); mbar_init(&sm.empty[i], 1); mbar_init(&sm.peer_full[i], 1); }
+        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], (CG == 2 && cta_rank == 0) ? 2 : 1); mbar_init(&sm.empty[i], 1); }
         mbar_init(sm.acc_full, 1); mbar_init(sm.acc_full2, 1); mbar_init(sm.a_ready, CG); mbar_init(sm.a_ready2, CG);
         for (int i = 0; i < 4; ++i) mbar_init(&sm.slab_free[i], 1);     // one elected arrival per CTA of the pair
         fence_barrier_init();
