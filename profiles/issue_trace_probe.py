@@ -30,5 +30,3 @@ for g in (0, 1, 2, 3):
     print(f"gemm {g}: epilogue starts waiting {int(t[g,0]-t0):6d}  chunk0 ready {int(t[g,1]-t0):6d}  chunk1 ready {int(t[g,3]-t0):6d}  epilogue done {int(t[g,2]-t0):6d}")
 print("gemm 1 final chunk, thread 0: acc barrier passed", int(t[53,0]-t0), " named barrier 2 passed", int(t[53,1]-t0), " block loop done", int(t[52,0]-t0),
       " tcgen05 fence", int(t[52,1]-t0), " proxy fence", int(t[52,2]-t0), " named barrier 1 passed", int(t[1,2]-t0))
-for it in (0, 1):
-    print(f"  block {it}: start {int(t[54+it,0]-t0)}  after tcgen05.ld {int(t[54+it,1]-t0)}  after epilogue math/stores {int(t[54+it,2]-t0)}")
