@@ -123,6 +123,14 @@ def cpu_reference_rays_per_s(n_rays, reps, warm, threads=None):
     return n_rays / statistics.median(times), torch.get_num_threads(), times
 
 
+def workload_config(world, precision="tc"):
+    """The `config` object of the JSON line: identical for both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": "configs[1]: sat-nerf synthetic RPC rays, 4096 rays x 64 samples per GPU, h=512, 8 layers, "
+                        "render_rays forward (no_grad)", "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES,
+            "fc_units": WIDTH, "precision": precision, "parallelism": f"ray-sharded x{world}, no collective in forward",
+            "l2": "256 MiB buffer written between steps (outside the timed events)"}
+
+
 def run_reference(opt, rank, world):
     if rank != 0:
         return
@@ -134,7 +142,7 @@ def run_reference(opt, rank, world):
     line = {"impl": "reference", "metric": "rays/sec (64 samples/ray)", "value": rps, "unit": "rays/s", "n_gpus": opt.gpus,
             "steps": steps, "warmup": opt.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: sat-nerf synthetic RPC rays, 64 samples/ray, h=512 (CPU arm: 1024-ray sample)"},
+            "config": workload_config(opt.gpus, opt.precision),
             "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -276,10 +284,7 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (first layer, heads, compositing f32)" if opt.precision == "tc" else "f32",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: sat-nerf synthetic RPC rays, 4096 rays x 64 samples per GPU, h=512, 8 layers, "
-                                   "render_rays forward (no_grad)", "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES,
-                       "fc_units": WIDTH, "precision": opt.precision, "parallelism": f"ray-sharded x{world}, no collective in forward",
-                       "l2": "256 MiB buffer written between steps (outside the timed events)"},
+            "config": workload_config(world, opt.precision),
             "e2e": {"value": rays_total / (e2e_ms * 1e-3), "unit": "rays/s",
                     "h2d_bytes_per_step": RAYS_PER_GPU * (11 * 4 + 8), "d2h_bytes_per_step": RAYS_PER_GPU * 16},
             "gpu_launches": launches,
