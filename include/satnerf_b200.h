@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 2
+#define SNB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SNB_API __attribute__((visibility("default")))
@@ -67,7 +67,15 @@ typedef struct snb_pass_desc {
                                 library wrote there on an earlier call with the SAME parameter values (the caller
                                 guarantees both): the per-call repacking (two small kernels) is skipped.  Evaluation
                                 loops (batched_inference, eval_satnerf.py:46-66) render many batches per weight set. */
+    int32_t flags;           /* SNB_PASS_* bits below                                                              */
+    float   t_min;           /* > 0: compositing stops along a ray once the transmittance has dropped below t_min (the
+                                remaining weights are written as 0; their sum is < t_min).  0 = exact reference behaviour */
 } snb_pass_desc;
+
+/* snb_pass_desc.flags */
+enum { SNB_PASS_SINGLE_CTA = 1,   /* tensor-core path: one CTA per 128-point tile instead of CTA pairs (A/B testing; bit-identical) */
+       SNB_PASS_NO_BETA    = 2 }; /* sat-nerf, inference: the caller does not consume the uncertainty head (create_satnerf_dsm.py:78
+                                     uses depth only): beta_from_xyz is not evaluated; io->beta must be NULL and aux_sums[4] is 0  */
 
 typedef struct snb_render_io {
     /* inputs */
@@ -93,7 +101,27 @@ typedef struct snb_render_io {
     float* nerf_rgb;            /* (R,S,3) per-sample colour of the nerf variant (stash)        */
     void*  stash;               /* training only: activation stash of snb_render_stash_bytes() bytes written by the
                                    tensor-core forward and consumed by its backward; NULL = inference / fp32 path  */
+    float* aux_sums;            /* (R,8) per-ray weighted sums the evaluation scripts form from the per-sample outputs
+                                   (eval_satnerf.py:125-146): [sum w*sun, sum w*albedo (3), sum w*beta, sum w*sky (3)];
+                                   with it an evaluation pass needs none of the (R,S,.) outputs                    */
 } snb_render_io;
+
+/* Losses of metrics.py evaluated per ray INSIDE the backward seed: with snb_render_grads.loss set, the
+ * upstream gradients g_* are not read; dL/d(rgb, depth, weights, beta, sun) come from the saved forward results and the targets. */
+enum { SNB_LOSS_COLOR_MSE = 1,   /* NerfLoss / SNerfLoss colour term: mean((rgb - target)^2)              (metrics.py:8-19, :36-55) */
+       SNB_LOSS_COLOR_BETA = 2,  /* SatNerfLoss: uncertainty_aware_loss, beta = sum w*beta + beta_min       (metrics.py:21-25)      */
+       SNB_LOSS_DEPTH = 3,       /* DepthLoss: lambda/3 * mean(weight * (depth - target)^2)                 (metrics.py:75-92)      */
+       SNB_LOSS_SOLAR = 4 };     /* solar_correction on a march_along_sun pass: lambda/3 * (mean sum (T - s)^2 + mean (1 - sum w s)),
+                                    T and w detached                                                          (metrics.py:27-34)      */
+typedef struct snb_loss_desc {
+    int32_t kind;               /* SNB_LOSS_*                                                                  */
+    int32_t n_rays_mean;        /* denominator of the reference's mean(): rays of the GLOBAL batch (all ranks)  */
+    float   lambda;             /* lambda_sc (SOLAR) / lambda_ds (DEPTH); unused otherwise                      */
+    float   beta_min;           /* COLOR_BETA: 0.05 (metrics.py:21)                                             */
+    const float* target;        /* (R,3) colours | (R) depths; unused for SOLAR                                */
+    const float* target_weight; /* DEPTH: (R) per-ray weights or NULL (= 1)                                    */
+    const float* g_terms;       /* (4) device: upstream gradient of each loss term below (autograd), NULL = 1   */
+} snb_loss_desc;
 
 typedef struct snb_render_grads {
     /* upstream gradients w.r.t. the outputs above; NULL = zero */
@@ -102,25 +130,13 @@ typedef struct snb_render_grads {
     /* results */
     float* g_params;            /* flat, same layout as params; ACCUMULATED into (+=)           */
     float* g_t_emb;             /* (R, t_dims), overwritten; NULL if not wanted                 */
+    const snb_loss_desc* loss;  /* non-NULL: fused loss seed (the g_* inputs above are ignored) */
 } snb_render_grads;
 
 SNB_API int         snb_abi_version(void);
 SNB_API const char* snb_last_error(void);
 /* number of CUDA kernels this library has launched since the last reset (bench accounting) */
 SNB_API int64_t     snb_launch_count(int reset);
-/* developer aid: copies the fused kernel's phase timestamps (int64 clock64 values) to a HOST buffer */
-SNB_API int         snb_debug_read(void* host_dst, size_t bytes);
-/* with SNB_TC_HANG_MIRROR set: 16 x [code, block, thread, parity] of the bounded barrier waits that trapped, by wait code (0xffffffff: none) */
-SNB_API int         snb_debug_hang_info(unsigned int* out64);
-/* developer / test entry: out (Fa x Fb) = Xa^T Xb through the point-atom packing and the tensor-core
- * weight-gradient kernel (csrc/tc_backward.cu); Xa (P x Fa), Xb (P x Fb) fp32 row-major, Fa % 128 == 0, Fb % 64 == 0 */
-SNB_API int         snb_debug_dw_gemm(const float* xa, const float* xb, int P, int Fa, int Fb, int k_splits, float* out,
-                                      void* workspace, size_t workspace_bytes, void* stream);
-/* developer microbenchmark: cycles for `iters` back-to-back tcgen05.mma (M=128 or 256, K=16) on n_blocks CTAs;
- * mode 0 SS cg1, 1 TS cg1 (A in TMEM), 2 SS cg2, 3 SS cg1 MN-major; host_out[0] = cycles, host_out[1] = iters */
-SNB_API int         snb_debug_mma_rate(int mode, int N, int iters, int n_blocks, long long* host_out);
-SNB_API int         snb_debug_mma_ring2(int N, int depth, int groups, int flags, int n_blocks, long long* host_out);
-SNB_API int         snb_debug_mma_ring(int N, int kstage, int depth, int groups, int flags, int n_blocks, long long* host_out);
 /* 1 when the device of the current context can run the tcgen05 path (compute capability 10.x). */
 SNB_API int         snb_device_supports_tc(void);
 
@@ -164,6 +180,18 @@ SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pass_desc* p, 
  * (weights, transparency, albedo, sun, sky, beta, sigma; nerf: nerf_rgb).                      */
 SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pass_desc* p, const snb_render_io* io,
                         const snb_render_grads* g, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Loss terms of one pass from its forward results (what metrics.py computes from the result dict): terms (4) device floats
+ *   COLOR_MSE: [colour, 0, 0, 0]   COLOR_BETA: [colour, logbeta, 0, 0]   DEPTH: [ds, 0, 0, 0]   SOLAR: [0, 0, sc_term2, sc_term3]
+ * io carries rgb / depth / weights / beta (SOLAR: transparency, weights, sun of the march_along_sun pass).  Deterministic
+ * (fixed-order reduction).  workspace: n_rays * 16 bytes.                                                               */
+SNB_API int snb_loss_forward(const snb_pass_desc* p, const snb_render_io* io, const snb_loss_desc* loss, float* terms,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient of those terms w.r.t. the result-dict tensors they read (autograd of the loss classes): any output may be NULL.
+ * g_rgb (R,3), g_depth (R), g_weights (R,S), g_beta (R,S), g_sun (R,S); loss->g_terms = upstream gradient of the 4 terms. */
+SNB_API int snb_loss_backward(const snb_pass_desc* p, const snb_render_io* io, const snb_loss_desc* loss,
+                      float* g_rgb, float* g_depth, float* g_weights, float* g_beta, float* g_sun, void* stream);
 
 /* <Field>.forward on B independent points (satnerf.py:156-208): xyz (B,3); aux_dir (B,3) = sun
  * direction (sat-nerf / s-nerf) or view direction (nerf); t_emb (B,t_dims); out (B,C) with

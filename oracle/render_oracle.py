@@ -10,8 +10,8 @@ Parity status: PINNED.  The reference has no golden vectors of its own (SURVEY.m
 is pinned against outputs of the reference itself: `tests/golden/make_golden.py` imports
 `/root/reference/rendering.py` + `models/` in the build container, captures every random draw, and
 commits inputs/outputs under `tests/golden/*.npz`; `tests/test_oracle_golden.py` replays them here.
-`tests/test_oracle_vs_reference.py` additionally compares live (values and gradients) whenever
-`/root/reference` is present.
+`tests/test_oracle_vs_reference.py` additionally compares live (bit-identical values, gradients to 1e-6) whenever
+`/root/reference` is present (the build container).
 
 Every function cites the reference lines it restates.  Parameters are passed as a plain
 `dict[str, Tensor]` keyed like the reference modules' `state_dict()` (e.g. ``fc_net.2.weight``).
@@ -44,9 +44,10 @@ class Draws:
     are replayed.
     """
 
-    def __init__(self, tape: Optional[List[torch.Tensor]] = None, dtype=torch.float32):
+    def __init__(self, tape: Optional[List[torch.Tensor]] = None, dtype=torch.float32, device="cpu"):
         self.tape = None if tape is None else list(tape)
         self.dtype = dtype
+        self.device = device
         self.log: List[torch.Tensor] = []
 
     def _next(self, kind, shape):
@@ -54,7 +55,7 @@ class Draws:
             t = self.tape.pop(0)
             assert tuple(t.shape) == tuple(shape), (kind, t.shape, shape)
         else:
-            t = torch.rand(*shape) if kind == "u" else torch.randn(*shape)
+            t = torch.rand(*shape, device=self.device) if kind == "u" else torch.randn(*shape, device=self.device)
         self.log.append(t)
         return t.to(self.dtype)
 
@@ -70,7 +71,7 @@ class Draws:
 # ----------------------------------------------------------------------------------------------
 def stratified_depths(near, far, n_samples, u):
     """rendering.py:65-78.  near/far (R,1); u (R,S) uniform in [0,1).  perturb is hard-wired to 1."""
-    steps = torch.linspace(0, 1, n_samples).to(near.dtype)          # :65
+    steps = torch.linspace(0, 1, n_samples, device=near.device).to(near.dtype)          # :65 (device: the bench's gpu_eager leg runs this file on CUDA)
     z = near * (1 - steps) + far * steps                            # :67
     mid = 0.5 * (z[:, :-1] + z[:, 1:])                              # :72
     hi = torch.cat([mid, z[:, -1:]], -1)                            # :74
@@ -219,7 +220,7 @@ def render_rays(params: Dict[str, Params], cfg, rays, ts, draws: Optional[Draws]
     Reproduces the reference including the RNG consumption order; the two code paths the reference
     cannot execute (s-nerf + fine: NameError at :134; fine + SC: result overwritten at :138/:149,
     SURVEY.md App. B) raise NotImplementedError instead of imitating the crash."""
-    draws = draws or Draws(dtype=rays.dtype)
+    draws = draws or Draws(dtype=rays.dtype, device=rays.device)
     variant, s, n_imp = cfg.model, cfg.n_samples, cfg.n_importance
     n_layers = getattr(cfg, "fc_layers", 8)
     o, d, near, far = rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], rays[:, 7:8]               # :62
@@ -293,37 +294,7 @@ def loss_depth(res, target, weights=1.0, lam_ds=1.0):
 
 
 # ----------------------------------------------------------------------------------------------
-# synthetic inputs shared by tests and bench — numpy-free, seeded
+# synthetic inputs: the seeded generators live with the product's bench inputs (satnerf_b200/synth.py) so that the product
+# bench never imports the checker; re-exported here for the tests.
 # ----------------------------------------------------------------------------------------------
-def synthetic_sat_rays(n_rays, n_images=17, seed=0, dtype=torch.float32):
-    """Rays shaped like datasets/satellite.py:18-65 + :218-227 output: (R,11) = o,d,near,far,sun; ts (R,)."""
-    g = torch.Generator().manual_seed(seed)
-    ts = torch.randint(0, n_images, (n_rays,), generator=g)
-    inc = torch.deg2rad(5 + 30 * torch.rand(n_images, generator=g))
-    azv = 2 * math.pi * torch.rand(n_images, generator=g)
-    view = torch.stack([torch.sin(inc) * torch.cos(azv), torch.sin(inc) * torch.sin(azv), -torch.cos(inc)], -1)
-    d = view[ts] + 1e-3 * torch.randn(n_rays, 3, generator=g)
-    d = d / d.norm(dim=-1, keepdim=True)
-    o = torch.cat([2 * torch.rand(n_rays, 2, generator=g) - 1, torch.ones(n_rays, 1)], -1)
-    near = torch.zeros(n_rays, 1)
-    far = 0.3 + 0.3 * torch.rand(n_rays, 1, generator=g)
-    el = torch.deg2rad(30 + 40 * torch.rand(n_images, generator=g))
-    az = torch.deg2rad(90 + 110 * torch.rand(n_images, generator=g))
-    sun = torch.stack([torch.sin(az) * torch.cos(el), torch.cos(az) * torch.cos(el), torch.sin(el)], -1)[ts]
-    return torch.cat([o, d, near, far, sun], -1).to(dtype), ts
-
-
-def synthetic_blender_rays(n_rays, seed=0, dtype=torch.float32):
-    """Rays shaped like datasets/blender.py:115-149: pinhole camera on a radius-4 sphere; (R,8), near 2, far 6."""
-    g = torch.Generator().manual_seed(seed)
-    th = 2 * math.pi * torch.rand(1, generator=g)
-    ph = torch.deg2rad(20 + 40 * torch.rand(1, generator=g))
-    cam = 4 * torch.tensor([torch.cos(th) * torch.cos(ph), torch.sin(th) * torch.cos(ph), torch.sin(ph)])
-    fwd = -cam / cam.norm()
-    right = torch.linalg.cross(fwd, torch.tensor([0.0, 0.0, 1.0])); right = right / right.norm()
-    up = torch.linalg.cross(right, fwd)
-    px = (400 * torch.rand(n_rays, 2, generator=g) - 200) / 555.5
-    d = fwd[None] + px[:, :1] * right[None] + px[:, 1:] * up[None]
-    d = d / d.norm(dim=-1, keepdim=True)
-    o = cam[None].expand(n_rays, 3)
-    return torch.cat([o, d, torch.full((n_rays, 1), 2.0), torch.full((n_rays, 1), 6.0)], -1).to(dtype)
+from satnerf_b200.synth import synthetic_blender_rays, synthetic_sat_rays  # noqa: E402,F401

@@ -17,7 +17,8 @@ with torch.no_grad():
     for _ in range(3):
         sb.render_rays(ms, a, rays, ts)
 torch.cuda.synchronize()
-t = capi.debug_timestamps()
+from satnerf_b200 import capi_dev
+t = capi_dev.debug_timestamps()
 t0 = t[20, 0]
 prev_end = t0
 for n in range(40):

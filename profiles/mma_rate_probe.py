@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from satnerf_b200 import capi
 torch.zeros(1, device="cuda")
-lib = capi.lib()
+from satnerf_b200 import capi_dev
+lib = capi_dev.lib()          # microbenchmarks live in libsatnerf_b200_dev.so
 out = (C.c_longlong * 2)()
 names = {0: "SS cg1 K-major", 1: "TS cg1 (A in TMEM)", 2: "SS cg2 M=256", 3: "SS cg1 MN-major"}
 for blocks, mode, N, it in [(b, m, n, i) for b in (1, 148) for m in (0, 1, 2, 3) for n in (64, 128, 256) for i in (0, 16)]:

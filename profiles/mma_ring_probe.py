@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from satnerf_b200 import capi
 torch.zeros(1, device="cuda")
-lib = capi.lib()
+from satnerf_b200 import capi_dev
+lib = capi_dev.lib()          # microbenchmarks live in libsatnerf_b200_dev.so
 out = (C.c_longlong * 2)()
 def run(N, kstage, depth, flags, blocks=148, total_mma=4096):
     groups = total_mma * 16 // kstage

@@ -17,7 +17,8 @@ with torch.enable_grad() if train else torch.no_grad():
     for _ in range(3):
         sb.render_rays(ms, a, rays, ts)
 torch.cuda.synchronize()
-t = capi.debug_timestamps()
+from satnerf_b200 import capi_dev
+t = capi_dev.debug_timestamps()
 print("layer0:", t[60, 1] - t[60, 0])
 tot_wait = tot_epi = 0
 for g in range(12):

@@ -28,13 +28,23 @@ class FieldDesc(C.Structure):
 
 class PassDesc(C.Structure):
     _fields_ = [("n_rays", C.c_int32), ("n_samples", C.c_int32), ("ray_cols", C.c_int32),
-                ("march_along_sun", C.c_int32), ("precision", C.c_int32), ("noise_std", C.c_float), ("weights_packed", C.c_int32)]
+                ("march_along_sun", C.c_int32), ("precision", C.c_int32), ("noise_std", C.c_float), ("weights_packed", C.c_int32),
+                ("flags", C.c_int32), ("t_min", C.c_float)]
+
+
+PASS_SINGLE_CTA, PASS_NO_BETA = 1, 2
+LOSS_COLOR_MSE, LOSS_COLOR_BETA, LOSS_DEPTH, LOSS_SOLAR = 1, 2, 3, 4
+
+
+class LossDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_rays_mean", C.c_int32), ("lambda_", C.c_float), ("beta_min", C.c_float),
+                ("target", C.c_void_p), ("target_weight", C.c_void_p), ("g_terms", C.c_void_p)]
 
 
 _IO_FIELDS = ["params", "rays", "z_vals", "t_emb", "noise", "xyz", "aux_dir", "rgb", "depth", "weights", "transparency",
-              "albedo", "sun", "sky", "beta", "sigma", "nerf_rgb", "stash"]
+              "albedo", "sun", "sky", "beta", "sigma", "nerf_rgb", "stash", "aux_sums"]
 _GRAD_FIELDS = ["g_rgb", "g_depth", "g_weights", "g_transparency", "g_albedo", "g_sun", "g_sky", "g_beta",
-                "g_params", "g_t_emb"]
+                "g_params", "g_t_emb"]       # + `loss` (pointer to LossDesc)
 
 
 class RenderIO(C.Structure):
@@ -42,7 +52,7 @@ class RenderIO(C.Structure):
 
 
 class RenderGrads(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in _GRAD_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in _GRAD_FIELDS] + [("loss", C.POINTER(LossDesc))]
 
 
 _SIGNATURES = {
@@ -50,12 +60,6 @@ _SIGNATURES = {
     "snb_last_error": (C.c_char_p, []),
     "snb_device_supports_tc": (C.c_int, []),
     "snb_launch_count": (C.c_int64, [C.c_int]),
-    "snb_debug_read": (C.c_int, [C.c_void_p, C.c_size_t]),
-    "snb_debug_hang_info": (C.c_int, [C.POINTER(C.c_uint)]),
-    "snb_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
-    "snb_debug_mma_ring2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
-    "snb_debug_mma_ring": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
-    "snb_debug_dw_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_param_layout": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
     "snb_param_count": (C.c_int64, [C.POINTER(FieldDesc)]),
@@ -68,6 +72,9 @@ _SIGNATURES = {
     "snb_render_forward": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.POINTER(RenderIO), C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_render_backward": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(RenderGrads),
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_loss_forward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_loss_backward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
     "snb_field_workspace": (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.POINTER(C.c_size_t)]),
     "snb_field_forward": (C.c_int, [C.POINTER(FieldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -88,7 +95,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.snb_abi_version() != 2:
+        if handle.snb_abi_version() != 3:
             raise RuntimeError("libsatnerf_b200.so ABI version mismatch")
         _lib = handle
     return _lib
@@ -149,28 +156,6 @@ def param_count(desc: FieldDesc) -> int:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().snb_launch_count(int(reset)))
-
-
-def debug_timestamps():
-    """(64,4) int64 phase timestamps of the fused kernel's block 0 (developer aid)."""
-    import numpy as np
-    buf = np.zeros((64, 4), dtype=np.int64)
-    _check(lib().snb_debug_read(buf.ctypes.data_as(C.c_void_p), buf.nbytes), "snb_debug_read")
-    return buf
-
-
-def debug_dw_gemm(xa, xb, k_splits=1):
-    """out = xa^T xb on the tensor-core weight-gradient kernel (developer / test entry)."""
-    P, Fa = xa.shape
-    Fb = xb.shape[1]
-    out = torch.empty(Fa, Fb, device=xa.device, dtype=torch.float32)
-    tiles = (P + 127) // 128
-    nbytes = tiles * (Fa // 64 + Fb // 64) * 16384 + (Fa // 128) * ((Fb // 64 + 3) // 4) * k_splits * (128 * 256 * 4 + 64) + (1 << 16)
-    ws = _workspace(xa.device, nbytes)
-    with torch.cuda.device(xa.device):
-        _check(lib().snb_debug_dw_gemm(_ptr(xa), _ptr(xb), P, Fa, Fb, k_splits, _ptr(out), C.c_void_p(ws.data_ptr()), ws.numel(),
-                                       _stream(xa.device)), "snb_debug_dw_gemm")
-    return out
 
 
 def device_supports_tc() -> bool:
@@ -254,10 +239,44 @@ def render_workspace_bytes(desc: FieldDesc, pd: PassDesc, backward: bool = False
     return int(n.value)
 
 
-def render_backward(desc: FieldDesc, pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]], grads: Dict[str, Optional[torch.Tensor]]):
+def loss_desc(kind: int, n_rays_mean: int, target=None, target_weight=None, g_terms=None, lam: float = 0.0, beta_min: float = 0.05) -> LossDesc:
+    """snb_loss_desc over device tensors (kept alive by the caller for the duration of the call)."""
+    return LossDesc(kind, int(n_rays_mean), float(lam), float(beta_min), _ptr(target), _ptr(target_weight), _ptr(g_terms))
+
+
+def loss_forward(pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]], loss: LossDesc) -> torch.Tensor:
+    """(4,) loss terms of one pass from its forward results (metrics.py:8-92 evaluated in the library)."""
+    ref = next(t for t in tensors.values() if t is not None)
+    dev = ref.device
+    io = _fill(RenderIO(), _IO_FIELDS, tensors)
+    terms = torch.empty(4, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, pd.n_rays * 16 + 256)
+        _check(lib().snb_loss_forward(C.byref(pd), C.byref(io), C.byref(loss), _ptr(terms), C.c_void_p(ws.data_ptr()), ws.numel(), _stream(dev)),
+               "snb_loss_forward")
+    return terms
+
+
+def loss_backward(pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]], loss: LossDesc, want: Dict[str, bool]):
+    """Gradients of the loss terms w.r.t. the result-dict tensors: {'rgb','depth','weights','beta','sun'} -> tensors (or None)."""
+    ref = next(t for t in tensors.values() if t is not None)
+    dev, R, S = ref.device, pd.n_rays, pd.n_samples
+    io = _fill(RenderIO(), _IO_FIELDS, tensors)
+    shapes = {"rgb": (R, 3), "depth": (R,), "weights": (R, S), "beta": (R, S), "sun": (R, S)}
+    out = {k: (torch.empty(shapes[k], device=dev, dtype=torch.float32) if want.get(k) else None) for k in shapes}
+    with torch.cuda.device(dev):
+        _check(lib().snb_loss_backward(C.byref(pd), C.byref(io), C.byref(loss), _ptr(out["rgb"]), _ptr(out["depth"]), _ptr(out["weights"]),
+                                       _ptr(out["beta"]), _ptr(out["sun"]), _stream(dev)), "snb_loss_backward")
+    return out
+
+
+def render_backward(desc: FieldDesc, pd: PassDesc, tensors: Dict[str, Optional[torch.Tensor]], grads: Dict[str, Optional[torch.Tensor]],
+                    loss: Optional[LossDesc] = None):
     dev = tensors["params"].device
     io = _fill(RenderIO(), _IO_FIELDS, tensors)
     g = _fill(RenderGrads(), _GRAD_FIELDS, grads)
+    if loss is not None:
+        g.loss = C.pointer(loss)
     n = C.c_size_t(0)
     with torch.cuda.device(dev):
         _check(lib().snb_render_workspace(C.byref(desc), C.byref(pd), 1, C.byref(n)), "snb_render_workspace")

@@ -104,6 +104,7 @@ extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pas
     a.R = p->n_rays; a.S = S; a.C = C; a.raw = pl.raw; a.z = io->z_vals; a.noise = io->noise; a.noise_std = p->noise_std;
     a.rgb = io->rgb; a.depth = io->depth; a.weights = io->weights; a.transparency = io->transparency;
     a.albedo = io->albedo; a.sun = io->sun; a.sky = io->sky; a.beta = io->beta; a.sigma = io->sigma; a.nerf_rgb = io->nerf_rgb;
+    a.aux_sums = io->aux_sums; a.t_min = p->t_min; a.no_beta = (p->flags & SNB_PASS_NO_BETA) ? 1 : 0;
     return launch_composite_fwd(a, st);
 }
 
@@ -133,6 +134,7 @@ extern "C" SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pa
     b.sky = io->sky; b.beta = io->beta; b.nerf_rgb = io->nerf_rgb;
     b.g_rgb = g->g_rgb; b.g_depth = g->g_depth; b.g_weights = g->g_weights; b.g_transparency = g->g_transparency;
     b.g_albedo = g->g_albedo; b.g_sun = g->g_sun; b.g_sky = g->g_sky; b.g_beta = g->g_beta; b.d_head = pl.d_head;
+    SNB_TRY(fill_loss(b, g->loss));
     SNB_TRY(launch_composite_bwd(b, st));
     const int dir_col = p->march_along_sun ? 8 : 3;
     for (int r0 = 0; r0 < p->n_rays; r0 += pl.rays_per_chunk) {
@@ -144,6 +146,42 @@ extern "C" SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pa
         SNB_TRY(field_backward_chunk(L, io->params, g->g_params, pl.chunk, in, pl.d_head + (size_t)r0 * S * C, gt, S, st));
     }
     return 0;
+}
+
+static int loss_args(const snb_pass_desc* p, const snb_render_io* io, const snb_loss_desc* loss, LossFwdArgs* a, const char* who) {
+    if (!p || !io || !loss) SNB_FAIL(-1, "%s: null argument", who);
+    if (p->n_rays < 0 || p->n_samples < 1) SNB_FAIL(-1, "bad pass shape R=%d S=%d", p->n_rays, p->n_samples);
+    if (loss->kind < SNB_LOSS_COLOR_MSE || loss->kind > SNB_LOSS_SOLAR) SNB_FAIL(-1, "unknown loss kind %d", loss->kind);
+    if (loss->n_rays_mean < 1) SNB_FAIL(-1, "snb_loss_desc.n_rays_mean must be >= 1");
+    a->R = p->n_rays; a->S = p->n_samples; a->kind = loss->kind; a->lambda = loss->lambda; a->beta_min = loss->beta_min; a->inv_n = 1.0f / (float)loss->n_rays_mean;
+    a->rgb = io->rgb; a->depth = io->depth; a->weights = io->weights; a->transparency = io->transparency; a->beta = io->beta; a->sun = io->sun;
+    a->target = loss->target; a->target_w = loss->target_weight;
+    if (p->n_rays == 0) return 0;
+    switch (loss->kind) {
+        case SNB_LOSS_COLOR_BETA: if (!io->weights || !io->beta) SNB_FAIL(-1, "%s: weights and beta are required", who); /* fallthrough */
+        case SNB_LOSS_COLOR_MSE: if (!io->rgb || !loss->target) SNB_FAIL(-1, "%s: rgb and target are required", who); break;
+        case SNB_LOSS_DEPTH: if (!io->depth || !loss->target) SNB_FAIL(-1, "%s: depth and target are required", who); break;
+        default: if (!io->sun || !io->weights || !io->transparency) SNB_FAIL(-1, "%s: sun, weights and transparency of the solar-correction pass are required", who);
+    }
+    return 0;
+}
+
+extern "C" SNB_API int snb_loss_backward(const snb_pass_desc* p, const snb_render_io* io, const snb_loss_desc* loss,
+                                         float* g_rgb, float* g_depth, float* g_weights, float* g_beta, float* g_sun, void* stream) {
+    LossBwdArgs b{};
+    SNB_TRY(loss_args(p, io, loss, &b.f, "snb_loss_backward"));
+    b.g_terms = loss->g_terms; b.g_rgb = g_rgb; b.g_depth = g_depth; b.g_weights = g_weights; b.g_beta = g_beta; b.g_sun = g_sun;
+    return launch_loss_backward(b, (cudaStream_t)stream);
+}
+
+extern "C" SNB_API int snb_loss_forward(const snb_pass_desc* p, const snb_render_io* io, const snb_loss_desc* loss, float* terms,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!terms) SNB_FAIL(-1, "snb_loss_forward: null output");
+    LossFwdArgs a{};
+    SNB_TRY(loss_args(p, io, loss, &a, "snb_loss_forward"));
+    if ((size_t)p->n_rays * 16 > workspace_bytes || (!workspace && p->n_rays)) SNB_FAIL(-4, "snb_loss_forward: workspace too small (%zu bytes given)", workspace_bytes);
+    a.per_ray = (float*)workspace; a.terms = terms;
+    return launch_loss_forward(a, (cudaStream_t)stream);
 }
 
 extern "C" SNB_API int snb_field_workspace(const snb_field_desc* f, int n_points, size_t* bytes) {
@@ -181,6 +219,9 @@ extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* p
     return 0;
 }
 
-// Developer aid: phase timestamps recorded by the fused kernel (see tc_field.cu); host buffer of int64.
+#ifdef SNB_DEV_BUILD
+#include "satnerf_b200_dev.h"
+// Developer aid (libsatnerf_b200_dev.so only): phase timestamps recorded by the fused kernel (see tc_field.cu); host buffer of int64.
 extern "C" SNB_API int snb_debug_read(void* host_dst, size_t bytes) { return tc_debug_read(host_dst, bytes); }
-extern "C" SNB_API int snb_debug_hang_info(unsigned int* out4) { return tc_debug_hang_info(out4); }
+extern "C" SNB_API int snb_debug_hang_info(unsigned int* out192) { return tc_debug_hang_info(out192); }
+#endif

@@ -3,6 +3,7 @@
 //                                               mode 2: SS cg2 (M=256, leader issues)   mode 3: SS cg1, MN-major operands
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "satnerf_b200_dev.h"
 
 namespace snb {
 using namespace ptx;

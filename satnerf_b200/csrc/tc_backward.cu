@@ -159,6 +159,8 @@ int launch_dw(const DwItem* d_items, int n_items, const void* base, float* parti
 
 }  // namespace snb
 
+#ifdef SNB_DEV_BUILD
+#include "satnerf_b200_dev.h"
 using namespace snb;
 
 // Developer / test entry: out (Fa x Fb, fp32 row-major) = Xa^T Xb for row-major fp32 Xa (P x Fa), Xb (P x Fb), through the
@@ -210,3 +212,4 @@ extern "C" SNB_API int snb_debug_dw_gemm(const float* xa, const float* xb, int P
     delete[] h; delete[] hp; delete[] ho;
     return 0;
 }
+#endif  // SNB_DEV_BUILD

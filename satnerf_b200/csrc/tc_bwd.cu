@@ -98,9 +98,11 @@ __global__ void absmax_kernel(const float* __restrict__ x, long long n, float* _
 // the fused input-gradient chain
 // ---------------------------------------------------------------------------------------------------------------
 struct YBuf { uint4 q[4]; };
-__device__ __forceinline__ YBuf yb_load(const unsigned char* arr, int gt, int F, int n0, int row) {
-    const uint4* s = reinterpret_cast<const uint4*>(arr + (((size_t)gt * (F >> 5) + (n0 >> 5)) * kTile + row) * 64);
-    YBuf b; b.q[0] = __ldg(s); b.q[1] = __ldg(s + 1); b.q[2] = __ldg(s + 2); b.q[3] = __ldg(s + 3);
+__device__ __forceinline__ YBuf yb_load(const unsigned char* arr, int gt, int F, int n0, int row) {      // 32 columns from n0 (n0 % 32 == 0)
+    const unsigned char* s = arr + (((size_t)gt * (F >> 3) + (n0 >> 3)) * kTile + row) * 16;                 // [gt][n/8][row][8 fp16]: coalesced over rows
+    YBuf b;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) b.q[c] = __ldg(reinterpret_cast<const uint4*>(s + (size_t)c * kTile * 16));
     return b;
 }
 // v[i] *= mul * cos(2 pi r_i)
@@ -445,6 +447,25 @@ __global__ void ray_sum_t_kernel(const float* __restrict__ per_point, float* __r
 // ---------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------
+// Small host -> device transfers without staging memory: the bytes ride in the kernel's parameter block.
+struct ParamBlob { uint4 q[1984]; };                      // 31 744 bytes (the limit is 32 764 per launch)
+__global__ void param_upload_kernel(const __grid_constant__ ParamBlob blob, uint4* __restrict__ dst, int n16) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = blob.q[i];
+}
+static int upload_by_param(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    static_assert(sizeof(ParamBlob) <= 32000, "parameter block too large");
+    for (size_t off = 0; off < bytes; off += sizeof(ParamBlob)) {
+        ParamBlob blob;
+        const size_t n = bytes - off < sizeof(ParamBlob) ? bytes - off : sizeof(ParamBlob);
+        memcpy(&blob, (const char*)src + off, n);
+        const int n16 = (int)((n + 15) / 16);            // (destination arrays are padded to 256 bytes by the arena)
+        param_upload_kernel<<<(n16 + 255) / 256, 256, 0, st>>>(blob, (uint4*)((char*)dst + off), n16);
+        SNB_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+bool tc_bwd_supported(const FieldLayout& L, const snb_pass_desc* p);
 static bool bwd_supported(const FieldLayout& L, const snb_pass_desc* p) {
     if (L.variant == SNB_NERF) return false;
     if (L.width % 128 != 0 || L.width > 512) return false;
@@ -453,6 +474,8 @@ static bool bwd_supported(const FieldLayout& L, const snb_pass_desc* p) {
     if (L.t_dims > 4) return false;
     return true;
 }
+
+bool tc_bwd_supported(const FieldLayout& L, const snb_pass_desc* p) { return bwd_supported(L, p); }
 
 static int group_for(int S) {
     int best = 1; double best_u = 0.0;
@@ -566,7 +589,7 @@ int tc_bwd_workspace(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes
 int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_render_io* io, const snb_render_grads* g,
                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (!bwd_supported(L, p) || !io->stash) return 1;
-    { const char* e = getenv("SNB_TC_BWD"); if (e && atoi(e) == 0) return 1; }
+    if (dev_knobs().bwd_off) return 1;
     static int sm_count = 0, max_smem = 0;
     if (!sm_count) {
         int dev = 0; SNB_CUDA(cudaGetDevice(&dev));
@@ -592,6 +615,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     b.sky = io->sky; b.beta = io->beta; b.nerf_rgb = io->nerf_rgb;
     b.g_rgb = g->g_rgb; b.g_depth = g->g_depth; b.g_weights = g->g_weights; b.g_transparency = g->g_transparency;
     b.g_albedo = g->g_albedo; b.g_sun = g->g_sun; b.g_sky = g->g_sky; b.g_beta = g->g_beta; b.d_head = d_head;
+    SNB_TRY(fill_loss(b, g->loss));
     float* ray_sums = (float*)(ws + B.off_raysums);
     SNB_TRY(launch_composite_bwd_warp(b, ray_sums, st));
     SNB_CUDA(cudaMemsetAsync(absmax, 0, 256, st));
@@ -685,25 +709,10 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     if (L.variant == SNB_SATNERF) tiny(L.beta2, fb + A.fs.b1, fg2, 5, 1);
     if ((int)items.size() > B.n_items || (int)outs.size() > B.n_outs) SNB_FAIL(-3, "internal: weight-gradient work list overflow (%zu/%d, %zu/%d)", items.size(), B.n_items, outs.size(), B.n_outs);
     DwItem* d_items = (DwItem*)(ws + B.off_items); DwOut* d_outs = (DwOut*)(ws + B.off_outs);
-    {
-        // Work lists go through a small ring of pinned staging buffers so the copies are truly asynchronous: no stream
-        // synchronisation in the middle of the step (a pageable copy would stall the CPU behind the chain kernel).
-        constexpr int kSlots = 8; constexpr size_t kSlotBytes = 256 * 1024;
-        static unsigned char* pinned = nullptr; static cudaEvent_t ev[kSlots]; static int slot = 0;
-        if (!pinned) {
-            SNB_CUDA(cudaHostAlloc((void**)&pinned, kSlots * kSlotBytes, cudaHostAllocDefault));
-            for (int i = 0; i < kSlots; ++i) SNB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        }
-        const size_t ib = sizeof(DwItem) * items.size(), ob = sizeof(DwOut) * outs.size();
-        if (ib + ob > kSlotBytes) SNB_FAIL(-3, "internal: weight-gradient work list too large (%zu bytes)", ib + ob);
-        slot = (slot + 1) % kSlots;
-        SNB_CUDA(cudaEventSynchronize(ev[slot]));          // slot was used 8 backward calls ago: already complete in practice
-        unsigned char* h = pinned + (size_t)slot * kSlotBytes;
-        memcpy(h, items.data(), ib); memcpy(h + ib, outs.data(), ob);
-        SNB_CUDA(cudaMemcpyAsync(d_items, h, ib, cudaMemcpyHostToDevice, st));
-        SNB_CUDA(cudaMemcpyAsync(d_outs, h + ib, ob, cudaMemcpyHostToDevice, st));
-        SNB_CUDA(cudaEventRecord(ev[slot], st));
-    }
+    // The work lists (~40 KB) travel to the device as KERNEL PARAMETERS (up to 32 KB per launch since CUDA 12.1): no pinned
+    // staging buffer, no event, no allocation -- the library keeps no state between calls.
+    SNB_TRY(upload_by_param(d_items, items.data(), sizeof(DwItem) * items.size(), st));
+    SNB_TRY(upload_by_param(d_outs, outs.data(), sizeof(DwOut) * outs.size(), st));
     float* partial = (float*)(ws + B.off_partial);
     SNB_TRY(launch_dw(d_items, (int)items.size(), nullptr, partial, st));
 

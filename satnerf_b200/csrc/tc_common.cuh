@@ -60,13 +60,23 @@ struct TcArgs {
     TcStash stash; unsigned char* stash_base;    // stash_base == nullptr: inference, nothing is stashed
     const float *params, *rays, *z, *t_emb, *noise, *xyz, *aux;
     float noise_std;
-    float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma;
+    float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma, *aux_sums;
+    float t_min;
     unsigned char* packed;
     int R, S, ray_cols, dir_col, G, n_groups;
     int dbg;      // developer knobs (env SNB_TC_DBG): 1 = skip sin, 2 = skip TMEM loads, 4 = skip activation stores,
                   // 8 = skip MMA issue, 16 = skip weight copies
 };
 
+
+// Developer knobs.  Product build: compile-time zeros (no getenv anywhere on the call path).  Dev build
+// (libsatnerf_b200_dev.so, -DSNB_DEV_BUILD): read ONCE from the environment on first use.
+struct DevKnobs { int no_early, cg, dbg, bwd_off, hang_mirror; };
+#ifdef SNB_DEV_BUILD
+const DevKnobs& dev_knobs();
+#else
+inline DevKnobs dev_knobs() { return DevKnobs{0, 0, 0, 0, 0}; }
+#endif
 
 struct Smem {
     unsigned char* a;        // activation tile: a_slabs x [128 rows x 128 B], 128B-swizzled, K-major
@@ -148,33 +158,21 @@ __device__ __forceinline__ float to_rev(float y) {
     float r = __fmul_rn(y, 0.15915494309189535f);
     return __fsub_rn(r, __fsub_rn(__fadd_rn(r, 12582912.0f), 12582912.0f));       // r - rint(r)
 }
-// 64-byte slot of (tile gt, 32-column block n0/32, row) in a yb array with F features
-__device__ __forceinline__ unsigned char* yb_slot(unsigned char* arr, int gt, int F, int n0, int row) {
-    return arr + (((size_t)gt * (F >> 5) + (n0 >> 5)) * kTile + row) * 64;
+// yb arrays: [tile gt][8-column block n/8][row 0..127][8 fp16] -- the 32 lanes of a warp (consecutive rows) write / read 512
+// contiguous bytes per 16-byte access (the round-1 layout [n/32][row][32] made every access a 64-byte-strided scatter and
+// the training forward 3x slower than inference).
+__device__ __forceinline__ unsigned char* yb_chunk(unsigned char* arr, int gt, int F, int n, int row) {      // n % 8 == 0
+    return arr + (((size_t)gt * (F >> 3) + (n >> 3)) * kTile + row) * 16;
 }
-__device__ __forceinline__ void yb_store32(unsigned char* slot, const float* y) {
-    uint4* d = reinterpret_cast<uint4*>(slot);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float* x = y + c * 8;
-        d[c] = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
-                          pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
-    }
+__device__ __forceinline__ uint4 yb_pack8(const float* x) {
+    return make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
+                      pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
 }
+// NC (multiple of 8) consecutive pre-activations of one row starting at column n0
 template <int NC>
-__device__ __forceinline__ void yb_store_cols(unsigned char* p, const float* y) {      // p: 16-byte aligned position inside a yb slot
-    uint4* d = reinterpret_cast<uint4*>(p);
+__device__ __forceinline__ void yb_store_cols(unsigned char* arr, int gt, int F, int n0, int row, const float* y) {
 #pragma unroll
-    for (int c = 0; c < NC / 8; ++c) {
-        const float* x = y + c * 8;
-        d[c] = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
-                          pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
-    }
-}
-// 8 consecutive pre-activations (16 bytes of a yb slot)
-__device__ __forceinline__ void yb_store8(unsigned char* p16, const float* x) {
-    *reinterpret_cast<uint4*>(p16) = make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
-                                                 pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
+    for (int c = 0; c < NC / 8; ++c) *reinterpret_cast<uint4*>(yb_chunk(arr, gt, F, n0 + c * 8, row)) = yb_pack8(y + c * 8);
 }
 // address of the 16-byte chunk (features k..k+7, k % 8 == 0) of point `row` of tile gt in an atoms array with `fgs` groups
 __device__ __forceinline__ unsigned char* atom_chunk(unsigned char* arr, int gt, int fgs, int row, int k) {

@@ -42,10 +42,10 @@ static bool tc_supported(const FieldLayout& L, const snb_pass_desc* p) {
     return true;
 }
 
-static int build_program(const FieldLayout& L, TcProgram* P) {
+static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = false) {
     memset(P, 0, sizeof(*P));
     const int H = L.width, H2 = H / 2;
-    P->H = H; P->H2 = H2; P->tau = L.t_dims; P->has_beta = L.variant == SNB_SATNERF;
+    P->H = H; P->H2 = H2; P->tau = L.t_dims; P->has_beta = L.variant == SNB_SATNERF && !no_beta;
     P->a_slabs = H / 64;
     int ng = 0; int tbl = 0;
     auto add = [&](int kind, int N, int K) -> TcGemm& {
@@ -102,7 +102,7 @@ static int build_program(const FieldLayout& L, TcProgram* P) {
 #endif
         if (P->g[i].k_early > P->g[i].k_slabs - 1) P->g[i].k_early = P->g[i].k_slabs - 1;
     }
-    { const char* e = getenv("SNB_TC_NO_EARLY"); if (e && atoi(e)) for (int i = 0; i < ng; ++i) P->g[i].k_early = 0; }
+    if (dev_knobs().no_early) for (int i = 0; i < ng; ++i) P->g[i].k_early = 0;
     P->consts = tbl; tbl += 8;
     P->sunw = tbl; tbl += 4 * H2;                 // [3][H2] weights + [H2] bias
     P->betaw = tbl; tbl += (L.t_dims + 1) * H2;   // [tau][H2] weights + [H2] bias
@@ -263,7 +263,7 @@ struct EpiStash { unsigned char *y0, *y1, *act0, *act1; int gt; };     // 0: fir
 #define SIN_(x) ((TC_DBG(dbg) & 1) ? (x) : __sinf(x))
 template <int NC>
 __device__ __forceinline__ void sin_cols(int dbg, float* v, unsigned char* yarr, int gt, int F, int n0, int row) {
-    if (yarr) yb_store_cols<NC>(yb_slot(yarr, gt, F, n0, row) + (n0 & 31) * 2, v);
+    if (yarr) yb_store_cols<NC>(yarr, gt, F, n0, row, v);
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] = SIN_(v[i]);
 }
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 float y = fmaf(w[i].z, rz[k], fmaf(w[i].y, ry[k], fmaf(w[i].x, rx[k], w[i].w)));
                                 v[i] = __fmul_rn(30.0f, y);
                             }
-                            if (sb) yb_store8(yb_slot(sb + A.stash.y[0], gt, H, n0, r) + (n0 & 31) * 2, v);
+                            if (sb) yb_store_cols<8>(sb + A.stash.y[0], gt, H, n0, r, v);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = __sinf(v[i]);
                             sts128(a_chunk_addr(a_base, r, n0), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
@@ -867,10 +867,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
             for (int gr = warp - 2; gr < n_rays; gr += kEpiWarps) {
                 const int ray = r0 + gr;
                 float carry = 1.f, depth = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+                float xs = 0.f, xa0 = 0.f, xa1 = 0.f, xa2 = 0.f, xb = 0.f, xw = 0.f;      // sum w*{sun, albedo, beta, 1} (aux_sums)
                 const float k0 = sm.skyc[gr * 4], k1 = sm.skyc[gr * 4 + 1], k2 = sm.skyc[gr * 4 + 2];
                 for (int b0 = 0; b0 < S; b0 += 32) {
                     const int i = b0 + lane, p = gr * S + i;
                     const bool ok = i < S;
+                    if (A.t_min > 0.f && carry < A.t_min) {          // early termination (snb_pass_desc.t_min): the tail's weights sum to < t_min
+                        if (ok) { const size_t gp = (size_t)ray * S + i; if (A.weights) A.weights[gp] = 0.f; if (A.transparency) A.transparency[gp] = 0.f; }
+                        continue;
+                    }
                     float alpha = 0.f, q = 1.f, zi = 0.f;
                     if (ok) {
                         zi = sm.z[p];
@@ -894,12 +899,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         c0 += w * sm.al0[p] * (s + (1.f - s) * k0);
                         c1 += w * sm.al1[p] * (s + (1.f - s) * k1);
                         c2 += w * sm.al2[p] * (s + (1.f - s) * k2);
+                        if (A.aux_sums) { xs = fmaf(w, s, xs); xa0 = fmaf(w, sm.al0[p], xa0); xa1 = fmaf(w, sm.al1[p], xa1); xa2 = fmaf(w, sm.al2[p], xa2);
+                                          xb = fmaf(w, sm.bt[p], xb); xw += w; }
                     }
                 }
 #pragma unroll
                 for (int off = 16; off; off >>= 1) {
                     depth += __shfl_xor_sync(~0u, depth, off); c0 += __shfl_xor_sync(~0u, c0, off);
                     c1 += __shfl_xor_sync(~0u, c1, off); c2 += __shfl_xor_sync(~0u, c2, off);
+                }
+                if (A.aux_sums) {                        // eval_satnerf.py:125-146: sum over samples of w * {sun, albedo, beta, sky}
+#pragma unroll
+                    for (int off = 16; off; off >>= 1) {
+                        xs += __shfl_xor_sync(~0u, xs, off); xa0 += __shfl_xor_sync(~0u, xa0, off); xa1 += __shfl_xor_sync(~0u, xa1, off);
+                        xa2 += __shfl_xor_sync(~0u, xa2, off); xb += __shfl_xor_sync(~0u, xb, off); xw += __shfl_xor_sync(~0u, xw, off);
+                    }
+                    if (lane == 0) {
+                        float4* o = reinterpret_cast<float4*>(A.aux_sums + (size_t)ray * 8);      // two 16-byte stores per ray
+                        o[0] = make_float4(xs, xa0, xa1, xa2); o[1] = make_float4(xb, xw * k0, xw * k1, xw * k2);
+                    }
                 }
                 if (lane == 0) {
                     if (A.depth) A.depth[ray] = depth;
@@ -933,10 +951,23 @@ int tc_workspace(const FieldLayout& L, const snb_pass_desc* p, bool backward, si
     *bytes = 0;
     if (!tc_supported(L, p)) return 0;
     if (backward) return tc_bwd_workspace(L, p, bytes);
-    TcProgram P; int nfl = build_program(L, &P);
+    TcProgram P; int nfl = build_program(L, &P);          // (the NO_BETA program is never larger)
     *bytes = (size_t)P.tables_base + (size_t)nfl * 4 + 1024;
     return 0;
 }
+
+#ifdef SNB_DEV_BUILD
+const DevKnobs& dev_knobs() {
+    static const DevKnobs k = [] {
+        auto num = [](const char* n) { const char* e = getenv(n); return e ? atoi(e) : 0; };
+        DevKnobs d; d.no_early = num("SNB_TC_NO_EARLY"); d.cg = num("SNB_TC_CG"); d.dbg = num("SNB_TC_DBG");
+        { const char* e = getenv("SNB_TC_BWD"); d.bwd_off = (e && atoi(e) == 0) ? 1 : 0; }
+        d.hang_mirror = getenv("SNB_TC_HANG_MIRROR") ? 1 : 0;
+        return d;
+    }();
+    return k;
+}
+#endif
 
 static unsigned int* g_hang_pinned = nullptr;
 static int hang_mirror_init() {
@@ -964,9 +995,12 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         SNB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         SNB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    if (getenv("SNB_TC_HANG_MIRROR")) { int rc = hang_mirror_init(); if (rc) return rc; }
+    if (dev_knobs().hang_mirror) { int rc = hang_mirror_init(); if (rc) return rc; }
+    const bool no_beta = (p->flags & SNB_PASS_NO_BETA) != 0 && L.variant == SNB_SATNERF;
+    if (no_beta && io->stash) SNB_FAIL(-1, "SNB_PASS_NO_BETA is an inference option (a training pass needs the beta head)");
+    if (no_beta && io->beta) SNB_FAIL(-1, "SNB_PASS_NO_BETA: io->beta must be NULL");
     TcArgs A; memset(&A, 0, sizeof(A));
-    int nfl = build_program(L, &A.prog);
+    int nfl = build_program(L, &A.prog, no_beta);
     TcProgram& P = A.prog;
     size_t need = (size_t)P.tables_base + (size_t)nfl * 4;
     if (need > workspace_bytes) SNB_FAIL(-4, "tensor-core path: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -975,7 +1009,8 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     // refill latency of its 2-stage ring (profiles/r1_phase_probe.md, mma_ring*_probe.py).  SNB_TC_CG=1 forces single CTAs.
     const int G_ = choose_group(p->n_samples);
     int cg = (p->n_rays + G_ - 1) / G_ >= 2 ? 2 : 1;
-    { const char* e = getenv("SNB_TC_CG"); if (e && atoi(e) == 2) cg = 2; if (e && atoi(e) == 1) cg = 1; }
+    if (p->flags & SNB_PASS_SINGLE_CTA) cg = 1;
+    if (dev_knobs().cg == 1 || dev_knobs().cg == 2) cg = dev_knobs().cg;
     size_t fixed = (size_t)P.a_slabs * kSlabBytes + smem_fixed_bytes() + 1024;
     int ns = (int)(((size_t)max_smem - fixed) / (P.stage_bytes / cg)); if (ns > 8) ns = 8;
     if (ns < 2) SNB_FAIL(-6, "tensor-core path: not enough shared memory for the weight ring");
@@ -985,13 +1020,13 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     A.params = io->params; A.rays = io->rays; A.z = io->z_vals; A.t_emb = io->t_emb; A.noise = p->noise_std != 0.f ? io->noise : nullptr;
     A.noise_std = p->noise_std; A.xyz = io->xyz; A.aux = io->aux_dir;
     A.rgb = io->rgb; A.depth = io->depth; A.weights = io->weights; A.transparency = io->transparency; A.albedo = io->albedo;
-    A.sun = io->sun; A.sky = io->sky; A.beta = io->beta; A.sigma = io->sigma;
+    A.sun = io->sun; A.sky = io->sky; A.beta = io->beta; A.sigma = io->sigma; A.aux_sums = io->aux_sums; A.t_min = p->t_min;
     A.packed = (unsigned char*)workspace;
     A.R = p->n_rays; A.S = p->n_samples; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
     A.G = choose_group(A.S); A.n_groups = (A.R + A.G - 1) / A.G;
     A.stash_base = (unsigned char*)io->stash;
     if (A.stash_base) { int tpg = (A.G * A.S + kTile - 1) / kTile; stash_layout(L, A.n_groups * tpg, tpg, &A.stash); }
-    { const char* e = getenv("SNB_TC_DBG"); A.dbg = e ? atoi(e) : 0; }
+    A.dbg = dev_knobs().dbg;
 
     MiscOffsets M; memset(&M, 0, sizeof(M));
     M.sigma_w = L.sigma.w; M.sigma_b = L.sigma.b; M.rgb0_b = L.rgb0.b; M.rgb2_w = L.rgb2.w; M.rgb2_b = L.rgb2.b;
@@ -1030,7 +1065,7 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
 
 int tc_stash_bytes(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes) {
     *bytes = 0;
-    if (!tc_supported(L, p)) return 0;
+    if (!tc_supported(L, p) || !tc_bwd_supported(L, p)) return 0;      // no tensor-core backward for this shape: nothing to stash (the fp32 backward recomputes)
     int G = choose_group(p->n_samples), tpg = (G * p->n_samples + kTile - 1) / kTile, groups = (p->n_rays + G - 1) / G;
     TcStash S; stash_layout(L, groups * tpg, tpg, &S);
     *bytes = (size_t)S.total + 1024;

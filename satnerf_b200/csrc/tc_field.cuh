@@ -14,6 +14,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
 
 int tc_debug_read(void* dst, size_t bytes);
 int tc_debug_hang_info(unsigned int* out4);
+bool tc_bwd_supported(const FieldLayout& L, const snb_pass_desc* p);
 int tc_bwd_workspace(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes);
 int tc_stash_bytes(const FieldLayout& L, const snb_pass_desc* p, size_t* bytes);
 

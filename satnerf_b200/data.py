@@ -14,6 +14,8 @@ from typing import Dict, Iterator, Optional
 
 import torch
 
+from .dist import shard_bounds
+
 
 class DeviceRaySampler:
     """Iterable over `{"rays", "ts", "rgbs" | "depths"}` batches with DataLoader(shuffle=True) semantics.
@@ -42,9 +44,9 @@ class DeviceRaySampler:
             perm = torch.arange(self.n, device=self.device)
         for b in range(len(self)):
             idx = perm[b * self.batch_size:(b + 1) * self.batch_size]
-            if self.world > 1:                      # contiguous ray shard of the global batch per rank (satnerf_b200.dist.shard_rays)
-                per = (idx.numel() + self.world - 1) // self.world
-                idx = idx[self.rank * per:(self.rank + 1) * per]
+            if self.world > 1:                      # contiguous ray shard of the global batch per rank: the split of dist.shard_bounds
+                lo, hi = shard_bounds(idx.numel(), self.rank, self.world)
+                idx = idx[lo:hi]
             yield {k: v[idx] for k, v in self.data.items()}
 
 

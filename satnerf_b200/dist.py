@@ -42,27 +42,53 @@ def gather_rays(local: Dict[str, torch.Tensor], n_rays: int) -> Dict[str, torch.
     return out
 
 
-def all_reduce_gradients(models: Dict[str, torch.nn.Module], average: bool = True) -> int:
-    """Sums (averages) gradients across ranks: one collective per field over its flat gradient buffer, one for
-    the embedding.  Returns the number of collectives issued."""
+def broadcast_parameters(models: Dict[str, torch.nn.Module], src: int = 0) -> int:
+    """Start-up: every rank takes rank `src`'s parameters (one broadcast per field over its flat buffer, one for the embedding), so
+    replicas agree whatever their local seeds were.  Writes go through `.data`, which autograd's version counters do not see:
+    the cached fp16 weight tiles are invalidated explicitly.  Returns the number of collectives."""
     r, w = world()
     if w == 1:
         return 0
     n = 0
-    for name, m in models.items():
-        if hasattr(m, "flat_grads"):
-            g = m.flat_grads(zero=False)
+    for m in models.values():
+        if hasattr(m, "flat_params"):
+            dist.broadcast(m.flat_params(), src)
+            m.invalidate_packed()
         else:
-            ps = [p for p in m.parameters() if p.grad is not None]
-            if not ps:
-                continue
-            g = torch.cat([p.grad.reshape(-1) for p in ps])
-        dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        if average:
-            g.div_(w)
-        if not hasattr(m, "flat_grads"):
-            off = 0
-            for p in ps:
-                p.grad.copy_(g[off:off + p.numel()].view_as(p.grad)); off += p.numel()
+            for p in m.parameters():
+                dist.broadcast(p.data, src)
         n += 1
     return n
+
+
+def all_reduce_gradients(models: Dict[str, torch.nn.Module], average: bool = True) -> int:
+    """Sums gradients across ranks with ONE collective per step: when every gradient already lives in one bucket (a single field
+    and no embedding) the flat buffer is reduced in place; otherwise the flat gradient buffers of the fields and the (tiny)
+    embedding gradient are packed into one bucket, reduced, and unpacked.  `average=False` when 1/world is already folded into
+    the loss seed (render_loss_backward(n_rays_mean = global batch)).  Returns the number of collectives issued (0 or 1)."""
+    r, w = world()
+    if w == 1:
+        return 0
+    parts = []
+    for m in models.values():
+        if hasattr(m, "flat_grads"):
+            parts.append(m.flat_grads(zero=False))
+        else:
+            for p in m.parameters():
+                if p.grad is not None:
+                    parts.append(p.grad)
+    if not parts:
+        return 0
+    if len(parts) == 1:
+        bucket = parts[0].view(-1)
+    else:
+        bucket = torch.cat([g.reshape(-1) for g in parts])
+    dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+    if average:
+        bucket.div_(w)
+    if len(parts) > 1:
+        off = 0
+        for g in parts:
+            g.copy_(bucket[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    return 1

@@ -92,6 +92,13 @@ class _Field(nn.Module):
         self._desc = capi.field_desc(self.variant, layers, feat, self.skips, t_dims, self.mapping_sizes, self.use_mapping)
         self._flat: Optional[torch.Tensor] = None
         self._flat_grad: Optional[torch.Tensor] = None
+        self._packed_epoch = 0
+
+    def invalidate_packed(self):
+        """Drops the cached fp16 weight tiles of the inference path.  In-place updates through the parameters (optimizer steps,
+        load_state_dict) are detected by their version counters; call this after writing through `.data` / `flat_params()`
+        (EMA swaps, dist.broadcast(p.data), manual copies), which autograd cannot see."""
+        self._packed_epoch += 1
 
     # ---- flat parameter storage -------------------------------------------------------------
     @property
@@ -123,7 +130,20 @@ class _Field(nn.Module):
                 p.data = flat[off:off + n].view(p.shape)
                 off += n
             self._flat, self._flat_grad = flat, None
+            self._packed_epoch += 1
         return flat
+
+    def flat_parameter(self) -> nn.Parameter:
+        """The flat buffer as ONE nn.Parameter (shares storage and version counter with `flat_params()`; `.grad` aliases
+        `flat_grads()`): what the training harness hands to Adam, so the update is one launch over one tensor.  The module's own
+        parameters are views of the same storage and see every update."""
+        flat = self.flat_params()
+        fp = getattr(self, "_flat_param", None)
+        if fp is None or fp.data_ptr() != flat.data_ptr() or fp.device != flat.device:
+            fp = nn.Parameter(flat, requires_grad=True)
+            object.__setattr__(self, "_flat_param", fp)      # not registered: state_dict / parameters() stay the reference's
+        fp.grad = self.flat_grads(zero=False)
+        return fp
 
     def flat_grads(self, zero: bool = True) -> torch.Tensor:
         """One flat gradient buffer whose slices are the parameters' `.grad` (a single NCCL all-reduce target)."""
@@ -150,6 +170,9 @@ class _Field(nn.Module):
             self._flat_grad = g
         elif zero:
             g.zero_()
+        fp = getattr(self, "_flat_param", None)
+        if fp is not None and (fp.grad is None or fp.grad.data_ptr() != g.data_ptr()):
+            fp.grad = g
         return g
 
     # ---- <Field>.forward: per-point evaluation ------------------------------------------------

@@ -18,7 +18,7 @@ from .rendering import render_rays
 
 
 class NeRFSystem:
-    def __init__(self, args, device="cuda"):
+    def __init__(self, args, device="cuda", train_len=None):
         self.args = copy.copy(args)
         self.device = torch.device(device)
         self.loss = metrics.load_loss(args)                                    # main.py:33
@@ -31,7 +31,13 @@ class NeRFSystem:
         self.use_ts = args.model == "sat-nerf"                                 # main.py:44-47
         if self.use_ts:
             self.loss_without_beta = metrics.SNerfLoss(lambda_sc=args.sc_lambda)
-        self.steps_per_epoch = getattr(args, "steps_per_epoch", None)
+        # epoch arithmetic of the reference (train_utils.py:14-15): epoch = step // (len(train_dataset) // batch_size).
+        # `train_len` = number of training rays; set_train_loaders() takes it from the sampler.
+        self.train_len = train_len
+        self.batches_per_epoch = None          # len(loader): where Lightning steps the 'epoch'-interval scheduler
+        self.fused = bool(getattr(args, "fused_loss", True))
+        self.optimizer = self.scheduler = None
+        sdist.broadcast_parameters(self.models)      # replicas start from rank 0's initialisation (no-op single-process)
 
     def define_models(self):                                                   # main.py:49-58
         a = self.args
@@ -41,6 +47,11 @@ class NeRFSystem:
             self.nerf_fine = self.models["fine"] = load_model(a).to(self.device)
         if a.model == "sat-nerf":
             self.embedding_t = self.models["t"] = torch.nn.Embedding(a.t_embbeding_vocab, a.t_embbeding_tau).to(self.device)
+
+    def set_train_loaders(self, loaders):
+        """The dict of loaders of train_dataloader (main.py:96-110): fixes the epoch arithmetic (dataset length, batches per epoch)."""
+        self.train_len = loaders["color"].n
+        self.batches_per_epoch = max(len(v) for v in loaders.values())
 
     def state_dict(self):
         """Lightning-style keys (`nerf_coarse.*`, `nerf_fine.*`, `embedding_t.*`) read by eval_satnerf.py:23-44."""
@@ -59,16 +70,31 @@ class NeRFSystem:
     __call__ = forward
 
     def configure_optimizers(self):                                            # main.py:81-94, train_utils.py:24-53
-        params = [p for m in self.models.values() for p in m.parameters()]
-        # same update rule as the reference (Adam, lr, no weight decay); the fused implementation is one launch on CUDA
-        self.optimizer = torch.optim.Adam(params, lr=self.args.lr, weight_decay=0, fused=params[0].is_cuda)
+        """Adam(lr, weight_decay=0) + StepLR(gamma=0.9) per epoch, as the reference.  The fields keep their parameters as views
+        of one flat buffer each, so Adam runs on that buffer (one multi-tensor launch over 1-3 tensors instead of 35-70); the
+        elementwise update -- and therefore every parameter value -- is identical to per-tensor Adam."""
+        groups = []
+        for m in self.models.values():
+            if hasattr(m, "flat_parameter"):
+                groups.append(m.flat_parameter())
+            else:
+                groups += list(m.parameters())
+        self.optimizer = torch.optim.Adam(groups, lr=self.args.lr, weight_decay=0, fused=groups[0].is_cuda)
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=1, gamma=0.9)   # stepped per epoch
         return self.optimizer
 
-    def get_current_epoch(self, tstep):
-        return 0 if not self.steps_per_epoch else tstep // self.steps_per_epoch
+    def get_current_epoch(self, tstep):                                        # main.py:230-231
+        if self.train_len is None:
+            if self.use_ts:
+                raise RuntimeError("NeRFSystem needs the training-set length (train_len= / set_train_loaders()): sat-nerf switches from "
+                                   "SNerfLoss to SatNerfLoss after epoch 2 (main.py:128) and the learning rate decays per epoch")
+            return 0
+        per_epoch = max(self.train_len // self.args.batch_size, 1)
+        return int(tstep // per_epoch)
 
     def training_step(self, batch):                                            # main.py:119-154
+        if self.fused:
+            return self.fused_training_step(batch)
         self.train_steps += 1
         rays, rgbs = batch["color"]["rays"], batch["color"]["rgbs"]
         ts = batch["color"]["ts"].squeeze() if self.use_ts else None
@@ -91,37 +117,119 @@ class NeRFSystem:
             loss_dict["psnr"] = metrics.psnr(results[f"rgb_{typ}"], rgbs)
         return loss, loss_dict
 
+    def fused_training_step(self, batch):
+        """training_step with the losses and their gradients evaluated inside the library (rendering.render_loss_backward):
+        same loss terms, same parameter gradients (accumulated straight into the flat `.grad` buffers -- no autograd graph, no
+        `loss.backward()`), same RNG consumption.  With N ranks every mean() divides by the GLOBAL batch size, so the gradient
+        all-reduce is a plain sum."""
+        self.train_steps += 1
+        a = self.args
+        world = sdist.world()[1]
+        chunk = a.chunk
+        kind = "mse" if (a.model != "sat-nerf" or self.get_current_epoch(self.train_steps) < 2) else "beta"
+        rays, rgbs = batch["color"]["rays"], batch["color"]["rgbs"]
+        ts = batch["color"]["ts"].reshape(-1) if self.use_ts else None
+        n_mean = rays.shape[0] * world
+        loss_dict, rgb_parts = {}, []
+
+        def run(rays_, ts_, backward, **what):
+            out = {}
+            for i in range(0, rays_.shape[0], chunk):                          # main.py:60-75: ray chunks; terms of the chunks add up
+                sl = slice(i, i + chunk)
+                spec = {k: tuple(v_[sl] if torch.is_tensor(v_) else v_ for v_ in v) for k, v in what.items()}
+                d, res = render_loss_backward(self.models, a, rays_[sl], None if ts_ is None else ts_[sl], n_rays_mean=rays_.shape[0] * world,
+                                              backward=backward, **spec)
+                for k, v in d.items():
+                    out[k] = v if k not in out else out[k] + v
+                rgb_parts.append(res)
+            return out
+
+        loss_dict.update(run(rays, ts, True, color=(kind, rgbs)))
+        typ = "fine" if a.n_importance > 0 else "coarse"
+        rgb = torch.cat([r[f"rgb_{typ}"] for r in rgb_parts], 0)
+        loss = sum(loss_dict.values())
+        a.noise_std *= 0.9
+        if self.depth:
+            dep = batch["depth"]
+            kp_depths = torch.flatten(dep["depths"][:, 0])
+            kp_weights = None if a.ds_noweights else torch.flatten(dep["depths"][:, 1])
+            use = self.train_steps < self.ds_drop          # (afterwards the reference still renders the batch, for logging only)
+            tmp = run(dep["rays"], dep["ts"].reshape(-1), use, depth=(kp_depths, kp_weights, a.ds_lambda))
+            if use:
+                loss = loss + sum(tmp.values())
+            loss_dict.update(tmp)
+        loss_dict["psnr"] = metrics.psnr(rgb, rgbs)
+        del n_mean
+        return loss, loss_dict
+
+    def zero_grad(self):
+        for m in self.models.values():
+            if hasattr(m, "flat_grads"):
+                m.flat_grads(zero=True)            # one memset; the parameters' .grad (and the flat parameter's) alias it
+            else:
+                for p in m.parameters():
+                    if p.grad is not None:
+                        p.grad.zero_()
+
     def optimization_step(self, batch):
-        """zero grads -> training_step -> backward -> [all-reduce] -> Adam (what Lightning's fit loop does)."""
-        for m in self.models.values():          # grads are (re)assigned as slices of one flat buffer by the render backward
-            for p in m.parameters():
-                p.grad = None
-        loss, info = self.training_step(batch)
-        loss.backward()
-        sdist.all_reduce_gradients(self.models)
+        """zero grads -> training_step -> backward -> [all-reduce] -> Adam -> [epoch end: StepLR] (Lightning's fit loop)."""
+        if self.fused:
+            self.zero_grad()
+            loss, info = self.training_step(batch)
+            sdist.all_reduce_gradients(self.models, average=False)       # 1/world is already in the loss seed (n_rays_mean)
+        else:
+            for m in self.models.values():      # grads are (re)assigned as slices of one flat buffer by the render backward
+                for p in m.parameters():
+                    p.grad = None
+            loss, info = self.training_step(batch)
+            loss.backward()
+            for m in self.models.values():
+                if hasattr(m, "flat_grads"):
+                    m.flat_grads(zero=False)    # (re)bind .grad to the flat buffer the backward filled
+            sdist.all_reduce_gradients(self.models, average=True)
         self.optimizer.step()
+        if self.batches_per_epoch and self.train_steps % self.batches_per_epoch == 0:
+            self.on_epoch_end()
         return loss.detach(), info
 
+    def on_epoch_end(self):
+        """Lightning steps an interval='epoch' scheduler here (main.py:88-93): lr *= 0.9."""
+        if self.scheduler is not None:
+            self.scheduler.step()
 
-def bench_training_step(args, dev, rank, world, n_rays, warm, steps, flush):
-    """bench.py's training leg: n_rays per rank, fwd + bwd + gradient all-reduce + Adam per step."""
+
+def bench_training_step(args, dev, rank, world, n_rays, warm, steps, flush, depth_batch=False, n_dataset=1 << 18):
+    """bench.py's training legs: n_rays per rank and step, fed by DeviceRaySampler from a GPU-resident synthetic training set
+    (n_dataset rays; every rank keeps the set and takes its shard of each global batch): render forward + in-kernel loss seed
+    + backward + one gradient all-reduce + Adam per step.  depth_batch adds the depth-supervision batch (main.py:134-142)."""
     import torch.distributed as dist
     from . import capi
+    from .data import DeviceRaySampler, combined_loader
+    from .synth import synthetic_sat_rays
     a = copy.copy(args)
-    a.lr, a.chunk = 5e-4, 1 << 20
+    a.lr, a.chunk, a.batch_size = 5e-4, 1 << 20, n_rays * world
     torch.manual_seed(0)
+    rays, ts = synthetic_sat_rays(n_dataset, seed=200)
+    g = torch.Generator().manual_seed(201)
+    data = {"rays": rays, "rgbs": torch.rand(n_dataset, 3, generator=g), "ts": ts.reshape(-1, 1)}
+    loaders = {"color": DeviceRaySampler(data, a.batch_size, device=dev, generator=torch.Generator().manual_seed(7), rank=rank, world=world)}
+    if depth_batch:
+        nd = n_dataset // 8
+        dd = {"rays": rays[:nd], "ts": ts[:nd].reshape(-1, 1),
+              "depths": torch.stack([0.1 + 0.2 * torch.rand(nd, generator=g), torch.rand(nd, generator=g)], -1)}
+        loaders["depth"] = DeviceRaySampler(dd, a.batch_size, device=dev, generator=torch.Generator().manual_seed(8), rank=rank, world=world)
     system = NeRFSystem(a, dev)
-    system.steps_per_epoch = 10 ** 9          # stay in the first epochs (SNerfLoss branch, main.py:128-129)
+    system.set_train_loaders(loaders)
     system.configure_optimizers()
-    g = torch.Generator().manual_seed(200 + rank)
-    u = torch.rand(n_rays, 2, generator=g) * 2 - 1
-    o = torch.cat([u, torch.ones(n_rays, 1)], -1)
-    d = torch.tensor([[0.3, 0.1, -0.95]]).expand(n_rays, 3) + 1e-3 * torch.randn(n_rays, 3, generator=g)
-    d = d / d.norm(dim=-1, keepdim=True)
-    sun = torch.tensor([[0.4, -0.5, 0.77]]).expand(n_rays, 3)
-    rays = torch.cat([o, d, torch.zeros(n_rays, 1), 0.3 + 0.3 * torch.rand(n_rays, 1, generator=g), sun], -1).to(dev)
-    batch = {"color": {"rays": rays, "rgbs": torch.rand(n_rays, 3, generator=g).to(dev),
-                       "ts": torch.randint(0, 17, (n_rays, 1), generator=g).to(dev)}}
+    batches = combined_loader(loaders)
+
+    def next_batch():
+        nonlocal batches
+        try:
+            return next(batches)
+        except StopIteration:
+            batches = combined_loader(loaders)
+            return next(batches)
 
     def sync():
         if world > 1:
@@ -129,14 +237,14 @@ def bench_training_step(args, dev, rank, world, n_rays, warm, steps, flush):
         torch.cuda.synchronize()
 
     for _ in range(warm):
-        system.optimization_step(batch)
+        system.optimization_step(next_batch())
     sync()
     capi.launch_count(reset=True)
     evs = []
     for _ in range(steps):
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); system.optimization_step(batch); e1.record()
+        e0.record(); system.optimization_step(next_batch()); e1.record()      # the sampler's gather is inside the timed region
         evs.append((e0, e1))
     sync()
     ms = sum(x.elapsed_time(y) for x, y in evs)
@@ -145,5 +253,8 @@ def bench_training_step(args, dev, rank, world, n_rays, warm, steps, flush):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    what = "DeviceRaySampler batch + render forward + loss seeded in the compositing backward + backward + one flat-gradient all-reduce + Adam"
+    if depth_batch:
+        what += " (colour batch + depth-supervision batch, both coarse + fine)"
     return {"value": world * n_rays * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,
-            "what": "render_rays forward + SNerfLoss + backward + flat-gradient all-reduce + Adam", "gpu_launches": launches}
+            "model": a.model, "what": what, "gpu_launches": launches / steps}

@@ -79,6 +79,20 @@ def pcg_params(shapes, seed):
     return out
 
 
+def trained_like(sd):
+    """'Trained-like' regime: default init gives sigma ~ 0.7 (60 % of the weight on the last sample); here the
+    density head is sharpened (weight x64, bias -2: rays saturate mid-way, alpha up to ~0.3 per sample) and the head layers
+    carry twice their init scale, as weights grown by training do.  Deterministic transform of a state dict (numpy arrays)."""
+    out = {k: v.copy() for k, v in sd.items()}
+    out["sigma_from_xyz.0.weight"] = out["sigma_from_xyz.0.weight"] * np.float32(64.0)
+    out["sigma_from_xyz.0.bias"] = np.full_like(out["sigma_from_xyz.0.bias"], -2.0)
+    for k in ("feats_from_xyz.weight", "rgb_from_xyzdir.0.weight", "rgb_from_xyzdir.2.weight", "sun_v_net.6.weight",
+              "beta_from_xyz.0.weight", "beta_from_xyz.2.weight"):
+        if k in out:
+            out[k] = out[k] * np.float32(2.0)
+    return out
+
+
 def make_args(**kw):
     base = dict(model="sat-nerf", n_samples=16, n_importance=0, noise_std=0.0, sc_lambda=0.0, chunk=5120,
                 fc_layers=8, fc_units=64, t_embbeding_tau=4, t_embbeding_vocab=30)
@@ -86,7 +100,7 @@ def make_args(**kw):
     return argparse.Namespace(**base)
 
 
-def build_models(args, seed, pcg_seed=None):
+def build_models(args, seed, pcg_seed=None, transform=None):
     torch.manual_seed(seed)
     ms = {"coarse": ref_models.load_model(args)}
     if args.n_importance > 0:
@@ -96,13 +110,16 @@ def build_models(args, seed, pcg_seed=None):
     if pcg_seed is not None:
         for i, lvl in enumerate(k for k in ("coarse", "fine") if k in ms):
             shapes = {k: tuple(v.shape) for k, v in ms[lvl].state_dict().items()}
-            sd = {k: torch.from_numpy(v) for k, v in pcg_params(shapes, pcg_seed + i).items()}
+            raw = pcg_params(shapes, pcg_seed + i)
+            if transform == "trained_v1":
+                raw = trained_like(raw)
+            sd = {k: torch.from_numpy(v) for k, v in raw.items()}
             ms[lvl].load_state_dict(sd)
     return ms
 
 
-def run_case(name, args, n_rays, seed, with_grads=None, pcg_seed=None, store_params=True):
-    ms = build_models(args, seed, pcg_seed)
+def run_case(name, args, n_rays, seed, with_grads=None, pcg_seed=None, store_params=True, transform=None):
+    ms = build_models(args, seed, pcg_seed, transform)
     if args.model == "nerf":
         rays, ts = synthetic_blender_rays(n_rays, seed=seed + 1), None
     else:
@@ -125,6 +142,8 @@ def run_case(name, args, n_rays, seed, with_grads=None, pcg_seed=None, store_par
         blob["param.t"] = ms["t"].weight.detach().numpy()
     if pcg_seed is not None:
         blob["pcg_seed"] = np.int64(pcg_seed)
+    if transform is not None:
+        blob["pcg_transform"] = np.array(transform)
     cfg = {k: getattr(args, k) for k in ("model", "n_samples", "n_importance", "noise_std", "sc_lambda",
                                          "fc_layers", "fc_units", "t_embbeding_tau", "t_embbeding_vocab")}
     blob["cfg"] = np.array(repr(cfg))
@@ -190,4 +209,5 @@ if __name__ == "__main__":
     run_case("nerf_fine_h64", make_args(model="nerf", n_importance=8), 24, 15, with_grads="snerf")
     run_case("satnerf_h512", make_args(fc_units=512, n_samples=64), 8, 16, pcg_seed=1234, store_params=False)
     run_case("satnerf_h256_s96", make_args(fc_units=256, n_samples=96), 6, 17, pcg_seed=4321, store_params=False)
+    run_case("satnerf_h512_trained", make_args(fc_units=512, n_samples=64), 16, 18, pcg_seed=1234, store_params=False, transform="trained_v1")
     sample_pdf_case()

@@ -10,6 +10,9 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["satnerf_h64", "satnerf_h64_snerfloss_depth", "satnerf_sc_h64", "satnerf_fine_h64", "snerf_sc_h64",
          "nerf_fine_h64", "satnerf_h512", "satnerf_h256_s96"]
+# 'trained-like' regime (sharp density head): same pinning, separate list because the fp16-operand path is
+# measured -- not gated at 1e-3 -- on it (tests/test_gpu_oracle_fullsize.py)
+TRAINED_CASES = ["satnerf_h512_trained"]
 
 
 def pcg_params(shapes, seed):
@@ -25,6 +28,18 @@ def pcg_params(shapes, seed):
         else:
             bound = 1.0 / np.sqrt(fan[name[:-5]])
         out[name] = (u * np.float32(bound)).astype(np.float32)
+    return out
+
+
+def trained_like(sd):
+    """Same transform as tests/golden/make_golden.py::trained_like (numpy arrays in, numpy arrays out)."""
+    out = {k: v.copy() for k, v in sd.items()}
+    out["sigma_from_xyz.0.weight"] = out["sigma_from_xyz.0.weight"] * np.float32(64.0)
+    out["sigma_from_xyz.0.bias"] = np.full_like(out["sigma_from_xyz.0.bias"], -2.0)
+    for k in ("feats_from_xyz.weight", "rgb_from_xyzdir.0.weight", "rgb_from_xyzdir.2.weight", "sun_v_net.6.weight",
+              "beta_from_xyz.0.weight", "beta_from_xyz.2.weight"):
+        if k in out:
+            out[k] = out[k] * np.float32(2.0)
     return out
 
 
@@ -65,8 +80,12 @@ class Golden:
         levels = ["coarse"] + (["fine"] if self.cfg.n_importance > 0 else [])
         if "pcg_seed" in z:
             sh = field_shapes(self.cfg.model, self.cfg.fc_units, self.cfg.fc_layers, self.cfg.t_embbeding_tau)
+            tr = str(z["pcg_transform"]) if "pcg_transform" in z else None
             for i, lvl in enumerate(levels):
-                self.params[lvl] = {k: torch.from_numpy(v) for k, v in pcg_params(sh, int(z["pcg_seed"]) + i).items()}
+                raw = pcg_params(sh, int(z["pcg_seed"]) + i)
+                if tr == "trained_v1":
+                    raw = trained_like(raw)
+                self.params[lvl] = {k: torch.from_numpy(v) for k, v in raw.items()}
         else:
             for lvl in levels:
                 pre = f"param.{lvl}."
@@ -85,3 +104,21 @@ def rel_err(a, b, floor=1e-6):
     """max |a-b| / max(max|b|, floor): the 'max-abs over max-ref' measure SURVEY.md §7 uses for the 1e-3 target."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / max(float(b.abs().max()), floor))
+
+
+# Elementwise parity measure: |a - b| <= rtol * |b| + atol[key].  rtol = 1e-3 is north_star's tolerance; the absolute
+# floors cover outputs that legitimately reach 0 (weights / transparency go down to 1e-10, satnerf.py:61; rgb is clamped
+# at 0): they are ~1e-4 of each tensor's natural scale (weights sum to 1 per ray, everything else lives in [0, 1]).
+ATOL = {"rgb": 1e-4, "depth": 1e-4, "weights": 2e-5, "transparency": 1e-4, "albedo": 1e-4, "sun": 1e-4, "sky": 1e-4,
+        "beta": 1e-4, "weights_sc": 2e-5, "transparency_sc": 1e-4, "sun_sc": 1e-4}
+
+
+def atol_for(key):
+    base = key.rsplit("_", 1)[0] if key.endswith(("_coarse", "_fine")) else key
+    return ATOL[base]
+
+
+def elementwise_excess(a, b, key, rtol=1e-3):
+    """max over elements of |a-b| / (rtol*|b| + atol(key)); <= 1 means every element is within tolerance."""
+    a, b = a.double(), b.double()
+    return float(((a - b).abs() / (rtol * b.abs() + atol_for(key))).max()) if a.numel() else 0.0

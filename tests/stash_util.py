@@ -38,6 +38,6 @@ def unpack_atoms(buf, off, n_tiles, F):
 
 
 def unpack_yb(buf, off, n_tiles, F):
-    """yb [gt][F/32][128][32] fp16 revolutions -> (n_tiles*128, F) float."""
-    raw = buf[off:off + n_tiles * 128 * F * 2].view(torch.float16).view(n_tiles, F // 32, 128, 32)
+    """yb [gt][F/8][128][8] fp16 revolutions -> (n_tiles*128, F) float."""
+    raw = buf[off:off + n_tiles * 128 * F * 2].view(torch.float16).view(n_tiles, F // 8, 128, 8)
     return raw.permute(0, 2, 1, 3).reshape(n_tiles * 128, F).float()

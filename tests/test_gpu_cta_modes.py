@@ -1,4 +1,5 @@
-"""The fused tensor-core forward runs as CTA pairs (cta_group::2, the default) or as single CTAs (SNB_TC_CG=1).
+"""The fused tensor-core forward runs as CTA pairs (cta_group::2, the default) or as single CTAs (args.tc_cta_group = 1 ->
+snb_pass_desc.flags & SNB_PASS_SINGLE_CTA).
 Both modes must give bit-identical results (same MMA shapes per point, same epilogue arithmetic), odd group counts
 (a pair with an idle half) included, in inference and in training mode (activation stash -> tensor-core backward)."""
 import pytest
@@ -10,9 +11,9 @@ from oracle import render_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def _run(monkeypatch, cg, args, ms, rays, ts, draws, target=None):
+def _run(cg, args, ms, rays, ts, draws, target=None):
     import satnerf_b200 as sb
-    monkeypatch.setenv("SNB_TC_CG", cg)
+    args.tc_cta_group = cg
     for m in ms.values():
         m.zero_grad(set_to_none=True)
     if target is None:
@@ -25,7 +26,7 @@ def _run(monkeypatch, cg, args, ms, rays, ts, draws, target=None):
 
 @pytest.mark.parametrize("h,n_rays,S,train", [(512, 4096, 64, False), (512, 101, 64, False), (256, 51, 96, False), (384, 7, 48, False),
                                                (512, 101, 64, True), (128, 50, 64, True)])
-def test_cta_pair_equals_single_cta(monkeypatch, h, n_rays, S, train):
+def test_cta_pair_equals_single_cta(h, n_rays, S, train):
     import satnerf_b200 as sb
     args = make_args(fc_units=h, n_samples=S, precision="tc")
     torch.manual_seed(5)
@@ -34,8 +35,8 @@ def test_cta_pair_equals_single_cta(monkeypatch, h, n_rays, S, train):
     g = torch.Generator().manual_seed(7)
     draws = [torch.rand(n_rays, S, generator=g), torch.randn(n_rays, S, generator=g)]
     target = torch.rand(n_rays, 3, generator=g).cuda() if train else None
-    a, ga = _run(monkeypatch, "2", args, ms, rays.cuda(), ts.cuda(), draws, target)
-    b, gb = _run(monkeypatch, "1", args, ms, rays.cuda(), ts.cuda(), draws, target)
+    a, ga = _run(2, args, ms, rays.cuda(), ts.cuda(), draws, target)
+    b, gb = _run(1, args, ms, rays.cuda(), ts.cuda(), draws, target)
     for k in a:
         assert torch.equal(a[k], b[k]), k
     if train:

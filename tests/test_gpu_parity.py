@@ -123,11 +123,17 @@ def test_sample_pdf_indices_bit_exact():
     z_out, k, z_new, cdf_dev = capi.importance_depths(zc.cuda().contiguous(), wfull.cuda().contiguous(), u.cuda().contiguous(), debug=True)
     cdf_dev = cdf_dev.cpu()
     assert (cdf_dev - cdf).abs().max() <= 2.4e-7
+    # (a) on EVERY row the kernel's indices are exactly searchsorted(right=True) of the cdf it built (pure comparisons)
+    assert torch.equal(k.cpu(), torch.searchsorted(cdf_dev, u.contiguous(), right=True))
+    # (b) wherever its (cdf, u) equal the reference's bit for bit, so do indices and samples
     same_cdf_rows = (cdf_dev == cdf).all(-1)
-    assert same_cdf_rows.float().mean() > 0.5
     assert torch.equal(k.cpu()[same_cdf_rows], inds[same_cdf_rows])
-    assert (k.cpu() != inds).float().mean() < 1e-3
     assert torch.equal(z_new.cpu()[same_cdf_rows], samples[same_cdf_rows])
+    # (c) report: rows whose cdf differs by an ulp (torch's CPU `sum` is a vectorised cascade no device order reproduces,
+    #     SURVEY.md 7) and index mismatches among all R*N samples -- none on this fixture
+    n_rows_diff, n_mismatch = int((~same_cdf_rows).sum()), int((k.cpu() != inds).sum())
+    print(f"importance sampling: {n_rows_diff}/{R} rows with an ulp-level cdf difference, {n_mismatch}/{inds.numel()} index mismatches")
+    assert n_mismatch <= 1e-3 * inds.numel(), n_mismatch
     # merged output is the sorted concatenation
     want_sorted = torch.sort(torch.cat([zc, z_new.cpu()], -1), -1)[0]
     assert torch.equal(z_out.cpu(), want_sorted)
@@ -216,13 +222,21 @@ def test_tc_backward_matches_fp64_oracle(model, h, n_rays, S):
     ms = {k: m.cuda() for k, m in ms.items()}
     res = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
     loss_fn(res, target.cuda())[0].backward()
-    worst = 0.0
+    errs = {}
     for name, prm in ms["coarse"].named_parameters():
         ref = P["coarse"][name].grad
         # a bias gradient is a signed sum over all points and can cancel to ~0: measure it on the scale of its layer's weight gradient
         floor = float(P["coarse"][name.replace(".bias", ".weight")].grad.abs().max()) if name.endswith(".bias") else 1e-12
-        err = rel_err(prm.grad.cpu(), ref, floor=floor)
-        worst = max(worst, err)
-        assert err < 2e-2, (name, err)
+        errs[name] = rel_err(prm.grad.cpu(), ref, floor=floor)
     if model == "sat-nerf":
-        assert rel_err(ms["t"].weight.grad.cpu(), P["t"].grad, floor=1e-12) < 2e-2
+        errs["t"] = rel_err(ms["t"].weight.grad.cpu(), P["t"].grad, floor=1e-12)
+    try:
+        import json, os
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "a") as f:
+            f.write(json.dumps({"test": f"tc_backward_vs_fp64[{model},{h},{n_rays},{S}]", "rows": errs}) + "\n")
+    except OSError:
+        pass
+    bad = {k: v for k, v in errs.items() if v >= GRAD_TOL["tc"]}
+    assert not bad, bad

@@ -9,11 +9,11 @@ pytestmark = pytest.mark.gpu
 def test_weight_gradient_gemm_matches_torch(P, Fa, Fb, ks):
     """dW = Ya^T Xb with K = points on MN-major UMMA operands in the point-atom layout.
     Inputs are rounded to fp16 by the packer; products accumulate in fp32: tolerance 1e-4 of max |ref|."""
-    from satnerf_b200 import capi
+    from satnerf_b200 import capi_dev
     g = torch.Generator().manual_seed(P + Fa)
     xa = (torch.randn(P, Fa, generator=g) * 0.5).cuda()
     xb = torch.randn(P, Fb, generator=g).cuda()
-    got = capi.debug_dw_gemm(xa, xb, ks)
+    got = capi_dev.debug_dw_gemm(xa, xb, ks)
     ref = xa.half().double().T @ xb.half().double()
     err = float((got.double() - ref).abs().max() / ref.abs().max())
     assert err < 1e-4, err
@@ -49,7 +49,7 @@ def test_forward_stash_matches_oracle_activations():
         h = torch.sin(y); acts.append(h); pres.append(y)
     feat = F.linear(h, p["feats_from_xyz.weight"], p["feats_from_xyz.bias"])
     field = field.cuda()
-    pd = capi.PassDesc(R, S, 11, 0, capi.FP16_TC, 0.0, 0)
+    pd = capi.PassDesc(R, S, 11, 0, capi.FP16_TC, 0.0, 0, 0, 0.0)
     nbytes = capi.render_stash_bytes(field.desc, pd)
     stash = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     outs = {k: torch.empty(s, device="cuda") for k, s in dict(rgb=(R, 3), depth=(R,), weights=(R, S), transparency=(R, S), albedo=(R, S, 3),

@@ -27,7 +27,21 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(capi.exported_symbols())
-    assert lib.snb_abi_version() == 2
+    assert lib.snb_abi_version() == 3
+
+
+def test_dev_library_exports_its_header():
+    """The developer entry points live in a separate library (libsatnerf_b200_dev.so), not in the product ABI."""
+    from satnerf_b200 import capi, capi_dev
+    header = open(os.path.join(ROOT, "include", "satnerf_b200_dev.h")).read()
+    declared = set(re.findall(r"SNB_API\s+[\w\s\*]+?\b(snb_\w+)\s*\(", header))
+    assert declared == set(capi_dev.exported_symbols()) and len(declared) == 6
+    lib = capi_dev.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    prod = capi.lib()
+    for name in declared:
+        assert not hasattr(prod, name), f"{name} leaked into the product library"
 
 
 @pytest.mark.parametrize("model,h", [("sat-nerf", 64), ("sat-nerf", 512), ("s-nerf", 256), ("nerf", 256)])

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_io import CASES, GOLDEN_DIR, Golden, rel_err
+from golden_io import CASES, GOLDEN_DIR, TRAINED_CASES, Golden, rel_err
 from oracle import render_oracle as orc
 
 
@@ -15,7 +15,7 @@ def _loss(g, res):
     return orc.loss_depth(res, g.depth_target, g.depth_weights, lam_ds=1000.0)[0]
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + TRAINED_CASES)
 def test_forward_matches_reference(name):
     g = Golden(name)
     res = orc.render_rays(g.params, g.cfg, g.rays, g.ts, orc.Draws(g.draws))
