@@ -14,7 +14,7 @@ import torch
 from . import dist as sdist
 from . import metrics
 from .models import load_model
-from .rendering import render_rays
+from .rendering import render_loss_backward, render_rays
 
 
 class NeRFSystem:

@@ -121,7 +121,7 @@ def test_training_gradients_tc_vs_fp32_fullsize():
         grads[prec] = torch.cat([p.grad.reshape(-1) for p in ms["coarse"].parameters()] + [ms["t"].weight.grad.reshape(-1)]).clone()
     cos = torch.nn.functional.cosine_similarity(grads["fp32"], grads["tc"], dim=0)
     assert cos > 0.999, float(cos)
-    assert rel_err(grads["tc"], grads["fp32"]) < 2e-2
+    assert rel_err(grads["tc"], grads["fp32"]) < 5e-3
 
 
 def test_config5_dsm_batch_65536_rays():

@@ -79,27 +79,27 @@ def test_depth_mode_skips_beta_head_bit_identically(precision):
 
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
 def test_early_termination_tail_is_bounded(precision):
-    """Sharp density (sigma head x64): most rays are absorbed within the first 32 samples; with t_min = 1e-3 the samples after
-    the block where T fell below t_min get weight 0 -- compared with the oracle the dropped weight is < 1e-3 per ray and
-    depth / rgb move by < 1e-3 (+ the path's own tolerance)."""
+    """Dense medium (sigma head x64, bias 30): most rays are absorbed within the first 32 samples; with t_min = 1e-2 the samples
+    after the block where T fell below t_min get weight 0 -- compared with the oracle the dropped weight is < t_min per ray and
+    depth / rgb move by < t_min (+ the path's own tolerance)."""
     import satnerf_b200 as sb
     args = make_args(fc_units=128, precision=precision)
     ms, params, rays, ts, draws = _setup(args, 400, 80)
     with torch.no_grad():
         ms["coarse"].sigma_from_xyz[0].weight.mul_(64.0)
-        ms["coarse"].sigma_from_xyz[0].bias.fill_(3.0)
+        ms["coarse"].sigma_from_xyz[0].bias.fill_(30.0)
     params["coarse"]["sigma_from_xyz.0.weight"] = ms["coarse"].sigma_from_xyz[0].weight.detach().cpu().clone()
     params["coarse"]["sigma_from_xyz.0.bias"] = ms["coarse"].sigma_from_xyz[0].bias.detach().cpu().clone()
     want = orc.render_rays(params, args, rays, ts, orc.Draws(draws))
-    args.t_min = 1e-3
+    args.t_min = 1e-2
     with torch.no_grad():
         got = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
     w, wr = got["weights_coarse"].cpu(), want["weights_coarse"]
     cut = (w[:, 32:] == 0).all(-1)
     assert cut.float().mean() > 0.3, float(cut.float().mean())            # the regime does terminate early
     dropped = (wr - w).clamp_min(0).sum(-1)
-    assert float(dropped.max()) < 1e-3 + 1e-4
-    tol = 2e-3 if precision == "fp32" else 2e-2
+    assert float(dropped.max()) < 1e-2 + 1e-4
+    tol = 1.2e-2 if precision == "fp32" else 3e-2
     assert rel_err(got["depth_coarse"].cpu(), want["depth_coarse"]) < tol and rel_err(got["rgb_coarse"].cpu(), want["rgb_coarse"]) < tol
 
 

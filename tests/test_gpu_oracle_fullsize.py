@@ -84,10 +84,14 @@ def test_config2_tc_vs_oracle():
 
 
 def test_config3_coarse_fine_tc_vs_oracle():
-    """configs[2]: sat-nerf 64 coarse + 32 importance samples (96 fine), 8192 rays.  The coarse level is compared strictly.
-    The fine depths are importance-sampled from the coarse weights (rendering.py:121-125): a 1e-4 difference in one weight
-    can move a sample to the neighbouring bin, so the fine level is compared (a) strictly on the rays whose merged depths
-    agree to 1e-6 and (b) on every ray at 5e-3; the fraction of rays with equal depths is reported and must exceed 90 %."""
+    """configs[2]: sat-nerf 64 coarse + 32 importance samples (96 fine), 8192 rays.
+      (1) coarse level: strict (elementwise 1e-3).
+      (2) fine level DECOUPLED from the coarse one: the fine field evaluated through `inference()` at the ORACLE's merged depths
+          (S = 96): strict.
+      (3) end to end: the fine depths are importance-sampled from the path's own coarse weights (rendering.py:121-125), 1e-4 away
+          from the reference's, which shifts samples inside their bins (and, rarely, across a bin edge): per-ray fine outputs
+          (rgb, depth) stay strict on ALL rays; per-sample fine outputs are compared on the rays whose 96 depths agree to 1e-4
+          (reported, must be > 90 %) at 2e-3."""
     import satnerf_b200 as sb
     R = 8192
     args = make_args(n_importance=32, precision="tc")
@@ -99,27 +103,32 @@ def test_config3_coarse_fine_tc_vs_oracle():
         got = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
     assert set(got) == set(want) and got["weights_fine"].shape == (R, 96)
     _compare("config3_coarse", got, want, keys=[k for k in want if k.endswith("_coarse")])
-    # merged fine depths: recover them from the transparency-independent identity depth = sum w z is not possible, so
-    # rebuild them with the library's sampler from ITS coarse weights and the oracle's from its own
-    from satnerf_b200 import capi
-    z = capi.stratified_depths(rays.cuda(), torch.linspace(0, 1, 64).cuda(), draws[0].cuda())
-    zf_dev = capi.importance_depths(z, got["weights_coarse"].contiguous(), draws[2].cuda().contiguous()).cpu()
+    # (2) the oracle's merged depths
     zc = orc.stratified_depths(rays[:, 6:7], rays[:, 7:8], 64, draws[0])
     mid = 0.5 * (zc[:, :-1] + zc[:, 1:])
     zf_ref = torch.sort(torch.cat([zc, orc.importance_depths(mid, want["weights_coarse"][:, 1:-1], draws[2])], -1), -1)[0]
-    same = ((zf_dev - zf_ref).abs().max(-1).values <= 1e-6)
+    xyz = rays[:, None, 0:3] + rays[:, None, 3:6] * zf_ref[:, :, None]
+    with torch.no_grad():
+        dec = sb.inference(ms["fine"], args, xyz.cuda().contiguous(), zf_ref.cuda().contiguous(), sun_d=rays[:, 8:11].cuda().contiguous(),
+                           rays_t=ms["t"](ts.cuda()))
+    _compare("config3_fine_decoupled", {f"{k}_fine": v for k, v in dec.items()}, want, keys=[k for k in want if k.endswith("_fine")])
+    # (3) end to end
+    from satnerf_b200 import capi
+    z = capi.stratified_depths(rays.cuda(), torch.linspace(0, 1, 64).cuda(), draws[0].cuda())
+    zf_dev = capi.importance_depths(z, got["weights_coarse"].contiguous(), draws[2].cuda().contiguous()).cpu()
+    same = ((zf_dev - zf_ref).abs().max(-1).values <= 1e-4)
     frac = float(same.float().mean())
     fine = [k for k in want if k.endswith("_fine")]
-    rows = {"rays_with_equal_fine_depths": frac}
+    rows = {"rays_with_equal_fine_depths": frac, "max_fine_depth_diff": float((zf_dev - zf_ref).abs().max())}
     for k in fine:
         a, b = got[k].cpu(), want[k]
-        rows[k] = {"elementwise_excess_equal_depth_rays": elementwise_excess(a[same], b[same], k), "max_rel_all_rays": rel_err(a, b)}
-    _report("config3_fine", rows)
+        rows[k] = {"elementwise_excess_equal_depth_rays_rtol_2e-3": elementwise_excess(a[same], b[same], k, rtol=2e-3), "max_rel_all_rays": rel_err(a, b)}
+    _report("config3_fine_end_to_end", rows)
     assert frac > 0.9, frac
     for k in fine:
-        assert rows[k]["elementwise_excess_equal_depth_rays"] <= 1.0, (k, rows[k])
+        assert rows[k]["elementwise_excess_equal_depth_rays_rtol_2e-3"] <= 1.0, (k, rows[k])
     for k in ("rgb_fine", "depth_fine"):
-        assert rows[k]["max_rel_all_rays"] < 5e-3, (k, rows[k])
+        assert elementwise_excess(got[k].cpu(), want[k], k) <= 1.0, (k, rows[k])
 
 
 def test_config4_snerf_sc_tc_vs_oracle():

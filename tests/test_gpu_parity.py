@@ -17,7 +17,14 @@ from oracle import render_oracle as orc
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": 2e-5, "tc": 1e-3}
-GRAD_TOL = {"fp32": 2e-4, "tc": 2e-2}
+GRAD_TOL = {"fp32": 2e-4, "tc": 5e-3}      # tc: measured <= 1.8e-3 of each tensor's max |grad| against the float64 oracle (gpurun_out/parity_report.json)
+
+
+def _grad_tol(precision, key):
+    """Gradient tolerance of one parameter tensor.  The fine level of the tensor-core path is evaluated at depths importance-
+    sampled from ITS OWN coarse weights (1e-4 away from the reference's): its gradients are those of a slightly different
+    sample set, measured at <= 1e-2 -- bound 2e-2; everything else GRAD_TOL."""
+    return 2e-2 if (precision == "tc" and key.startswith("fine.")) else GRAD_TOL[precision]
 
 
 def _tc_cases():
@@ -90,7 +97,7 @@ def test_gradients_match_golden(name, precision):
         assert got is not None, key
         ref_noise = rel_err(ref, exact[key], floor=1e-12)
         err = rel_err(got.cpu(), exact[key], floor=1e-12)
-        assert err < max(GRAD_TOL[precision], 3 * ref_noise), (key, err, ref_noise)
+        assert err < max(_grad_tol(precision, key), 3 * ref_noise), (key, err, ref_noise)
         checked += 1
     assert checked > 10
 
@@ -201,8 +208,8 @@ def test_field_forward_matches_oracle():
 @pytest.mark.parametrize("model,h,n_rays,S", [("sat-nerf", 128, 50, 64), ("sat-nerf", 256, 33, 96), ("s-nerf", 128, 20, 64), ("sat-nerf", 384, 17, 48)])
 def test_tc_backward_matches_fp64_oracle(model, h, n_rays, S):
     """Tensor-core backward (fused input-gradient chain + split-K weight-gradient GEMMs, fp16 gradients with a loss scale)
-    against float64 autograd of the oracle.  Tolerance 2e-2 of each tensor's max |grad| (north_star gives no gradient
-    tolerance; forward tolerance is 1e-3 and the backward passes through ~10 fp16 GEMMs)."""
+    against float64 autograd of the oracle.  Tolerance GRAD_TOL['tc'] = 5e-3 of each tensor's max |grad| (north_star gives no
+    gradient tolerance; the forward tolerance is 1e-3 and the backward passes through ~10 more fp16 GEMMs; measured <= 1.8e-3)."""
     import satnerf_b200 as sb
     args = make_args(model=model, fc_units=h, n_samples=S, precision="tc", sc_lambda=0.0)
     torch.manual_seed(31)
