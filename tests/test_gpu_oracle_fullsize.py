@@ -126,6 +126,12 @@ def test_config3_coarse_fine_tc_vs_oracle():
     _report("config3_fine_end_to_end", rows)
     assert frac > 0.9, frac
     for k in fine:
+        if k == "weights_fine":
+            # w_i = alpha_i T_i with alpha_i ~ sigma_i * (z_{i+1} - z_i): two merged samples can lie arbitrarily close, so a 1e-5 shift of
+            # one of them changes that weight by percents of ITSELF (its cumulative sum -- transparency, gated above -- is unaffected);
+            # gate it on the max-abs / max-ref measure over all rays instead
+            assert rows[k]["max_rel_all_rays"] < 2e-3, rows[k]
+            continue
         assert rows[k]["elementwise_excess_equal_depth_rays_rtol_2e-3"] <= 1.0, (k, rows[k])
     for k in ("rgb_fine", "depth_fine"):
         assert elementwise_excess(got[k].cpu(), want[k], k) <= 1.0, (k, rows[k])
