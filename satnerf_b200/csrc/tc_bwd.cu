@@ -13,6 +13,7 @@
 // Gradients travel in fp16 with one global power-of-two loss scale (taken from max |d_head|) and are accumulated in fp32.
 // Everything is deterministic: no float atomics, fixed reduction orders.
 #include "tc_common.cuh"
+#include "tc_pipeline.cuh"
 #include "tc_backward.cuh"
 #include "tc_field.cuh"
 #include "composite.cuh"
@@ -35,6 +36,8 @@ struct TcBwdArgs {
     const float* absmax;                          // device scalar: max |d_head|
     float* d_t;                                   // (P, tau) fp32, unscaled; or null
     unsigned char* packed;
+    const float *rays, *z, *xyz;                  // sample positions (layer 0's pre-activation is recomputed from them)
+    int ray_cols, dir_col;
     int n_layers, R, S, G, n_groups, tiles_per_group;
 };
 
@@ -68,7 +71,7 @@ __global__ void tc_bwd_pack_kernel(TcProgram P, const float* __restrict__ W, uns
     }
 }
 
-struct BwdMisc { long long s3_w, r2_w, b2_w, b0_w, sigma_w; int b0_ld, H, H2, tau, has_beta; int t_seed, t_r2, t_beta, t_betav, t_sigma; };
+struct BwdMisc { long long s3_w, r2_w, b2_w, b0_w, sigma_w, l0_w, l0_b; int b0_ld, H, H2, tau, has_beta; int t_seed, t_r2, t_beta, t_betav, t_sigma, t_l0; };
 
 __global__ void tc_bwd_tables_kernel(BwdMisc M, long long tables_base, const float* __restrict__ W, unsigned char* __restrict__ packed) {
     float* T = reinterpret_cast<float*>(packed + tables_base);
@@ -84,7 +87,11 @@ __global__ void tc_bwd_tables_kernel(BwdMisc M, long long tables_base, const flo
             T[M.t_betav + n] = M.tau > 3 ? W[M.b0_w + (long long)n * M.b0_ld + M.H + 3] : 0.f;
         }
     }
-    for (int n = tid; n < M.H; n += nthr) T[M.t_sigma + n] = W[M.sigma_w + n];
+    for (int n = tid; n < M.H; n += nthr) {
+        T[M.t_sigma + n] = W[M.sigma_w + n];
+        float* t = T + M.t_l0 + n * 4;                                         // trunk layer 0: [wx wy wz b] (its pre-activation is recomputed)
+        t[0] = W[M.l0_w + n * 3]; t[1] = W[M.l0_w + n * 3 + 1]; t[2] = W[M.l0_w + n * 3 + 2]; t[3] = W[M.l0_b + n];
+    }
 }
 
 __global__ void absmax_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
@@ -105,85 +112,68 @@ __device__ __forceinline__ YBuf yb_load(const unsigned char* arr, int gt, int F,
     for (int c = 0; c < 4; ++c) b.q[c] = __ldg(reinterpret_cast<const uint4*>(s + (size_t)c * kTile * 16));
     return b;
 }
-// v[i] *= mul * cos(2 pi r_i)
-__device__ __forceinline__ void mul_cos32(float* v, const YBuf& b, float mul) {
-    const __half2* h = reinterpret_cast<const __half2*>(&b);
+__device__ __forceinline__ YBuf yb_zero() { YBuf b; for (int c = 0; c < 4; ++c) b.q[c] = make_uint4(0u, 0u, 0u, 0u); return b; }
+// v[i] *= mul * cos(y_i), i < 16: y = columns [16 * hf, 16 * hf + 16) of a 32-column y block
+__device__ __forceinline__ void mul_cos16(float* v, const YBuf& b, int hf, float mul) {
+    const __half2* h = reinterpret_cast<const __half2*>(&b.q[2 * hf]);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float2 r = __half22float2(h[i]);
-        v[2 * i] *= mul * __cosf(6.283185307179586f * r.x);
-        v[2 * i + 1] *= mul * __cosf(6.283185307179586f * r.y);
+    for (int i = 0; i < 8; ++i) {
+        const float2 y = __half22float2(h[i]);
+        v[2 * i] *= mul * __cosf(y.x);
+        v[2 * i + 1] *= mul * __cosf(y.y);
     }
 }
+__device__ __forceinline__ void mul_cos32(float* v, const YBuf& b, float mul) { mul_cos16(v, b, 0, mul); mul_cos16(v + 16, b, 1, mul); }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_constant__ TcBwdArgs A) {
+// The chain kernel follows the forward's tile pipeline (tc_pipeline.cuh): CTA pairs (CG = 2) or single CTAs, 4-deep half-stage
+// weight ring, two N-chunks per GEMM with the epilogue of chunk 0 under the MMAs of chunk 1, direct stores into released
+// K-slabs, early start of the next GEMM on the K-slabs chunk 0 has rewritten.
+//
+// Per 128-point tile (sat-nerf; s-nerf drops the beta steps), A = the fp16 dY tile in shared memory, D = TMEM accumulator:
+//   seed   A[:, :H2]   = g_sun w_s3 cos(s3y)                                                    -> dump d s3y
+//   S2     D = A W_s2 ;  A[:, :H2] = D cos(s2y)                                                 -> dump d s2y
+//   S1     D = A W_s1 ;  A[:, :H2] = D cos(s1y),  A[:, H2:] = (g_rgb . W_r2) cos(r1y)           -> dump d s1y, d r1y
+//   FA     D = A [W_s0[:, :H]; W_r0]          (d feat, stays in TMEM when a beta head follows)
+//          beta: A[:, :H2] = g_beta w_b2 cos(b1y)  (+ d t_emb dot products)                     -> dump d b1y
+//   FB     D += A W_b0[:, :H] ;  A = D                                                          -> dump d feat
+//   A7     D = A W_feats ;  A = (D + g_sigma w_sigma) cos(y_7)                                  -> dump d y_7
+//   TRUNK  l = L-1 .. 1:  D = A W_l[:, skip:] ;  A = D w0_{l-1} cos(y_{l-1})                    -> dump d y_{l-1}
+// (y_0 = 30 (W_0 x + b_0) is recomputed from the sample position; every other y comes from the forward's fp16 stash.)
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcBwdArgs A) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcProgram& P = A.prog;
-    Smem sm = carve(base, P, 1);
+    Smem sm = carve(base, P, CG);
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int stage_bytes = P.stage_bytes / CG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* T = reinterpret_cast<const float*>(A.packed + P.tables_base);
-    const int stage_bytes = P.stage_bytes;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
-        mbar_init(sm.acc_full, 1); mbar_init(sm.a_ready, 1);
+        for (int i = 0; i < P.n_stages; ++i) { mbar_init(&sm.full[i], (CG == 2 && cta_rank == 0) ? 2 : 1); mbar_init(&sm.empty[i], 1); }
+        mbar_init(sm.acc_full, 1); mbar_init(sm.acc_full2, 1); mbar_init(sm.a_ready, CG); mbar_init(sm.a_ready2, CG);
+        for (int i = 0; i < 4; ++i) mbar_init(&sm.slab_free[i], 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(sm.tmem_ptr, 512);
+    if (CG == 2) { __syncthreads(); cluster_sync_all(); }
+    if (warp == 1) { if (CG == 2) tmem_alloc_2cta(sm.tmem_ptr, 512); else tmem_alloc(sm.tmem_ptr, 512); }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_ptr;
-    const int n_work = A.n_groups, tpg = A.tiles_per_group;
+    const int tpg = A.tiles_per_group;
+    const int n_work = CG == 2 ? (A.n_groups + 1) / 2 : A.n_groups;
 
     if (warp == 0) {
-        int st = 0; uint32_t ph = 0;
-        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x)
-            for (int t = 0; t < tpg; ++t) {
-                const unsigned char* src = A.packed;
-                for (int gi = 0; gi < P.n_gemms; ++gi) {
-                    const uint32_t bytes = (uint32_t)P.g[gi].chunk_n * 128u;
-                    const int n = P.g[gi].n_chunks * P.g[gi].k_slabs;
-                    for (int i = 0; i < n; ++i) {
-                        if (lane == 0) {
-                            mbar_wait(&sm.empty[st], ph ^ 1, 21);
-                            mbar_arrive_expect_tx(&sm.full[st], bytes);
-                            bulk_g2s(sm.b + (size_t)st * stage_bytes, src, bytes, &sm.full[st]);
-                        }
-                        __syncwarp();
-                        src += bytes;
-                        if (++st == P.n_stages) { st = 0; ph ^= 1; }
-                    }
-                }
-            }
+        pipe_producer<CG>(P, sm, A.packed, stage_bytes, unit, n_units, n_work, tpg, cta_rank, lane);
     } else if (warp == 1) {
-        int st = 0; uint32_t ph = 0, ready_ph = 0;
-        const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
-        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x)
-            for (int t = 0; t < tpg; ++t)
-                for (int gi = 0; gi < P.n_gemms; ++gi) {
-                    const TcGemm& g = P.g[gi];
-                    mbar_wait(sm.a_ready, ready_ph, 22); ready_ph ^= 1;
-                    tc_fence_after();
-                    const uint32_t idesc = umma_idesc_f16((uint32_t)g.chunk_n);
-                    for (int j = 0; j < g.n_chunks; ++j)
-                        for (int s = 0; s < g.k_slabs; ++s) {
-                            mbar_wait(&sm.full[st], ph, 23);
-                            tc_fence_after();
-                            if (lane == 0) {
-                                int ksteps = g.K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) / 16;
-                                const uint32_t a_addr = a_base + (uint32_t)s * kSlabBytes, b_addr = b_base + (uint32_t)st * stage_bytes;
-                                for (int k = 0; k < ksteps; ++k)      // g.skip = 1: accumulate onto what the previous GEMM left in TMEM
-                                    umma_f16_ss(tmem + (uint32_t)(j * g.chunk_n), umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32),
-                                                idesc, ((s | k) != 0 || g.skip) ? 1u : 0u);
-                                umma_commit(&sm.empty[st]);
-                                if (j == g.n_chunks - 1 && s == g.k_slabs - 1) umma_commit(sm.acc_full);
-                            }
-                            __syncwarp();
-                            if (++st == P.n_stages) { st = 0; ph ^= 1; }
-                        }
-                }
+        const uint32_t tm = __shfl_sync(0xffffffffu, *sm.tmem_ptr, 0);
+        if (CG == 2 && cta_rank == 1) pipe_relay(P, sm, unit, n_units, n_work, tpg, lane);
+        else pipe_issuer<CG>(P, sm, stage_bytes, unit, n_units, n_work, tpg, tm);
     } else {
         const int tid_e = threadIdx.x - 64;
         const int quad = warp & 3, half = (warp - 2) >> 2;
@@ -193,23 +183,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
         const uint32_t tF = smem_u32(sm.tblF), tV = smem_u32(sm.tblV);
         const int H = P.H, H2 = P.H2, S = A.S, fgsH = H >> 6, fgs2 = H2 >> 6;
         const float scale = loss_scale(*A.absmax), inv_scale = 1.0f / scale;
-        uint32_t acc_ph = 0;
         float* scratch = sm.z;                                    // per-point tables of the forward are unused here: (4 x 128 x 4) floats
-        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
-            const int r0 = wk * A.G;
-            const int n_rays = min(A.G, A.R - r0);
+        const uint32_t ready_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready), 0) : 0u;
+        const uint32_t ready2_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready2), 0) : 0u;
+        auto signal_ready = [&](int which) {          // one elected arrival per CTA (see tc_field.cu)
+            if (tid_e == 0) {
+                if (CG == 2 && cta_rank != 0) mbar_arrive_cluster_relaxed(which ? ready2_bar : ready_bar);
+                else mbar_arrive(which ? sm.a_ready2 : sm.a_ready);
+            }
+        };
+        int tile_seq = 0;
+        for (int wk = unit; wk < n_work; wk += n_units) {
+            const int grp = CG == 2 ? 2 * wk + (int)cta_rank : wk;
+            const bool live = grp < A.n_groups;                   // false: this CTA only keeps the pair in lockstep
+            const int r0 = grp * A.G;
+            const int n_rays = live ? min(A.G, A.R - r0) : 0;
             const int Pg = n_rays * S;
-            for (int t = 0; t < tpg; ++t) {
-                const int gt = wk * tpg + t;
+            for (int t = 0; t < tpg; ++t, ++tile_seq) {
+                const int gt = grp * tpg + t;
                 const int p = t * kTile + row;
                 const bool valid = p < Pg;
-                float g0 = 0.f, g1 = 0.f, g2 = 0.f, gsig = 0.f, gsun = 0.f, gbeta = 0.f;
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, gsig = 0.f, gsun = 0.f, gbeta = 0.f, px = 0.f, py = 0.f, pz = 0.f;
                 if (valid) {
-                    const float* dh = A.d_head + ((size_t)r0 * S + p) * A.C;
+                    const size_t gp = (size_t)r0 * S + p;
+                    const float* dh = A.d_head + gp * A.C;
                     g0 = dh[0] * scale; g1 = dh[1] * scale; g2 = dh[2] * scale; gsig = dh[3] * scale; gsun = dh[4] * scale;
                     if (P.has_beta) gbeta = dh[8] * scale;
+                    if (A.xyz) { px = A.xyz[gp * 3]; py = A.xyz[gp * 3 + 1]; pz = A.xyz[gp * 3 + 2]; }
+                    else {
+                        const float zz = A.z[gp];
+                        const float* ray = A.rays + (size_t)(r0 + p / S) * A.ray_cols;       // same rounding as the forward (rendering.py:81)
+                        px = __fadd_rn(ray[0], __fmul_rn(ray[A.dir_col], zz));
+                        py = __fadd_rn(ray[1], __fmul_rn(ray[A.dir_col + 1], zz));
+                        pz = __fadd_rn(ray[2], __fmul_rn(ray[A.dir_col + 2], zz));
+                    }
                 }
-                if (half == 0) {                                  // head-gradient block for the tiny-N weight gradients
+                if (half == 0 && live) {                          // head-gradient block for the tiny-N weight gradients
                     unsigned char* da = A.bbase + A.bs.dhead;
                     *reinterpret_cast<uint4*>(atom_chunk(da, gt, 1, row, 0)) = make_uint4(pack_half2(g0, g1), pack_half2(g2, gsig), pack_half2(gsun, gbeta), 0u);
 #pragma unroll
@@ -218,12 +227,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
                 // ---- seed: d s3y = g_sun * w_s3 * cos(s3y)  ->  A[:, 0:H2) ----
                 table_copy(sm.tblF, T + P.l0_tbl, H2 * 4, tid_e);
                 cp_async_wait_all();
-                if (tid_e == 0) bulk_wait_read();
+                if (tid_e == 0) bulk_wait_read();                 // the previous tile's last dump has left shared memory
                 named_bar_sync(1, kEpiThreads);
                 {
                     const uint32_t tok = fresh_token(0x7fffu);
                     for (int n0 = half * 32; n0 < H2; n0 += 32 * kEpiSub) {
-                        YBuf yb = yb_load(A.fbase + A.fs.s3y, gt, H2, n0, row);
+                        const YBuf yb = live ? yb_load(A.fbase + A.fs.s3y, gt, H2, n0, row) : yb_zero();
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
@@ -236,112 +245,166 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, kEpiThreads);
-                if (tid_e == 0) {
-                    bulk_s2g(A.bbase + A.bs.ds3y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit();
-                    mbar_arrive(sm.a_ready);
-                }
+                if (tid_e == 0 && live) { bulk_s2g(A.bbase + A.bs.ds3y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit(); }
+                {   const TcGemm& gn = P.g[0];                   // tables of the first GEMM (none for S2) -- the seed table is dead
+                    (void)gn; }
+                signal_ready(0);
+                signal_ready(1);
+
                 int trunk_l = A.n_layers - 1;                     // layer whose dY the next BK_TRUNK GEMM consumes
                 for (int gi = 0; gi < P.n_gemms; ++gi) {
                     const TcGemm& g = P.g[gi];
-                    const int kind = g.kind;
-                    // epilogue tables of this GEMM (tiny) + make sure earlier stash dumps have left shared memory
+                    const int kind = g.kind, N = g.N, n_chunks = g.n_chunks, chunk_n = g.chunk_n;
+                    const bool nodrain = kind == BK_FA && P.has_beta;
+                    // epilogue tables of this GEMM + make sure earlier dumps have left shared memory
                     if (kind == BK_S1) table_copy(sm.tblF, T + g.tbl_off, H2 * 16, tid_e);
-                    else if (kind == BK_FA && P.has_beta) { table_copy(sm.tblF, T + g.tbl_off, H2 * 16, tid_e); table_copy(sm.tblV, T + g.vec_off, H2 * 4, tid_e); }
+                    else if (nodrain) { table_copy(sm.tblF, T + g.tbl_off, H2 * 16, tid_e); table_copy(sm.tblV, T + g.vec_off, H2 * 4, tid_e); }
                     else if (kind == BK_A7) table_copy(sm.tblF, T + g.tbl_off, H * 4, tid_e);
+                    else if (kind == BK_TRUNK && trunk_l - 1 == 0) table_copy(sm.tblF, T + g.tbl_off, H * 16, tid_e);
                     cp_async_wait_all();
                     if (tid_e == 0) bulk_wait_read();
                     named_bar_sync(1, kEpiThreads);
-                    // first cos block prefetched while the MMAs run
-                    const unsigned char* yarr = nullptr; int yF = H; float ymul = 1.f;
+                    const uint32_t tok = fresh_token((uint32_t)gi);
+                    // where cos() comes from
+                    const unsigned char* yarr = nullptr; int yF = H; float ymul = 1.f; bool y_l0 = false;
                     if (kind == BK_S2) { yarr = A.fbase + A.fs.s2y; yF = H2; }
                     else if (kind == BK_S1) { yarr = A.fbase + A.fs.s1y; yF = H2; }
                     else if (kind == BK_A7) yarr = A.fbase + A.fs.y[A.n_layers - 1];
-                    else if (kind == BK_TRUNK) { yarr = A.fbase + A.fs.y[trunk_l - 1]; if (trunk_l - 1 == 0) ymul = 30.f; }
-                    const int N = g.N;
-                    int n0 = half * 32;
-                    YBuf ynext;
-                    if (yarr && n0 < N) ynext = yb_load(yarr, gt, yF, n0, row);
-                    mbar_wait(sm.acc_full, acc_ph, 24); acc_ph ^= 1;
-                    tc_fence_after();
-                    const uint32_t tok = fresh_token((uint32_t)gi);
+                    else if (kind == BK_TRUNK) { if (trunk_l - 1 == 0) { y_l0 = true; ymul = 30.f; } else yarr = A.fbase + A.fs.y[trunk_l - 1]; }
+                    if (!live) yarr = nullptr;
+                    const bool stores = !nodrain;
+                    const bool next_early = gi + 1 < P.n_gemms && n_chunks > 1 && P.g[gi + 1].k_early > 0;
+                    bool early_signaled = false;
                     float dt0 = 0.f, dt1 = 0.f, dt2 = 0.f, dt3 = 0.f;
-                    if (kind == BK_FA && P.has_beta) {
-                        // D (= d feat so far) stays in TMEM; build d b1y = g_beta * w_b2 * cos(b1y) as the next A operand
-                        for (; n0 < H2; n0 += 32 * kEpiSub) {
-                            YBuf yb = yb_load(A.fbase + A.fs.b1y, gt, H2, n0, row);
-                            float v[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = gbeta * lds128(tF + (uint32_t)(n0 + i) * 16u, tok).x;
-                            mul_cos32(v, yb, 1.f);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
-                                dt0 = fmaf(w.y, v[i], dt0); dt1 = fmaf(w.z, v[i], dt1); dt2 = fmaf(w.w, v[i], dt2);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
-                                dt3 = fmaf(w.x, v[i], dt3); dt3 = fmaf(w.y, v[i + 1], dt3); dt3 = fmaf(w.z, v[i + 2], dt3); dt3 = fmaf(w.w, v[i + 3], dt3);
-                            }
-                            store_act32(a_base, row, n0, v);
+                    // first y block of chunk 0 in flight while the MMAs run
+                    YBuf ynext = yb_zero();
+                    if (yarr && half * 32 < min(chunk_n, N)) ynext = yb_load(yarr, gt, yF, half * 32, row);
+                    for (int ch = 0; ch < n_chunks; ++ch) {
+                        if (tid_e == 0) {
+                            if (ch == 0) mbar_wait(sm.acc_full, (uint32_t)(tile_seq * P.n_gemms + gi) & 1u, 24);
+                            else mbar_wait(sm.acc_full2, (uint32_t)(tile_seq * P.n_two + g.two_idx) & 1u, 24);
                         }
-                    } else {
-                        for (; n0 < N; n0 += 32 * kEpiSub) {
-                            float v[32];
-                            tmem_ld32(tm_row + (uint32_t)n0, v);
-                            tmem_ld_wait();
-                            YBuf ycur = ynext;
-                            if (yarr && n0 + 32 * kEpiSub < N) ynext = yb_load(yarr, gt, yF, n0 + 32 * kEpiSub, row);
-                            if (kind == BK_A7) {
+                        named_bar_sync(2, kEpiThreads);
+                        tc_fence_after();
+                        const bool final_chunk = ch == n_chunks - 1;
+                        if (!nodrain) {
+                            const int n_end = min((ch + 1) * chunk_n, N);
+                            int n0 = ch * chunk_n + half * 32;
+                            bool have = n0 < n_end;
+                            uint64_t* const slab_bar = (stores && !final_chunk) ? sm.slab_free : nullptr;
+                            const uint32_t slab_par = (uint32_t)(tile_seq * P.n_store2 + g.store2_idx) & 1u;
+                            uint32_t va[16], vb[16];
+                            if (ch > 0 && yarr && have) ynext = yb_load(yarr, gt, yF, n0, row);
+                            if (have) tmem_ld16(tm_row + (uint32_t)n0, va);
+                            while (have) {
+                                const YBuf ycur = ynext;
+                                const int n1 = n0 + 32 * kEpiSub;
+                                const bool more = n1 < n_end;
+                                if (yarr && more) ynext = yb_load(yarr, gt, yF, n1, row);
+                                tmem_ld_wait16(va);
+                                tmem_ld16(tm_row + (uint32_t)(n0 + 16), vb);
 #pragma unroll
-                                for (int i = 0; i < 32; i += 4) {
-                                    float4 w = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
-                                    v[i] = fmaf(gsig, w.x, v[i]); v[i + 1] = fmaf(gsig, w.y, v[i + 1]); v[i + 2] = fmaf(gsig, w.z, v[i + 2]); v[i + 3] = fmaf(gsig, w.w, v[i + 3]);
+                                for (int hf = 0; hf < 2; ++hf) {
+                                    float* v = reinterpret_cast<float*>(hf ? vb : va);
+                                    const int c0 = n0 + 16 * hf;
+                                    if (hf == 1) { tmem_ld_wait16(vb); if (more) tmem_ld16(tm_row + (uint32_t)n1, va); }
+                                    if (kind == BK_A7) {
+#pragma unroll
+                                        for (int i = 0; i < 16; i += 4) {
+                                            float4 w = lds128(tF + (uint32_t)(c0 + i) * 4u, tok);
+                                            v[i] = fmaf(gsig, w.x, v[i]); v[i + 1] = fmaf(gsig, w.y, v[i + 1]); v[i + 2] = fmaf(gsig, w.z, v[i + 2]); v[i + 3] = fmaf(gsig, w.w, v[i + 3]);
+                                        }
+                                    }
+                                    if (y_l0) {
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) {
+                                            const float4 w = lds128(tF + (uint32_t)(c0 + i) * 16u, tok);
+                                            const float y = __fmul_rn(30.0f, fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w))));     // as the forward's layer 0
+                                            v[i] *= 30.f * __cosf(y);
+                                        }
+                                    } else if (yarr) mul_cos16(v, ycur, hf, ymul);
+                                    else if (kind != BK_FA && kind != BK_FB) {
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) v[i] = 0.f;       // idle half of a pair: keep the tile finite
+                                    }
+                                    if (slab_bar) mbar_wait(slab_bar + (c0 >> 6), slab_par, 28);
+                                    store_act_cols<16>(a_base, row, c0, v);
                                 }
+                                if (kind == BK_S1) {
+                                    // d r1y = (sum_c g_c W_r2[c][m]) cos(r1y)  ->  A[:, H2 + m)
+                                    const YBuf yr = live ? yb_load(A.fbase + A.fs.r1y, gt, H2, n0, row) : yb_zero();
+                                    float u[32];
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) {
+                                        float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
+                                        u[i] = fmaf(g2, w.z, fmaf(g1, w.y, g0 * w.x));
+                                    }
+                                    mul_cos32(u, yr, 1.f);
+                                    store_act32(a_base, row, H2 + n0, u);
+                                }
+                                n0 = n1; have = more;
                             }
-                            if (yarr) mul_cos32(v, ycur, ymul);
-                            store_act32(a_base, row, n0, v);
-                            if (kind == BK_S1) {
-                                // d r1y = (sum_c g_c W_r2[c][m]) cos(r1y)  ->  A[:, H2 + m)
-                                YBuf yr = yb_load(A.fbase + A.fs.r1y, gt, H2, n0, row);
-                                float u[32];
+                        } else if (final_chunk) {
+                            // d feat (so far) stays in TMEM; build d b1y = g_beta * w_b2 * cos(b1y) as the operand of FB
+                            for (int n0 = half * 32; n0 < H2; n0 += 32 * kEpiSub) {
+                                const YBuf yb = live ? yb_load(A.fbase + A.fs.b1y, gt, H2, n0, row) : yb_zero();
+                                float v[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = gbeta * lds128(tF + (uint32_t)(n0 + i) * 16u, tok).x;
+                                mul_cos32(v, yb, 1.f);
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
-                                    u[i] = fmaf(g2, w.z, fmaf(g1, w.y, g0 * w.x));
+                                    dt0 = fmaf(w.y, v[i], dt0); dt1 = fmaf(w.z, v[i], dt1); dt2 = fmaf(w.w, v[i], dt2);
                                 }
-                                mul_cos32(u, yr, 1.f);
-                                store_act32(a_base, row, H2 + n0, u);
+#pragma unroll
+                                for (int i = 0; i < 32; i += 4) {
+                                    float4 w = lds128(tV + (uint32_t)(n0 + i) * 4u, tok);
+                                    dt3 = fmaf(w.x, v[i], dt3); dt3 = fmaf(w.y, v[i + 1], dt3); dt3 = fmaf(w.z, v[i + 2], dt3); dt3 = fmaf(w.w, v[i + 3], dt3);
+                                }
+                                store_act32(a_base, row, n0, v);
+                            }
+                        }
+                        if (!final_chunk) {
+                            tc_fence_before();
+                            if (next_early) {
+                                fence_proxy_async_smem();
+                                named_bar_sync(1, kEpiThreads);
+                                signal_ready(0);
+                                early_signaled = true;
                             }
                         }
                     }
                     tc_fence_before();
                     fence_proxy_async_smem();
-                    if (kind == BK_FA && P.has_beta && A.d_t) {
+                    if (nodrain && A.d_t) {
                         float* sc = scratch + (size_t)(half * kTile + row) * 4;
                         sc[0] = dt0; sc[1] = dt1; sc[2] = dt2; sc[3] = dt3;
                     }
-                    named_bar_sync(1, kEpiThreads);
-                    if (kind == BK_FA && P.has_beta && A.d_t && half == 0 && valid) {
+                    named_bar_sync(1, kEpiThreads);              // all TMEM reads / A writes / table reads of this GEMM done
+                    if (nodrain && A.d_t && half == 0 && valid) {
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                         for (int h2 = 0; h2 < kEpiSub; ++h2) { const float* sc = scratch + (size_t)(h2 * kTile + row) * 4; s0 += sc[0]; s1 += sc[1]; s2 += sc[2]; s3 += sc[3]; }
                         float* o = A.d_t + ((size_t)r0 * S + p) * P.tau;
                         o[0] = s0 * inv_scale; if (P.tau > 1) o[1] = s1 * inv_scale; if (P.tau > 2) o[2] = s2 * inv_scale; if (P.tau > 3) o[3] = s3 * inv_scale;
                     }
-                    if (tid_e == 0) {
-                        // dump the dY tile(s) this step produced
+                    if (tid_e == 0 && live) {
+                        // dump the dY tile(s) this step produced (A-tile image = atoms)
                         unsigned char* bb = A.bbase;
                         if (kind == BK_S2) bulk_s2g(bb + A.bs.ds2y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
                         else if (kind == BK_S1) {
                             bulk_s2g(bb + A.bs.ds1y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
                             bulk_s2g(bb + A.bs.dr1y + (size_t)gt * fgs2 * kSlabBytes, sm.a + (size_t)fgs2 * kSlabBytes, (uint32_t)fgs2 * kSlabBytes);
-                        } else if (kind == BK_FA && P.has_beta) bulk_s2g(bb + A.bs.db1y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
+                        } else if (nodrain) bulk_s2g(bb + A.bs.db1y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
                         else if (kind == BK_FB || kind == BK_FA) bulk_s2g(bb + A.bs.df + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
                         else if (kind == BK_A7) bulk_s2g(bb + A.bs.dy[A.n_layers - 1] + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
                         else bulk_s2g(bb + A.bs.dy[trunk_l - 1] + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
                         bulk_commit();
-                        if (gi + 1 < P.n_gemms) mbar_arrive(sm.a_ready);
+                    }
+                    if (gi + 1 < P.n_gemms) {
+                        if (!early_signaled) signal_ready(0);
+                        signal_ready(1);
                     }
                     if (kind == BK_TRUNK) --trunk_l;
                 }
@@ -351,7 +414,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (CG == 2) cluster_sync_all();          // the leader's MMAs read the peer's shared memory: leave together
+    if (warp == 1) { if (CG == 2) tmem_dealloc_2cta(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -502,12 +566,18 @@ static int build_bwd_program(const FieldLayout& L, TcProgram* P, BwdMisc* M) {
     { TcGemm& g = add(BK_S1, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; g.tbl_off = tbl; M->t_r2 = tbl; tbl += 4 * H2; }
     { TcGemm& g = add(BK_FA, H, H); g.src0 = L.sun[0].w; g.ld0 = L.sun[0].n_in; g.rows0 = H2; g.src1 = L.rgb0.w; g.ld1 = L.rgb0.n_in;
       g.tbl_off = tbl; M->t_beta = tbl; tbl += 4 * H2; g.vec_off = tbl; M->t_betav = tbl; tbl += H2; }
-    if (P->has_beta) { TcGemm& g = add(BK_FB, H, H2); g.src0 = L.beta0.w; g.ld0 = L.beta0.n_in; g.rows0 = H2; g.skip = 1; }
+    if (P->has_beta) { TcGemm& g = add(BK_FB, H, H2); g.src0 = L.beta0.w; g.ld0 = L.beta0.n_in; g.rows0 = H2; g.accumulate = 1; }
     { TcGemm& g = add(BK_A7, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; g.tbl_off = tbl; M->t_sigma = tbl; tbl += H; }
     for (int l = L.n_layers - 1; l >= 1; --l) {
         TcGemm& g = add(BK_TRUNK, H, H); g.src0 = L.trunk[l].w; g.ld0 = L.trunk[l].n_in; g.col0 = l == L.skip ? L.in_xyz : 0; g.rows0 = H;
+        if (l == 1) { g.tbl_off = tbl; M->t_l0 = tbl; tbl += 4 * H; }          // [wx wy wz b] of trunk layer 0: its pre-activation is recomputed
     }
     P->n_gemms = ng;
+    // pipeline fields (tc_pipeline.cuh): every GEMM rewrites the tile from its accumulator except FA when a beta head follows
+    // (d feat stays in TMEM and FB adds onto it); the seed publishes the whole first input tile at once (no early start of S2)
+    const bool has_beta = P->has_beta != 0;
+    pipe_finish_program(P, [has_beta](const TcGemm& g) { return !(g.kind == BK_FA && has_beta); }, 0);
+    if (dev_knobs().no_early) for (int i = 0; i < ng; ++i) P->g[i].k_early = 0;
     long long wbytes = 0; int max_stage = 0;
     for (int i = 0; i < ng; ++i) {
         wbytes += (long long)P->g[i].n_chunks * P->g[i].k_slabs * P->g[i].chunk_n * 128;
@@ -515,6 +585,7 @@ static int build_bwd_program(const FieldLayout& L, TcProgram* P, BwdMisc* M) {
     }
     P->stage_bytes = max_stage; P->tables_base = (wbytes + 255) & ~255LL;
     M->s3_w = L.sun[3].w; M->r2_w = L.rgb2.w; M->b2_w = L.beta2.w; M->b0_w = L.beta0.w; M->b0_ld = L.beta0.n_in; M->sigma_w = L.sigma.w;
+    M->l0_w = L.trunk[0].w; M->l0_b = L.trunk[0].b;
     M->H = H; M->H2 = H2; M->tau = L.t_dims; M->has_beta = P->has_beta;
     return tbl;
 }
@@ -526,7 +597,7 @@ static void fwd_stash_layout(const FieldLayout& L, int n_tiles, int tpg, TcStash
     const long long yH = (long long)kTile * H * 2, yH2 = (long long)kTile * H2 * 2;
     long long off = 0;
     auto take = [&](long long per_tile) { long long o = off; off += per_tile * n_tiles; off = (off + 1023) & ~1023LL; return o; };
-    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(yH); }
+    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(l == 0 ? 0 : yH); }
     S->feat = take(tH);
     S->r1 = take(tH2); S->s1 = take(tH2); S->s2 = take(tH2); S->s3 = take(tH2); S->b1 = take(tH2);
     S->r1y = take(yH2); S->s1y = take(yH2); S->s2y = take(yH2); S->s3y = take(yH2); S->b1y = take(yH2);
@@ -628,18 +699,36 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     SNB_CHECK_LAUNCH();
     tc_bwd_tables_kernel<<<4, 256, 0, st>>>(M, P.tables_base, io->params, A.packed);
     SNB_CHECK_LAUNCH();
+    // CTA pairs as in the forward (each CTA streams and buffers half of every transposed weight tile: 4 x 16 KB ring)
+    int cg = B.groups >= 2 ? 2 : 1;
+    if (p->flags & SNB_PASS_SINGLE_CTA) cg = 1;
+    if (dev_knobs().cg == 1 || dev_knobs().cg == 2) cg = dev_knobs().cg;
     size_t fixed = (size_t)P.a_slabs * kSlabBytes + (kTblF + kTblV + 8 * kMaxGroupPts * 4 + 2 * kMaxGroupRays * 256 * 4 + 768) + 1024;
-    int ns = (int)(((size_t)max_smem - fixed) / P.stage_bytes); if (ns > 8) ns = 8;
+    int ns = (int)(((size_t)max_smem - fixed) / (P.stage_bytes / cg)); if (ns > 8) ns = 8;
     if (ns < 2) SNB_FAIL(-6, "tensor-core backward: not enough shared memory for the weight ring");
     P.n_stages = ns;
-    size_t smem = fixed + (size_t)ns * P.stage_bytes;
+    size_t smem = fixed + (size_t)ns * (P.stage_bytes / cg);
     fwd_stash_layout(L, B.n_tiles, B.tpg, &A.fs); A.fbase = (const unsigned char*)io->stash;
     A.bs = B.bs; A.bbase = ws + B.off_bstash;
     A.d_head = d_head; A.C = C; A.absmax = absmax; A.d_t = (L.t_dims && g->g_t_emb) ? d_t : nullptr;
+    A.rays = io->rays; A.z = io->z_vals; A.xyz = io->xyz; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
     A.n_layers = L.n_layers; A.R = R; A.S = S; A.G = B.G; A.n_groups = B.groups; A.tiles_per_group = B.tpg;
-    SNB_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_bwd_kernel<<<B.groups < sm_count ? B.groups : sm_count, kThreads, smem, st>>>(A);
-    SNB_CHECK_LAUNCH();
+    if (cg == 2) {
+        SNB_CUDA(cudaFuncSetAttribute(tc_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int n_pairs = (B.groups + 1) / 2, max_pairs = sm_count / 2;
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SNB_CUDA(cudaLaunchKernelEx(&cfg, tc_chain_kernel<2>, A));
+        ++g_launches;
+    } else {
+        SNB_CUDA(cudaFuncSetAttribute(tc_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_chain_kernel<1><<<B.groups < sm_count ? B.groups : sm_count, kThreads, smem, st>>>(A);
+        SNB_CHECK_LAUNCH();
+    }
 
     // 3. weight-gradient GEMMs: work list
     std::vector<DwItem> items; std::vector<DwOut> outs;

@@ -28,7 +28,8 @@ struct TcGemm {
     int aux;                         // 1: bias (2: + the skip layer's xyz term) comes from one extra K-step on the aux operand tiles
     int two_idx;                     // number of two-chunk GEMMs before this one in the program
     int k_early;                     // K-slabs of the input tile that are valid (and chunk-0 accumulator columns free) at the FIRST
-                                     // ready signal; the rest needs the second one (forward kernel only)
+                                     // ready signal; the rest needs the second one
+    int accumulate;                  // 1: the MMAs add onto what the previous GEMM left in the accumulator (backward chain)
     int tbl_off, vec_off;            // float offsets into the packed table area
     // weight sources (flat fp32 params): rows [0,rows0) from src0, the rest from src1
     long long src0, src1; int ld0, ld1, col0, col1, rows0;
@@ -45,7 +46,7 @@ struct TcProgram {
 // Activation stash written by the training-mode forward (byte offsets from the stash base; every array is indexed
 // by the global tile id gt = group * tiles_per_group + tile).
 //   atoms : [gt][fg = f/64][pg][8 points][64 features] fp16, 128B-swizzled (see tc_backward.cu) — A-tile images
-//   yb    : [gt][f/32][128 rows][32] fp16 pre-activations as revolutions frac(y / 2pi) (cos() argument of the backward)
+//   yb    : [gt][f/8][128 rows][8] fp16 pre-activations y (cos() argument of the backward); layer 0 is recomputed, not stashed
 struct TcStash {
     long long a[kMaxTrunk];                 // a_l = sin(.) outputs of trunk layer l (atoms, H wide)
     long long feat, r1, s1, s2, s3, b1;     // feats_from_xyz output; first-layer activations of the rgb / sun / beta heads
@@ -152,12 +153,9 @@ __device__ __forceinline__ void store_act_cols(uint32_t a_base, int row, int k0,
     }
 }
 // ---- training stash helpers -------------------------------------------------------------------------------
-// pre-activations are stashed as fp16 revolutions r = frac(y / 2pi) in [-0.5, 0.5]: cos(2 pi r) = cos(y) with a uniform
-// absolute error (fp16 ulp 2.4e-4 rev = 1.5e-3 rad) whatever |y| is (first layer: y = 30 (W0 x + b0) reaches +-50 rad)
-__device__ __forceinline__ float to_rev(float y) {
-    float r = __fmul_rn(y, 0.15915494309189535f);
-    return __fsub_rn(r, __fsub_rn(__fadd_rn(r, 12582912.0f), 12582912.0f));       // r - rint(r)
-}
+// Pre-activations of the sine layers are stashed as plain fp16 (one pack per pair of elements: the training forward's epilogue is
+// bound by instruction issue).  |y| < 8 for SIREN layers with w0 = 1 (fp16 ulp <= 3.9e-3 rad, <= 2e-3 rad rounding error on
+// cos'); the first layer (w0 = 30, |y| up to ~50 rad) is NOT stashed: the backward recomputes 30 (W0 x + b0) exactly from x.
 // yb arrays: [tile gt][8-column block n/8][row 0..127][8 fp16] -- the 32 lanes of a warp (consecutive rows) write / read 512
 // contiguous bytes per 16-byte access (the round-1 layout [n/32][row][32] made every access a 64-byte-strided scatter and
 // the training forward 3x slower than inference).
@@ -165,8 +163,7 @@ __device__ __forceinline__ unsigned char* yb_chunk(unsigned char* arr, int gt, i
     return arr + (((size_t)gt * (F >> 3) + (n >> 3)) * kTile + row) * 16;
 }
 __device__ __forceinline__ uint4 yb_pack8(const float* x) {
-    return make_uint4(pack_half2(to_rev(x[0]), to_rev(x[1])), pack_half2(to_rev(x[2]), to_rev(x[3])),
-                      pack_half2(to_rev(x[4]), to_rev(x[5])), pack_half2(to_rev(x[6]), to_rev(x[7])));
+    return make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
 }
 // NC (multiple of 8) consecutive pre-activations of one row starting at column n0
 template <int NC>

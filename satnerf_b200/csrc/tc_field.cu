@@ -125,7 +125,7 @@ static void stash_layout(const FieldLayout& L, int n_tiles, int tiles_per_group,
     const long long yH = (long long)kTile * H * 2, yH2 = (long long)kTile * H2 * 2;                           // yb bytes per tile
     long long off = 0;
     auto take = [&](long long per_tile) { long long o = off; off += per_tile * n_tiles; off = (off + 1023) & ~1023LL; return o; };
-    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(yH); }
+    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(l == 0 ? 0 : yH); }      // (layer 0's pre-activation is recomputed by the backward)
     S->feat = take(tH);
     S->r1 = take(tH2); S->s1 = take(tH2); S->s2 = take(tH2); S->s3 = take(tH2); S->b1 = take(tH2);
     S->r1y = take(yH2); S->s1y = take(yH2); S->s2y = take(yH2); S->s3y = take(yH2); S->b1y = take(yH2);
@@ -673,7 +673,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 float y = fmaf(w[i].z, rz[k], fmaf(w[i].y, ry[k], fmaf(w[i].x, rx[k], w[i].w)));
                                 v[i] = __fmul_rn(30.0f, y);
                             }
-                            if (sb) yb_store_cols<8>(sb + A.stash.y[0], gt, H, n0, r, v);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = __sinf(v[i]);
                             sts128(a_chunk_addr(a_base, r, n0), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
