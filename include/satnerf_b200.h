@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 3
+#define SNB_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SNB_API __attribute__((visibility("default")))
@@ -200,6 +200,14 @@ SNB_API int snb_field_workspace(const snb_field_desc* f, int n_points, size_t* b
 SNB_API int snb_field_forward(const snb_field_desc* f, const float* params, const float* xyz,
                       const float* aux_dir, const float* t_emb, float* out, int n_points,
                       int sigma_only, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Optimiser step of the training loop on a flat parameter buffer (main.py:81-94 builds torch.optim.Adam(lr, weight_decay=0)
+ * through train_utils.py:24-53; Lightning calls its step after every training_step): torch.optim.Adam arithmetic (amsgrad
+ * off, L2 weight decay folded into the gradient; hyper-parameters as doubles like torch's Python scalars), `step` = 1-based
+ * count of this update.  All buffers n floats, 16-byte
+ * aligned; updates params / exp_avg / exp_avg_sq in place.                                                          */
+SNB_API int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                  double lr, double beta1, double beta2, double eps, double weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ SNB_API int snb_debug_read(void* host_dst, size_t bytes);
  * waits that trapped, by wait code (0xffffffff: none), followed by per-block progress words of SNB_TC_PROGRESS builds */
 SNB_API int snb_debug_hang_info(unsigned int* out192);
 /* out (Fa x Fb) = Xa^T Xb through the point-atom packing and the tensor-core weight-gradient kernel (csrc/tc_backward.cu);
- * Xa (P x Fa), Xb (P x Fb) fp32 row-major, Fa % 128 == 0, Fb % 64 == 0 */
+ * Xa (P x Fa), Xb (P x Fb) fp32 row-major, Fa % 64 == 0, Fb % 64 == 0 */
 SNB_API int snb_debug_dw_gemm(const float* xa, const float* xb, int P, int Fa, int Fb, int k_splits, float* out,
                               void* workspace, size_t workspace_bytes, void* stream);
 /* cycles for `iters` back-to-back tcgen05.mma (M=128 or 256, K=16) on n_blocks CTAs; mode 0 SS cg1, 1 TS cg1 (A in TMEM),

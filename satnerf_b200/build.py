@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsatnerf_b200.so")
 DEV_LIB = os.path.join(PKG, "libsatnerf_b200_dev.so")       # product sources + -DSNB_DEV_BUILD + microbenchmarks (include/satnerf_b200_dev.h)
-SOURCES = ["layout.cu", "sampling.cu", "composite.cu", "simt_field.cu", "tc_field.cu", "tc_backward.cu", "tc_bwd.cu", "geo.cu", "capi.cu"]
+SOURCES = ["layout.cu", "sampling.cu", "composite.cu", "simt_field.cu", "tc_field.cu", "tc_backward.cu", "tc_bwd.cu", "geo.cu", "optim.cu", "capi.cu"]
 DEV_SOURCES = SOURCES + ["mma_rate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "snb_loss_forward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_loss_backward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "snb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double,
+                                C.c_double, C.c_int, C.c_void_p]),
     "snb_field_workspace": (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.POINTER(C.c_size_t)]),
     "snb_field_forward": (C.c_int, [C.POINTER(FieldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -95,7 +97,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.snb_abi_version() != 3:
+        if handle.snb_abi_version() != 4:
             raise RuntimeError("libsatnerf_b200.so ABI version mismatch")
         _lib = handle
     return _lib
@@ -296,3 +298,14 @@ def field_forward(desc: FieldDesc, params, xyz, aux_dir, t_emb, sigma_only: bool
                                        int(sigma_only), precision, C.c_void_p(ws.data_ptr()), ws.numel(), _stream(xyz.device)),
                "snb_field_forward")
     return out
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+    """torch.optim.Adam update of one flat fp32 buffer, in place (one launch)."""
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == params.numel()):
+            raise ValueError("adam_step: contiguous fp32 CUDA buffers of one size expected")
+    with torch.cuda.device(params.device):
+        _check(lib().snb_adam_step(C.c_void_p(params.data_ptr()), C.c_void_p(grads.data_ptr()), C.c_void_p(exp_avg.data_ptr()),
+                                   C.c_void_p(exp_avg_sq.data_ptr()), params.numel(), lr, beta1, beta2, eps, weight_decay, int(step),
+                                   _stream(params.device)), "snb_adam_step")

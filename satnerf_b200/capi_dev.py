@@ -62,7 +62,7 @@ def debug_dw_gemm(xa, xb, k_splits=1):
     Fb = xb.shape[1]
     out = torch.empty(Fa, Fb, device=xa.device, dtype=torch.float32)
     tiles = (P + 127) // 128
-    nbytes = tiles * (Fa // 64 + Fb // 64) * 16384 + (Fa // 128) * ((Fb // 64 + 3) // 4) * k_splits * (128 * 256 * 4 + 64) + (1 << 16)
+    nbytes = tiles * (Fa // 64 + Fb // 64) * 16384 + ((Fa // 64 + 3) // 4) * ((Fb // 64 + 7) // 8) * k_splits * (256 * 512 * 4 + 128) + (1 << 16)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=xa.device)
     with torch.cuda.device(xa.device):
         _check(lib().snb_debug_dw_gemm(capi._ptr(xa), capi._ptr(xb), P, Fa, Fb, k_splits, capi._ptr(out), C.c_void_p(ws.data_ptr()), ws.numel(),

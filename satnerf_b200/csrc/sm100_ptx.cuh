@@ -67,6 +67,12 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk group of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// asynchronous prefetch of a contiguous global range into L2 (TMA engine; bytes % 16 == 0)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 
 // ---- Ampere-style cp.async for the small epilogue tables ------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {

@@ -39,6 +39,7 @@ struct TcBwdArgs {
     const float *rays, *z, *xyz;                  // sample positions (layer 0's pre-activation is recomputed from them)
     int ray_cols, dir_col;
     int n_layers, R, S, G, n_groups, tiles_per_group;
+    int dbg;                                      // developer what-if knobs (dev library only, see tc_common.cuh)
 };
 
 __device__ __forceinline__ float loss_scale(float absmax) {      // power of two that brings max |d_head| to ~64
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                 signal_ready(1);
 
                 int trunk_l = A.n_layers - 1;                     // layer whose dY the next BK_TRUNK GEMM consumes
+                bool prev_split = false;                          // the previous GEMM's dump left as two bulk groups
                 for (int gi = 0; gi < P.n_gemms; ++gi) {
                     const TcGemm& g = P.g[gi];
                     const int kind = g.kind, N = g.N, n_chunks = g.n_chunks, chunk_n = g.chunk_n;
@@ -262,7 +264,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     else if (kind == BK_A7) table_copy(sm.tblF, T + g.tbl_off, H * 4, tid_e);
                     else if (kind == BK_TRUNK && trunk_l - 1 == 0) table_copy(sm.tblF, T + g.tbl_off, H * 16, tid_e);
                     cp_async_wait_all();
-                    if (tid_e == 0) bulk_wait_read();
+                    // Dumps of a two-chunk GEMM leave in two bulk groups (low K-slabs after chunk 0's epilogue, the rest after
+                    // chunk 1's), so each group has half a layer to drain before its slabs are rewritten: chunk 0 of this GEMM
+                    // rewrites the low slabs (the previous GEMM's HIGH group may still be reading), chunk 1 the high ones.
+                    if (tid_e == 0) { if (prev_split) bulk_wait_read1(); else bulk_wait_read(); }
                     named_bar_sync(1, kEpiThreads);
                     const uint32_t tok = fresh_token((uint32_t)gi);
                     // where cos() comes from
@@ -271,18 +276,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     else if (kind == BK_S1) { yarr = A.fbase + A.fs.s1y; yF = H2; }
                     else if (kind == BK_A7) yarr = A.fbase + A.fs.y[A.n_layers - 1];
                     else if (kind == BK_TRUNK) { if (trunk_l - 1 == 0) { y_l0 = true; ymul = 30.f; } else yarr = A.fbase + A.fs.y[trunk_l - 1]; }
-                    if (!live) yarr = nullptr;
+                    if (!live || (SNB_DEV_DBG(A.dbg) & 512)) yarr = nullptr;
                     const bool stores = !nodrain;
                     const bool next_early = gi + 1 < P.n_gemms && n_chunks > 1 && P.g[gi + 1].k_early > 0;
-                    bool early_signaled = false;
+                    bool early_signaled = false, low_dumped = false;
                     float dt0 = 0.f, dt1 = 0.f, dt2 = 0.f, dt3 = 0.f;
+                    // destination of the dY tile this GEMM produces (atoms; the tile's K-slabs are contiguous there as in shared memory)
+                    unsigned char* dump_dst = A.bbase;
+                    if (kind == BK_FB || kind == BK_FA) dump_dst += A.bs.df + (size_t)gt * fgsH * kSlabBytes;
+                    else if (kind == BK_A7) dump_dst += A.bs.dy[A.n_layers - 1] + (size_t)gt * fgsH * kSlabBytes;
+                    else if (kind == BK_TRUNK) dump_dst += A.bs.dy[trunk_l - 1] + (size_t)gt * fgsH * kSlabBytes;
+                    if (tid_e == 0 && live && gi + 1 < P.n_gemms) {
+                        // the next GEMM's pre-activation tile (contiguous) on its way into L2 while this one runs
+                        const int kn = P.g[gi + 1].kind;
+                        const unsigned char* ya = nullptr; uint32_t yb_bytes = (uint32_t)kTile * (uint32_t)H * 2u;
+                        if (kn == BK_S1) { ya = A.fbase + A.fs.s1y; yb_bytes >>= 1; bulk_prefetch_l2(A.fbase + A.fs.r1y + (size_t)gt * yb_bytes, yb_bytes); }
+                        else if (kn == BK_FA && P.has_beta) { ya = A.fbase + A.fs.b1y; yb_bytes >>= 1; }
+                        else if (kn == BK_A7) ya = A.fbase + A.fs.y[A.n_layers - 1];
+                        else if (kn == BK_TRUNK) { const int ln = (kind == BK_TRUNK ? trunk_l - 1 : trunk_l) - 1; if (ln > 0) ya = A.fbase + A.fs.y[ln]; }
+                        if (ya) bulk_prefetch_l2(ya + (size_t)gt * yb_bytes, yb_bytes);
+                    }
                     // first y block of chunk 0 in flight while the MMAs run
                     YBuf ynext = yb_zero();
                     if (yarr && half * 32 < min(chunk_n, N)) ynext = yb_load(yarr, gt, yF, half * 32, row);
                     for (int ch = 0; ch < n_chunks; ++ch) {
                         if (tid_e == 0) {
                             if (ch == 0) mbar_wait(sm.acc_full, (uint32_t)(tile_seq * P.n_gemms + gi) & 1u, 24);
-                            else mbar_wait(sm.acc_full2, (uint32_t)(tile_seq * P.n_two + g.two_idx) & 1u, 24);
+                            else {
+                                mbar_wait(sm.acc_full2, (uint32_t)(tile_seq * P.n_two + g.two_idx) & 1u, 24);
+                                if (low_dumped) bulk_wait_read1(); else bulk_wait_read();      // the high slabs' previous dump has left
+                            }
                         }
                         named_bar_sync(2, kEpiThreads);
                         tc_fence_after();
@@ -372,6 +395,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                                 named_bar_sync(1, kEpiThreads);
                                 signal_ready(0);
                                 early_signaled = true;
+                                if (stores && chunk_n % 64 == 0) {                 // low K-slabs are final: first bulk group of this GEMM's dump
+                                    if (tid_e == 0 && live && !(SNB_DEV_DBG(A.dbg) & 1024)) { bulk_s2g(dump_dst, sm.a, (uint32_t)(chunk_n >> 6) * kSlabBytes); bulk_commit(); }
+                                    low_dumped = true;
+                                }
                             }
                         }
                     }
@@ -389,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                         float* o = A.d_t + ((size_t)r0 * S + p) * P.tau;
                         o[0] = s0 * inv_scale; if (P.tau > 1) o[1] = s1 * inv_scale; if (P.tau > 2) o[2] = s2 * inv_scale; if (P.tau > 3) o[3] = s3 * inv_scale;
                     }
-                    if (tid_e == 0 && live) {
+                    if (tid_e == 0 && live && !(SNB_DEV_DBG(A.dbg) & 1024)) {
                         // dump the dY tile(s) this step produced (A-tile image = atoms)
                         unsigned char* bb = A.bbase;
                         if (kind == BK_S2) bulk_s2g(bb + A.bs.ds2y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
@@ -397,11 +424,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                             bulk_s2g(bb + A.bs.ds1y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
                             bulk_s2g(bb + A.bs.dr1y + (size_t)gt * fgs2 * kSlabBytes, sm.a + (size_t)fgs2 * kSlabBytes, (uint32_t)fgs2 * kSlabBytes);
                         } else if (nodrain) bulk_s2g(bb + A.bs.db1y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes);
-                        else if (kind == BK_FB || kind == BK_FA) bulk_s2g(bb + A.bs.df + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
-                        else if (kind == BK_A7) bulk_s2g(bb + A.bs.dy[A.n_layers - 1] + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
-                        else bulk_s2g(bb + A.bs.dy[trunk_l - 1] + (size_t)gt * fgsH * kSlabBytes, sm.a, (uint32_t)fgsH * kSlabBytes);
+                        else {
+                            const uint32_t lo = low_dumped ? (uint32_t)(chunk_n >> 6) * kSlabBytes : 0u;
+                            bulk_s2g(dump_dst + lo, sm.a + lo, (uint32_t)fgsH * kSlabBytes - lo);
+                        }
                         bulk_commit();
                     }
+                    prev_split = low_dumped;
                     if (gi + 1 < P.n_gemms) {
                         if (!early_signaled) signal_ready(0);
                         signal_ready(1);
@@ -422,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 // finalize: ordered split-K reduction + scatter-add into the flat gradient buffer
 // ---------------------------------------------------------------------------------------------------------------
 struct DwOut {
-    long long part_off, part_stride; int ks, N;      // partial tiles: [ks][128][N] floats
+    long long part_off, part_stride; int ks, N;      // partial tiles: [ks][256][N] floats
     int kind;                                         // 0 weight block, 1 extra-input block [x sun t 1], 2 tiny head (transposed)
     long long w_off, b_off; int ld, m0, M, col_off, n0, ncols;    // kind 0: G[w_off + (m0+r)*ld + col_off + n0 + c], c < ncols
     int xcol, suncol, tcol, tau;                      // kind 1: destination columns of x / sun / t (-1: none); bias always
@@ -432,7 +461,7 @@ struct DwOut {
 __global__ void dw_finalize_kernel(const DwOut* __restrict__ outs, const float* __restrict__ partial, const float* __restrict__ absmax, float* __restrict__ G) {
     const DwOut o = outs[blockIdx.x];
     const float inv = 1.0f / loss_scale(*absmax);
-    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 128 * o.N; e += gridDim.y * blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 256 * o.N; e += gridDim.y * blockDim.x) {
         const int r = e / o.N, c = e - r * o.N;
         if (o.m0 + r >= o.M) continue;
         long long dst = -1;
@@ -444,8 +473,15 @@ __global__ void dw_finalize_kernel(const DwOut* __restrict__ outs, const float* 
             else if (c == 10) dst = o.b_off + o.m0 + r;
         } else { if (c >= o.hc0 && c < o.hc0 + o.nhc) dst = o.w_off + (long long)(c - o.hc0) * o.ld + o.m0 + r; }
         if (dst < 0) continue;
+        const float* src = partial + o.part_off + e;
         float acc = 0.f;
-        for (int s = 0; s < o.ks; ++s) acc += partial[o.part_off + (long long)s * o.part_stride + e];
+        int sp = 0;
+        for (; sp + 4 <= o.ks; sp += 4) {               // four independent loads in flight; the sum keeps the sequential order
+            const float a0 = src[(long long)sp * o.part_stride], a1 = src[(long long)(sp + 1) * o.part_stride];
+            const float a2 = src[(long long)(sp + 2) * o.part_stride], a3 = src[(long long)(sp + 3) * o.part_stride];
+            acc = (((acc + a0) + a1) + a2) + a3;
+        }
+        for (; sp < o.ks; ++sp) acc += src[(long long)sp * o.part_stride];
         G[dst] += acc * inv;
     }
 }
@@ -608,8 +644,139 @@ static void fwd_stash_layout(const FieldLayout& L, int n_tiles, int tpg, TcStash
 struct BwdPlan {
     int G, groups, tpg, n_tiles, ks, n_outs, n_items;
     TcBwdStash bs;
-    size_t off_dhead, off_raysums, off_absmax, off_dt, off_packed, packed_bytes, off_bstash, off_items, off_outs, off_partial, partial_floats, total;
+    size_t off_dhead, off_raysums, off_absmax, off_dt, off_packed, packed_bytes, off_bstash, off_items, off_outs, off_partial, partial_floats, off_sync, sync_ints, total;
 };
+
+// Work of the weight-gradient kernel for one pass.  Outputs (DwOut): one per 256-row block of dY features and per N operand
+// (the layer's input, <= 512 features; the extra block [x sun t 1]; the head-gradient block for the N <= 3 heads, computed
+// transposed with the features as M).  Pieces (DwItem): a "main" piece per input-block output, and the small-N outputs of the
+// same arrays grouped three at a time into multi-accumulator pieces, so that every piece of a bundle streams a similar number
+// of bytes per stage; all pieces cover the same `ks` point ranges and the pieces of one (bundle, range) are adjacent in the
+// list -- piece i runs on pair i % kDwPairs, so they run at the same time, sweep the points in step, and every stash array
+// comes from HBM once (the other readers hit L2).  fbase / bbase: forward and backward stash (null in the sizing pass: only
+// counts and sizes are used then).
+static void dw_work(const FieldLayout& L, const BwdPlan& B, int n_tiles, const unsigned char* fbase, const unsigned char* bbase,
+                    std::vector<DwOut>* outs, std::vector<DwItem>* items, size_t* partial_floats, size_t* sync_ints, const TcStash* fs_in = nullptr) {
+    const int H = L.width, H2 = H / 2, fgH = H / 64, fg2 = H2 / 64;
+    TcStash fs_local; const TcStash* fs = fs_in;
+    if (!fs) { fwd_stash_layout(L, n_tiles, B.tpg, &fs_local); fs = &fs_local; }
+    struct Opnd { const unsigned char* arr; int fgs, fg0, nfg; DwOut o; };
+    struct Piece { int n_acc; Opnd a[kDwMaxAcc]; const unsigned char* b_arr; int b_fgs, b_nfg; };
+    std::vector<std::vector<Piece>> bundles;
+    const unsigned char* e_arr = fbase + fs->e; const unsigned char* dh_arr = bbase + B.bs.dhead;
+    auto blocks = [](int fgs) { return (fgs + 3) / 4; };
+    auto block_nfg = [](int fgs, int m) { return fgs - 4 * m < 4 ? fgs - 4 * m : 4; };
+    // main pieces of one linear layer: dY (atoms dy_arr, dy_fgs groups) x IN (in_fgs groups, Nin features)
+    auto add_main = [&](std::vector<Piece>& bd, const Lin& l, const unsigned char* dy_arr, int dy_fgs, const unsigned char* in_arr, int in_fgs, int Nin, int col_off) {
+        for (int m = 0; m < blocks(dy_fgs); ++m) {
+            Piece pc; memset(&pc, 0, sizeof(pc)); pc.n_acc = 1; pc.b_arr = in_arr; pc.b_fgs = in_fgs; pc.b_nfg = in_fgs;
+            Opnd& a = pc.a[0]; a.arr = dy_arr; a.fgs = dy_fgs; a.fg0 = 4 * m; a.nfg = block_nfg(dy_fgs, m);
+            a.o.kind = 0; a.o.w_off = l.w; a.o.ld = l.n_in; a.o.m0 = m * 256; a.o.M = l.n_out; a.o.col_off = col_off; a.o.n0 = 0; a.o.ncols = Nin; a.o.N = in_fgs * 64;
+            bd.push_back(pc);
+        }
+    };
+    // small outputs: collected per bundle, then packed three accumulators to a piece
+    struct Small { Opnd a; const unsigned char* b_arr; };
+    auto add_extra = [&](std::vector<Small>& sm, const Lin& l, const unsigned char* dy_arr, int dy_fgs, int xcol, int suncol, int tcol) {   // dY x [x sun t 1]
+        for (int m = 0; m < blocks(dy_fgs); ++m) {
+            Small q; memset(&q, 0, sizeof(q)); q.b_arr = e_arr;
+            q.a.arr = dy_arr; q.a.fgs = dy_fgs; q.a.fg0 = 4 * m; q.a.nfg = block_nfg(dy_fgs, m);
+            q.a.o.kind = 1; q.a.o.w_off = l.w; q.a.o.b_off = l.b; q.a.o.ld = l.n_in; q.a.o.m0 = m * 256; q.a.o.M = l.n_out;
+            q.a.o.xcol = xcol; q.a.o.suncol = suncol; q.a.o.tcol = tcol; q.a.o.tau = L.t_dims; q.a.o.N = 64;
+            sm.push_back(q);
+        }
+    };
+    auto add_tiny = [&](std::vector<Small>& sm, const Lin& l, const unsigned char* in_arr, int in_fgs, int hc0, int nhc) {     // W (nhc x n_in): rows = head columns
+        for (int m = 0; m < blocks(in_fgs); ++m) {
+            Small q; memset(&q, 0, sizeof(q)); q.b_arr = dh_arr;
+            q.a.arr = in_arr; q.a.fgs = in_fgs; q.a.fg0 = 4 * m; q.a.nfg = block_nfg(in_fgs, m);
+            q.a.o.kind = 2; q.a.o.w_off = l.w; q.a.o.ld = l.n_in; q.a.o.m0 = m * 256; q.a.o.M = l.n_in; q.a.o.hc0 = hc0; q.a.o.nhc = nhc; q.a.o.N = 64;
+            sm.push_back(q);
+        }
+    };
+    auto pack_small = [&](std::vector<Piece>& bd, const std::vector<Small>& sm) {
+        for (size_t i = 0; i < sm.size();) {
+            Piece pc; memset(&pc, 0, sizeof(pc)); pc.b_arr = sm[i].b_arr; pc.b_fgs = 1; pc.b_nfg = 1;
+            while (i < sm.size() && pc.n_acc < kDwMaxAcc && sm[i].b_arr == pc.b_arr) pc.a[pc.n_acc++] = sm[i++].a;
+            bd.push_back(pc);
+        }
+    };
+    const unsigned char* fb = fbase; const unsigned char* bb = bbase;
+    for (int l = L.n_layers - 1; l >= 1; --l) {
+        std::vector<Piece> bd; std::vector<Small> sm;
+        add_main(bd, L.trunk[l], bb + B.bs.dy[l], fgH, fb + fs->a[l - 1], fgH, H, l == L.skip ? L.in_xyz : 0);
+        add_extra(sm, L.trunk[l], bb + B.bs.dy[l], fgH, l == L.skip ? 0 : -1, -1, -1);
+        pack_small(bd, sm); bundles.push_back(bd);
+    }
+    {   std::vector<Piece> bd; std::vector<Small> sm;                                   // feats + sigma head (both read a_{L-1}) + trunk layer 0 (no input block)
+        add_main(bd, L.feats, bb + B.bs.df, fgH, fb + fs->a[L.n_layers - 1], fgH, H, 0);
+        add_extra(sm, L.feats, bb + B.bs.df, fgH, -1, -1, -1);
+        pack_small(bd, sm); sm.clear();
+        add_tiny(sm, L.sigma, fb + fs->a[L.n_layers - 1], fgH, 3, 1);
+        pack_small(bd, sm); sm.clear();
+        add_extra(sm, L.trunk[0], bb + B.bs.dy[0], fgH, 0, -1, -1);
+        pack_small(bd, sm); bundles.push_back(bd); }
+    {   std::vector<Piece> bd; std::vector<Small> sm;                                   // first head layers: all read feat
+        add_main(bd, L.rgb0, bb + B.bs.dr1y, fg2, fb + fs->feat, fgH, H, 0);
+        add_main(bd, L.sun[0], bb + B.bs.ds1y, fg2, fb + fs->feat, fgH, H, 0);
+        if (L.variant == SNB_SATNERF) add_main(bd, L.beta0, bb + B.bs.db1y, fg2, fb + fs->feat, fgH, H, 0);
+        add_extra(sm, L.rgb0, bb + B.bs.dr1y, fg2, -1, -1, -1);
+        add_extra(sm, L.sun[0], bb + B.bs.ds1y, fg2, -1, H, -1);
+        if (L.variant == SNB_SATNERF) add_extra(sm, L.beta0, bb + B.bs.db1y, fg2, -1, -1, H);
+        pack_small(bd, sm); bundles.push_back(bd); }
+    {   std::vector<Piece> bd; std::vector<Small> sm;                                   // sun_v_net.2 / .4 and the N <= 3 heads of the H/2-wide activations
+        add_main(bd, L.sun[1], bb + B.bs.ds2y, fg2, fb + fs->s1, fg2, H2, 0);
+        add_main(bd, L.sun[2], bb + B.bs.ds3y, fg2, fb + fs->s2, fg2, H2, 0);
+        add_extra(sm, L.sun[1], bb + B.bs.ds2y, fg2, -1, -1, -1);
+        add_extra(sm, L.sun[2], bb + B.bs.ds3y, fg2, -1, -1, -1);
+        pack_small(bd, sm); sm.clear();
+        add_tiny(sm, L.rgb2, fb + fs->r1, fg2, 0, 3);
+        add_tiny(sm, L.sun[3], fb + fs->s3, fg2, 4, 1);
+        if (L.variant == SNB_SATNERF) add_tiny(sm, L.beta2, fb + fs->b1, fg2, 5, 1);
+        pack_small(bd, sm); bundles.push_back(bd); }
+    // split-K: the same ranges for every piece; ks = the count (<= 8) that fills whole waves of kDwPairs pieces best
+    int per_range = 0;
+    for (const auto& bd : bundles) per_range += (int)bd.size();
+    int ks = 1; double best = -1.0;
+    for (int k = 1; k <= 8 && k <= n_tiles; ++k) {
+        const int n = per_range * k, waves = (n + kDwPairs - 1) / kDwPairs;
+        double eff = (double)n / ((double)waves * kDwPairs);
+        if (k == 1 && n_tiles >= 16) eff *= 0.5;                  // a single range leaves most pairs idle on a real batch
+        if (eff > best + 1e-9) { best = eff; ks = k; }
+    }
+    outs->clear(); items->clear();
+    long long off = 0;
+    // outputs first (their partial offsets), then the pieces range by range, bundle by bundle
+    std::vector<std::vector<std::vector<int>>> out_idx(bundles.size());
+    for (size_t bi = 0; bi < bundles.size(); ++bi) {
+        out_idx[bi].resize(bundles[bi].size());
+        for (size_t pi = 0; pi < bundles[bi].size(); ++pi)
+            for (int a = 0; a < bundles[bi][pi].n_acc; ++a) {
+                DwOut o = bundles[bi][pi].a[a].o; o.ks = ks; o.part_off = off; o.part_stride = 256LL * o.N;
+                off += (long long)ks * o.part_stride;
+                out_idx[bi][pi].push_back((int)outs->size());
+                outs->push_back(o);
+            }
+    }
+    const int max_stages = 2 * ((n_tiles + ks - 1) / ks), sync_per_group = (max_stages + kDwSyncEvery - 1) / kDwSyncEvery;
+    *sync_ints = (size_t)ks * bundles.size() * sync_per_group;
+    for (int sp = 0; sp < ks; ++sp)
+        for (size_t bi = 0; bi < bundles.size(); ++bi)
+            for (size_t pi = 0; pi < bundles[bi].size(); ++pi) {
+                const Piece& pc = bundles[bi][pi];
+                DwItem w; memset(&w, 0, sizeof(w));
+                w.n_acc = pc.n_acc; w.b_off = (long long)(uintptr_t)pc.b_arr; w.b_fgs = pc.b_fgs; w.b_fg0 = 0; w.b_nfg = pc.b_nfg;
+                w.k_tile0 = (int)((long long)n_tiles * sp / ks); w.k_tiles = (int)((long long)n_tiles * (sp + 1) / ks) - w.k_tile0;
+                w.sync_off = (int)((sp * bundles.size() + bi) * sync_per_group); w.sync_n = (int)bundles[bi].size();
+                for (int a = 0; a < pc.n_acc; ++a) {
+                    w.a_off[a] = (long long)(uintptr_t)pc.a[a].arr; w.a_fgs[a] = pc.a[a].fgs; w.a_fg0[a] = pc.a[a].fg0; w.a_nfg[a] = pc.a[a].nfg;
+                    const DwOut& o = (*outs)[out_idx[bi][pi][a]];
+                    w.out_off[a] = o.part_off + (long long)sp * o.part_stride;
+                }
+                items->push_back(w);
+            }
+    *partial_floats = (size_t)off;
+}
 
 static void plan_bwd(const FieldLayout& L, const snb_pass_desc* p, const TcProgram& P, int n_tbl_floats, BwdPlan* B) {
     const int H = L.width, H2 = H / 2, S = p->n_samples;
@@ -621,18 +788,10 @@ static void plan_bwd(const FieldLayout& L, const snb_pass_desc* p, const TcProgr
     B->bs.df = take(tH); B->bs.dr1y = take(tH2); B->bs.ds1y = take(tH2); B->bs.ds2y = take(tH2); B->bs.ds3y = take(tH2); B->bs.db1y = take(tH2);
     B->bs.dhead = take(kSlabBytes);
     B->bs.total = off;
-    // output tiles of the weight-gradient GEMMs
-    const int mH = (H + 127) / 128, mH2 = (H2 + 127) / 128;       // 128-row output tiles per layer (last one may be partial)
-    const int cH = (H / 64 + 3) / 4, cH2 = (H2 / 64 + 3) / 4;
-    int outs = 0;
-    outs += (L.n_layers - 1) * mH * (cH + 1) + mH;             // trunk layers >= 1: [a_{l-1} | E]; layer 0: E only
-    outs += mH * (cH + 1);                                    // feats
-    outs += (L.variant == SNB_SATNERF ? 3 : 2) * mH2 * (cH + 1);   // rgb0, sun0 (, beta0): [feat | E]
-    outs += 2 * mH2 * (cH2 + 1);                              // sun1, sun2
-    outs += mH + (L.variant == SNB_SATNERF ? 3 : 2) * mH2;    // tiny heads: sigma (a_7), rgb2 (r1), sun3 (s3) (, beta2 (b1))
-    B->n_outs = outs;
-    int ks = (148 * 3 + outs - 1) / outs; if (ks < 1) ks = 1; if (ks > B->n_tiles) ks = B->n_tiles; if (ks > 16) ks = 16;
-    B->ks = ks; B->n_items = outs * ks;
+    // weight-gradient GEMMs: outputs (256-row blocks), split-K pieces and the partial buffer
+    std::vector<DwOut> outs; std::vector<DwItem> items;
+    dw_work(L, *B, B->n_tiles, nullptr, nullptr, &outs, &items, &B->partial_floats, &B->sync_ints);
+    B->n_outs = (int)outs.size(); B->n_items = (int)items.size(); B->ks = 0;
     Arena ar(nullptr, 0);
     B->off_dhead = ar.off; ar.take<float>((size_t)p->n_rays * S * L.n_channels);
     B->off_raysums = ar.off; ar.take<float>((size_t)p->n_rays * 16);
@@ -642,9 +801,9 @@ static void plan_bwd(const FieldLayout& L, const snb_pass_desc* p, const TcProgr
     B->off_packed = ar.off; ar.take<unsigned char>(B->packed_bytes);
     B->off_bstash = ar.off; ar.take<unsigned char>((size_t)B->bs.total + 1024);
     B->off_items = ar.off; ar.take<DwItem>(B->n_items);
-    B->off_outs = ar.off; ar.take<DwOut>(outs);
-    B->partial_floats = (size_t)B->n_items * 128 * 256;
+    B->off_outs = ar.off; ar.take<DwOut>(B->n_outs);
     B->off_partial = ar.off; ar.take<float>(B->partial_floats);
+    B->off_sync = ar.off; ar.take<int>(B->sync_ints);
     B->total = ar.off;
 }
 
@@ -713,6 +872,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     A.d_head = d_head; A.C = C; A.absmax = absmax; A.d_t = (L.t_dims && g->g_t_emb) ? d_t : nullptr;
     A.rays = io->rays; A.z = io->z_vals; A.xyz = io->xyz; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
     A.n_layers = L.n_layers; A.R = R; A.S = S; A.G = B.G; A.n_groups = B.groups; A.tiles_per_group = B.tpg;
+    A.dbg = dev_knobs().dbg;
     if (cg == 2) {
         SNB_CUDA(cudaFuncSetAttribute(tc_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int n_pairs = (B.groups + 1) / 2, max_pairs = sm_count / 2;
@@ -730,83 +890,24 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
         SNB_CHECK_LAUNCH();
     }
 
-    // 3. weight-gradient GEMMs: work list
-    std::vector<DwItem> items; std::vector<DwOut> outs;
-    items.reserve(B.n_items); outs.reserve(B.n_outs);
-    const unsigned char* fb = (const unsigned char*)io->stash; const unsigned char* bb = ws + B.off_bstash;
-    const int fgH = H / 64, fg2 = H2 / 64;
-    // Work-list order matters for DRAM traffic: the output tiles of one layer share their operands (every N-chunk reads the
-    // same dY rows, every M-tile the same input columns), so all tiles of a layer for ONE split-K range are made adjacent in
-    // the list — they run concurrently on neighbouring CTAs and the second reader of an operand slab hits L2.
-    std::vector<DwItem> pend;              // split 0 items of the current layer, one per output tile
-    auto add_out = [&](const unsigned char* a_arr, int a_fgs, int a_fg0, const unsigned char* b_arr, int b_fgs, int b_fg0, int b_nfg, DwOut o) {
-        o.N = b_nfg * 64; o.ks = B.ks;
-        DwItem w; memset(&w, 0, sizeof(w));
-        w.a_off = (long long)(uintptr_t)a_arr; w.b_off = (long long)(uintptr_t)b_arr; w.a_fgs = a_fgs; w.b_fgs = b_fgs;
-        w.a_fg0 = a_fg0; w.b_fg0 = b_fg0; w.b_nfg = b_nfg;
-        pend.push_back(w);
-        outs.push_back(o);
-    };
-    auto flush_layer = [&]() {
-        const size_t n = pend.size(), first_out = outs.size() - n;
-        const long long base = (long long)items.size() * 128 * 256;
-        for (int sp = 0; sp < B.ks; ++sp)
-            for (size_t e = 0; e < n; ++e) {
-                DwItem w = pend[e];
-                w.k_tile0 = (int)((long long)B.n_tiles * sp / B.ks); w.k_tiles = (int)((long long)B.n_tiles * (sp + 1) / B.ks) - w.k_tile0;
-                w.out_off = base + (long long)(sp * n + e) * 128 * 256;
-                items.push_back(w);
-            }
-        for (size_t e = 0; e < n; ++e) { outs[first_out + e].part_off = base + (long long)e * 128 * 256; outs[first_out + e].part_stride = (long long)n * 128 * 256; }
-        pend.clear();
-    };
-    // one linear layer: dY (out features M, atoms dy_arr with dy_fgs groups) x [IN (in features Nin, atoms) | E]
-    auto layer = [&](const Lin& l, const unsigned char* dy_arr, int dy_fgs, const unsigned char* in_arr, int in_fgs, int Nin, int col_off,
-                     int xcol, int suncol, int tcol) {
-        const int M_ = l.n_out;
-        for (int m = 0; m * 128 < M_; ++m) {
-            if (in_arr) for (int c0 = 0; c0 < in_fgs; c0 += 4) {
-                DwOut o; memset(&o, 0, sizeof(o)); o.kind = 0; o.w_off = l.w; o.ld = l.n_in; o.m0 = m * 128; o.M = M_; o.col_off = col_off; o.n0 = c0 * 64;
-                int nfg = in_fgs - c0 < 4 ? in_fgs - c0 : 4; o.ncols = Nin - c0 * 64 < nfg * 64 ? Nin - c0 * 64 : nfg * 64;
-                add_out(dy_arr, dy_fgs, 2 * m, in_arr, in_fgs, c0, nfg, o);
-            }
-            DwOut o; memset(&o, 0, sizeof(o)); o.kind = 1; o.w_off = l.w; o.b_off = l.b; o.ld = l.n_in; o.m0 = m * 128; o.M = M_;
-            o.xcol = xcol; o.suncol = suncol; o.tcol = tcol; o.tau = L.t_dims;
-            add_out(dy_arr, dy_fgs, 2 * m, fb + A.fs.e, 1, 0, 1, o);
-        }
-        flush_layer();
-    };
-    auto tiny = [&](const Lin& l, const unsigned char* in_arr, int in_fgs, int hc0, int nhc) {     // W (nhc x n_in): rows = head columns
-        for (int m = 0; m * 128 < l.n_in; ++m) {
-            DwOut o; memset(&o, 0, sizeof(o)); o.kind = 2; o.w_off = l.w; o.ld = l.n_in; o.m0 = m * 128; o.M = l.n_in; o.hc0 = hc0; o.nhc = nhc;
-            add_out(in_arr, in_fgs, 2 * m, bb + B.bs.dhead, 1, 0, 1, o);
-        }
-        flush_layer();
-    };
-    for (int l = L.n_layers - 1; l >= 1; --l)
-        layer(L.trunk[l], bb + B.bs.dy[l], fgH, fb + A.fs.a[l - 1], fgH, H, l == L.skip ? L.in_xyz : 0, l == L.skip ? 0 : -1, -1, -1);
-    layer(L.trunk[0], bb + B.bs.dy[0], fgH, nullptr, 0, 0, 0, 0, -1, -1);
-    layer(L.feats, bb + B.bs.df, fgH, fb + A.fs.a[L.n_layers - 1], fgH, H, 0, -1, -1, -1);
-    layer(L.rgb0, bb + B.bs.dr1y, fg2, fb + A.fs.feat, fgH, H, 0, -1, -1, -1);
-    layer(L.sun[0], bb + B.bs.ds1y, fg2, fb + A.fs.feat, fgH, H, 0, -1, H, -1);
-    if (L.variant == SNB_SATNERF) layer(L.beta0, bb + B.bs.db1y, fg2, fb + A.fs.feat, fgH, H, 0, -1, -1, H);
-    layer(L.sun[1], bb + B.bs.ds2y, fg2, fb + A.fs.s1, fg2, H2, 0, -1, -1, -1);
-    layer(L.sun[2], bb + B.bs.ds3y, fg2, fb + A.fs.s2, fg2, H2, 0, -1, -1, -1);
-    tiny(L.sigma, fb + A.fs.a[L.n_layers - 1], fgH, 3, 1);
-    tiny(L.rgb2, fb + A.fs.r1, fg2, 0, 3);
-    tiny(L.sun[3], fb + A.fs.s3, fg2, 4, 1);
-    if (L.variant == SNB_SATNERF) tiny(L.beta2, fb + A.fs.b1, fg2, 5, 1);
-    if ((int)items.size() > B.n_items || (int)outs.size() > B.n_outs) SNB_FAIL(-3, "internal: weight-gradient work list overflow (%zu/%d, %zu/%d)", items.size(), B.n_items, outs.size(), B.n_outs);
+    // 3. weight-gradient GEMMs: balanced per-pair work lists
+    std::vector<DwOut> outs; std::vector<DwItem> items; size_t partial_floats = 0;
+    size_t sync_ints = 0;
+    dw_work(L, B, B.n_tiles, (const unsigned char*)io->stash, ws + B.off_bstash, &outs, &items, &partial_floats, &sync_ints, &A.fs);
+    if ((int)items.size() != B.n_items || (int)outs.size() != B.n_outs || partial_floats != B.partial_floats)
+        SNB_FAIL(-3, "internal: weight-gradient work list mismatch (%zu/%d, %zu/%d)", items.size(), B.n_items, outs.size(), B.n_outs);
     DwItem* d_items = (DwItem*)(ws + B.off_items); DwOut* d_outs = (DwOut*)(ws + B.off_outs);
-    // The work lists (~40 KB) travel to the device as KERNEL PARAMETERS (up to 32 KB per launch since CUDA 12.1): no pinned
+    // The work lists (~25 KB) travel to the device as KERNEL PARAMETERS (up to 32 KB per launch since CUDA 12.1): no pinned
     // staging buffer, no event, no allocation -- the library keeps no state between calls.
     SNB_TRY(upload_by_param(d_items, items.data(), sizeof(DwItem) * items.size(), st));
     SNB_TRY(upload_by_param(d_outs, outs.data(), sizeof(DwOut) * outs.size(), st));
     float* partial = (float*)(ws + B.off_partial);
-    SNB_TRY(launch_dw(d_items, (int)items.size(), nullptr, partial, st));
+    int* d_sync = (int*)(ws + B.off_sync);
+    SNB_CUDA(cudaMemsetAsync(d_sync, 0, B.sync_ints * sizeof(int), st));
+    SNB_TRY(launch_dw(d_items, (int)items.size(), nullptr, partial, d_sync, st));
 
     // 4. reductions / scatter into the flat gradient
-    dw_finalize_kernel<<<dim3((unsigned)outs.size(), 8), 256, 0, st>>>(d_outs, partial, absmax, g->g_params);
+    dw_finalize_kernel<<<dim3((unsigned)outs.size(), 64), 256, 0, st>>>(d_outs, partial, absmax, g->g_params);
     SNB_CHECK_LAUNCH();
     BiasDst bd; for (int c = 0; c < 9; ++c) bd.off[c] = -1;
     bd.off[0] = L.rgb2.b; bd.off[1] = L.rgb2.b + 1; bd.off[2] = L.rgb2.b + 2; bd.off[3] = L.sigma.b; bd.off[4] = L.sun[3].b;

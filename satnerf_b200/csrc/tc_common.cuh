@@ -75,8 +75,13 @@ struct TcArgs {
 struct DevKnobs { int no_early, cg, dbg, bwd_off, hang_mirror; };
 #ifdef SNB_DEV_BUILD
 const DevKnobs& dev_knobs();
+// what-if knobs of the training kernels (SNB_TC_DBG bits, dev library only; results are wrong by design):
+// 128 forward: no pre-activation stash stores, 256 forward: no activation-tile dumps, 512 chain: no pre-activation loads,
+// 1024 chain: no dY dumps
+#define SNB_DEV_DBG(x) (x)
 #else
 inline DevKnobs dev_knobs() { return DevKnobs{0, 0, 0, 0, 0}; }
+#define SNB_DEV_DBG(x) 0
 #endif
 
 struct Smem {

@@ -682,6 +682,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         fence_proxy_async_smem();
                         named_bar_sync(1, kEpiThreads);
                         signal_ready(0);
+                        // training: activation tiles leave for the stash in two bulk groups (low K-slabs now, the rest when the tile is
+                        // complete), so each group has half a layer to drain before its slabs are rewritten
+                        if (sb && tid_e == 0) { bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)(l0_split >> 6) * kSlabBytes); bulk_commit(); }
                     }
                 }
                 fence_proxy_async_smem();
@@ -701,7 +704,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, kEpiThreads);                  // aux rows in place before the second ready signal
-                if (sb && tid_e == 0) { bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
+                if (sb && tid_e == 0) {
+                    const uint32_t lo = (uint32_t)(l0_split >> 6) * kSlabBytes;
+                    bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes + lo, sm.a + lo, (uint32_t)P.a_slabs * kSlabBytes - lo); bulk_commit();
+                }
+                bool prev_split = l0_split > 0;                  // the previous activation tile left as two bulk groups
                 {   const TcGemm& g0 = P.g[0];
                     if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
                     if (g0.has_vec) table_copy(sm.tblV, T + g0.vec_off, g0.N * 4, tid_e); }
@@ -716,7 +723,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     if (g_hang_host && blockIdx.x < 16 && tid_e == 0) ((volatile unsigned int*)g_hang_host)[64 + blockIdx.x * 8 + 2] = (unsigned)(wk << 16 | t << 8 | gi);
 #endif
                     cp_async_wait_all();
-                    if (sb && tid_e == 0) bulk_wait_read();      // the stash copy of the previous activation tile has left shared memory
+                    // the stash copy of the slabs chunk 0 is about to rewrite (low K-slabs) has left shared memory; a HIGH group of
+                    // the previous tile may still be draining
+                    if (sb && tid_e == 0) { if (prev_split) bulk_wait_read1(); else bulk_wait_read(); }
                     named_bar_sync(1, kEpiThreads);              // tables of this GEMM are in shared memory
                     TC_MARK(gi, 0);
                     // N-chunks (<=256 columns) complete one after the other: the epilogue of chunk 0 runs while the tensor core
@@ -726,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     const bool skip = g.skip != 0, last = g.last != 0;
                     const bool stores = kind == GK_TRUNK || kind == GK_FEAT || kind == GK_SUN1 || kind == GK_SUN2;
                     EpiStash es; es.gt = gt; es.y0 = es.y1 = es.act0 = es.act1 = nullptr;
-                    if (sb) {
+                    if (sb && !(SNB_DEV_DBG(A.dbg) & 128)) {
                         if (kind == GK_TRUNK) es.y0 = sb + A.stash.y[gi + 1];
                         else if (kind == GK_HEADA) { es.y0 = sb + A.stash.b1y; es.act0 = sb + A.stash.b1; es.y1 = sb + A.stash.r1y; es.act1 = sb + A.stash.r1; }
                         else if (kind == GK_SUN1) es.y0 = sb + A.stash.s1y;
@@ -735,7 +744,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     }
                     uint32_t tok = 0;
                     const bool next_early = gi + 1 < P.n_gemms && n_chunks > 1 && P.g[gi + 1].k_early > 0;
-                    bool early_signaled = false;
+                    bool early_signaled = false, low_dumped = false;
+                    unsigned char* dump_dst = nullptr;           // stash array of the activation tile this GEMM produces
+                    if (sb && !(SNB_DEV_DBG(A.dbg) & 256)) {
+                        const int fgs2 = (H2 + 63) >> 6;
+                        if (kind == GK_TRUNK) dump_dst = sb + A.stash.a[gi + 1] + (size_t)gt * P.a_slabs * kSlabBytes;
+                        else if (kind == GK_FEAT) dump_dst = sb + A.stash.feat + (size_t)gt * P.a_slabs * kSlabBytes;
+                        else if (kind == GK_SUN1) dump_dst = sb + A.stash.s1 + (size_t)gt * fgs2 * kSlabBytes;
+                        else if (kind == GK_SUN2) dump_dst = sb + A.stash.s2 + (size_t)gt * fgs2 * kSlabBytes;
+                    }
                     for (int ch = 0; ch < n_chunks; ++ch) {
                         // one thread polls the mbarrier; the others park in a hardware barrier instead of spinning on shared memory
 #ifdef SNB_V_ONE_ACC
@@ -746,7 +763,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                         if (tid_e == 0) {
                             const int tile_seq = tile_counter - 1;
                             if (ch == 0) mbar_wait(sm.acc_full, (uint32_t)(tile_seq * P.n_gemms + gi) & 1u, 4);
-                            else mbar_wait(sm.acc_full2, (uint32_t)(tile_seq * P.n_two + g.two_idx) & 1u, 4);
+                            else {
+                                mbar_wait(sm.acc_full2, (uint32_t)(tile_seq * P.n_two + g.two_idx) & 1u, 4);
+                                if (sb) { if (low_dumped) bulk_wait_read1(); else bulk_wait_read(); }      // the high slabs' previous stash copy has left
+                            }
                         }
 #endif
 #ifdef SNB_TC_PROBE
@@ -799,6 +819,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 named_bar_sync(1, kEpiThreads);
                                 signal_ready(0);
                                 early_signaled = true;
+                                if (dump_dst && stores && chunk_n % 64 == 0) {          // low K-slabs are final: first bulk group of the stash copy
+                                    if (tid_e == 0) { bulk_s2g(dump_dst, sm.a, (uint32_t)(chunk_n >> 6) * kSlabBytes); bulk_commit(); }
+                                    low_dumped = true;
+                                }
                             }
                         }
                     }
@@ -815,13 +839,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 #endif
                     named_bar_sync(1, kEpiThreads);              // all TMEM reads / A writes / table reads of this GEMM done
                     TC_MARK(gi, 2);
-                    if (sb && tid_e == 0) {                      // dump the activation tile this GEMM produced (A-tile image = atoms)
-                        const int fgs2 = (H2 + 63) >> 6;
-                        if (kind == GK_TRUNK) { bulk_s2g(sb + A.stash.a[gi + 1] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
-                        else if (kind == GK_FEAT) { bulk_s2g(sb + A.stash.feat + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)P.a_slabs * kSlabBytes); bulk_commit(); }
-                        else if (kind == GK_SUN1) { bulk_s2g(sb + A.stash.s1 + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit(); }
-                        else if (kind == GK_SUN2) { bulk_s2g(sb + A.stash.s2 + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit(); }
+                    if (dump_dst && tid_e == 0) {                // dump (the rest of) the activation tile this GEMM produced (A-tile image = atoms)
+                        const uint32_t lo = low_dumped ? (uint32_t)(chunk_n >> 6) * kSlabBytes : 0u;
+                        const uint32_t all = (uint32_t)((kind == GK_TRUNK || kind == GK_FEAT) ? P.a_slabs : ((H2 + 63) >> 6)) * kSlabBytes;
+                        bulk_s2g(dump_dst + lo, sm.a + lo, all - lo); bulk_commit();
                     }
+                    prev_split = low_dumped;
                     if (gi + 1 < P.n_gemms) {
                         const TcGemm& gn = P.g[gi + 1];
                         if (gn.fmt != TF_NONE) table_copy(sm.tblF, T + gn.tbl_off, gn.N * gn.fmt * 4, tid_e);
