@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../.."
 mkdir -p profiles/dev/variants /tmp/snbv_$1
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -DSNB_DEV_BUILD -I include -I satnerf_b200/csrc $2"
-for s in layout sampling composite simt_field tc_field tc_backward tc_bwd geo mma_rate capi; do
+for s in layout sampling composite simt_field tc_field tc_backward tc_bwd geo optim mma_rate capi; do
   /usr/local/cuda/bin/nvcc $F -c satnerf_b200/csrc/$s.cu -o /tmp/snbv_$1/$s.o &
 done
 wait

@@ -141,7 +141,8 @@ __device__ __forceinline__ void mul_cos32(float* v, const YBuf& b, float mul) { 
 //   TRUNK  l = L-1 .. 1:  D = A W_l[:, skip:] ;  A = D w0_{l-1} cos(y_{l-1})                    -> dump d y_{l-1}
 // (y_0 = 30 (W_0 x + b_0) is recomputed from the sample position; every other y comes from the forward's fp16 stash.)
 template <int CG>
-__global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcBwdArgs A) {
+__global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(const __grid_constant__ TcBwdArgs A) {
+    constexpr int EW = kEpiWarpsTrain, ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcProgram& P = A.prog;
@@ -226,13 +227,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     for (int c = 1; c < 8; ++c) *reinterpret_cast<uint4*>(atom_chunk(da, gt, 1, row, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 // ---- seed: d s3y = g_sun * w_s3 * cos(s3y)  ->  A[:, 0:H2) ----
-                table_copy(sm.tblF, T + P.l0_tbl, H2 * 4, tid_e);
+                table_copy<ET>(sm.tblF, T + P.l0_tbl, H2 * 4, tid_e);
                 cp_async_wait_all();
                 if (tid_e == 0) bulk_wait_read();                 // the previous tile's last dump has left shared memory
-                named_bar_sync(1, kEpiThreads);
+                named_bar_sync(1, ET);
                 {
                     const uint32_t tok = fresh_token(0x7fffu);
-                    for (int n0 = half * 32; n0 < H2; n0 += 32 * kEpiSub) {
+                    for (int n0 = half * 32; n0 < H2; n0 += 32 * ES) {
                         const YBuf yb = live ? yb_load(A.fbase + A.fs.s3y, gt, H2, n0, row) : yb_zero();
                         float v[32];
 #pragma unroll
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, kEpiThreads);
+                named_bar_sync(1, ET);
                 if (tid_e == 0 && live) { bulk_s2g(A.bbase + A.bs.ds3y + (size_t)gt * fgs2 * kSlabBytes, sm.a, (uint32_t)fgs2 * kSlabBytes); bulk_commit(); }
                 {   const TcGemm& gn = P.g[0];                   // tables of the first GEMM (none for S2) -- the seed table is dead
                     (void)gn; }
@@ -259,16 +260,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                     const int kind = g.kind, N = g.N, n_chunks = g.n_chunks, chunk_n = g.chunk_n;
                     const bool nodrain = kind == BK_FA && P.has_beta;
                     // epilogue tables of this GEMM + make sure earlier dumps have left shared memory
-                    if (kind == BK_S1) table_copy(sm.tblF, T + g.tbl_off, H2 * 16, tid_e);
-                    else if (nodrain) { table_copy(sm.tblF, T + g.tbl_off, H2 * 16, tid_e); table_copy(sm.tblV, T + g.vec_off, H2 * 4, tid_e); }
-                    else if (kind == BK_A7) table_copy(sm.tblF, T + g.tbl_off, H * 4, tid_e);
-                    else if (kind == BK_TRUNK && trunk_l - 1 == 0) table_copy(sm.tblF, T + g.tbl_off, H * 16, tid_e);
+                    if (kind == BK_S1) table_copy<ET>(sm.tblF, T + g.tbl_off, H2 * 16, tid_e);
+                    else if (nodrain) { table_copy<ET>(sm.tblF, T + g.tbl_off, H2 * 16, tid_e); table_copy<ET>(sm.tblV, T + g.vec_off, H2 * 4, tid_e); }
+                    else if (kind == BK_A7) table_copy<ET>(sm.tblF, T + g.tbl_off, H * 4, tid_e);
+                    else if (kind == BK_TRUNK && trunk_l - 1 == 0) table_copy<ET>(sm.tblF, T + g.tbl_off, H * 16, tid_e);
                     cp_async_wait_all();
                     // Dumps of a two-chunk GEMM leave in two bulk groups (low K-slabs after chunk 0's epilogue, the rest after
                     // chunk 1's), so each group has half a layer to drain before its slabs are rewritten: chunk 0 of this GEMM
                     // rewrites the low slabs (the previous GEMM's HIGH group may still be reading), chunk 1 the high ones.
                     if (tid_e == 0) { if (prev_split) bulk_wait_read1(); else bulk_wait_read(); }
-                    named_bar_sync(1, kEpiThreads);
+                    named_bar_sync(1, ET);
                     const uint32_t tok = fresh_token((uint32_t)gi);
                     // where cos() comes from
                     const unsigned char* yarr = nullptr; int yF = H; float ymul = 1.f; bool y_l0 = false;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                                 if (low_dumped) bulk_wait_read1(); else bulk_wait_read();      // the high slabs' previous dump has left
                             }
                         }
-                        named_bar_sync(2, kEpiThreads);
+                        named_bar_sync(2, ET);
                         tc_fence_after();
                         const bool final_chunk = ch == n_chunks - 1;
                         if (!nodrain) {
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                             if (have) tmem_ld16(tm_row + (uint32_t)n0, va);
                             while (have) {
                                 const YBuf ycur = ynext;
-                                const int n1 = n0 + 32 * kEpiSub;
+                                const int n1 = n0 + 32 * ES;
                                 const bool more = n1 < n_end;
                                 if (yarr && more) ynext = yb_load(yarr, gt, yF, n1, row);
                                 tmem_ld_wait16(va);
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                             }
                         } else if (final_chunk) {
                             // d feat (so far) stays in TMEM; build d b1y = g_beta * w_b2 * cos(b1y) as the operand of FB
-                            for (int n0 = half * 32; n0 < H2; n0 += 32 * kEpiSub) {
+                            for (int n0 = half * 32; n0 < H2; n0 += 32 * ES) {
                                 const YBuf yb = live ? yb_load(A.fbase + A.fs.b1y, gt, H2, n0, row) : yb_zero();
                                 float v[32];
 #pragma unroll
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                             tc_fence_before();
                             if (next_early) {
                                 fence_proxy_async_smem();
-                                named_bar_sync(1, kEpiThreads);
+                                named_bar_sync(1, ET);
                                 signal_ready(0);
                                 early_signaled = true;
                                 if (stores && chunk_n % 64 == 0) {                 // low K-slabs are final: first bulk group of this GEMM's dump
@@ -408,11 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                         float* sc = scratch + (size_t)(half * kTile + row) * 4;
                         sc[0] = dt0; sc[1] = dt1; sc[2] = dt2; sc[3] = dt3;
                     }
-                    named_bar_sync(1, kEpiThreads);              // all TMEM reads / A writes / table reads of this GEMM done
+                    named_bar_sync(1, ET);              // all TMEM reads / A writes / table reads of this GEMM done
                     if (nodrain && A.d_t && half == 0 && valid) {
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                        for (int h2 = 0; h2 < kEpiSub; ++h2) { const float* sc = scratch + (size_t)(h2 * kTile + row) * 4; s0 += sc[0]; s1 += sc[1]; s2 += sc[2]; s3 += sc[3]; }
+                        for (int h2 = 0; h2 < ES; ++h2) { const float* sc = scratch + (size_t)(h2 * kTile + row) * 4; s0 += sc[0]; s1 += sc[1]; s2 += sc[2]; s3 += sc[3]; }
                         float* o = A.d_t + ((size_t)r0 * S + p) * P.tau;
                         o[0] = s0 * inv_scale; if (P.tau > 1) o[1] = s1 * inv_scale; if (P.tau > 2) o[2] = s2 * inv_scale; if (P.tau > 3) o[3] = s3 * inv_scale;
                     }
@@ -877,7 +878,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
         SNB_CUDA(cudaFuncSetAttribute(tc_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int n_pairs = (B.groups + 1) / 2, max_pairs = sm_count / 2;
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(kThreads);
+        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(64 + 32 * kEpiWarpsTrain);
         cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -886,7 +887,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
         ++g_launches;
     } else {
         SNB_CUDA(cudaFuncSetAttribute(tc_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_chain_kernel<1><<<B.groups < sm_count ? B.groups : sm_count, kThreads, smem, st>>>(A);
+        tc_chain_kernel<1><<<B.groups < sm_count ? B.groups : sm_count, 64 + 32 * kEpiWarpsTrain, smem, st>>>(A);
         SNB_CHECK_LAUNCH();
     }
 

@@ -14,10 +14,20 @@ constexpr int kMaxGroupRays = 4;
 constexpr int kMaxGroupPts = 384;
 constexpr int kSlabBytes = kTile * 128;      // one 64-wide K slab of the A tile
 constexpr int kTblF = 8192, kTblV = 2048;    // epilogue table region: [N][4] or [N] floats + extra vector
-constexpr int kEpiWarps = 16;                 // 4 warps per TMEM lane quadrant
-constexpr int kEpiSub = kEpiWarps / 4;         // column-block interleave factor within a quadrant
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;
+// Epilogue warps (kEpi / 4 per TMEM lane quadrant).  Inference: 16 (with the producer and issuer warps 18 warps = 5 on two of
+// the four sub-partitions: at most 96 registers per thread).  Training kernels (forward with stash, backward chain): 8 --
+// 10 warps leave 168 registers per thread; at 96 their epilogues spilled ~50 values and re-derived loop invariants every
+// 32-column block (LDL / indexed LDC stalls: measured 1.99 ms per 1024-ray step with 16, 1.70 with 12, 1.64 with 8 warps); the
+// inference kernel has no spills at 96 and loses 2.5 % with 12 warps.
+#ifndef SNB_EPI_WARPS
+#define SNB_EPI_WARPS 16
+#endif
+#ifndef SNB_EPI_WARPS_TRAIN
+#define SNB_EPI_WARPS_TRAIN 8
+#endif
+constexpr int kEpiWarps = SNB_EPI_WARPS;
+constexpr int kEpiWarpsTrain = SNB_EPI_WARPS_TRAIN;
+constexpr int kMaxEpiWarps = kEpiWarps > kEpiWarpsTrain ? kEpiWarps : kEpiWarpsTrain;
 
 enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3 };
 enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
@@ -202,8 +212,9 @@ __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // cooperative copy (all epilogue threads) of `bytes` (multiple of 16) from global to shared with cp.async
+template <int ET>
 __device__ __forceinline__ void table_copy(void* dst, const void* src, int bytes, int tid_e) {
-    for (int o = tid_e * 16; o < bytes; o += kEpiThreads * 16) cp_async16((char*)dst + o, (const char*)src + o);
+    for (int o = tid_e * 16; o < bytes; o += ET * 16) cp_async16((char*)dst + o, (const char*)src + o);
 }
 
 

@@ -347,7 +347,8 @@ __device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool s
 // leader issues M=256 MMAs that read each CTA's own activation tile and HALF of every weight tile from each
 // CTA's shared memory, so each SM streams / buffers only half of the weights.
 template <int CG, bool TRAIN>
-__global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
+__global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps), 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
+    constexpr int EW = TRAIN ? kEpiWarpsTrain : kEpiWarps, ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcProgram& P = A.prog;
@@ -540,11 +541,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
             }
         }
     } else {
-        // ================= epilogue warps (kEpiWarps warps; kEpiSub threads per point) =================
-        // Warp w may touch TMEM lanes [32*(w%4), +32).  The kEpiSub warps of a quadrant interleave the 32-column
+        // ================= epilogue warps (EW warps; ES threads per point) =================
+        // Warp w may touch TMEM lanes [32*(w%4), +32).  The ES warps of a quadrant interleave the 32-column
         // blocks of every layer; several warps per scheduler let MUFU work of one overlap pack/store work of another.
         const int tid_e = threadIdx.x - 64;
-        const int quad = warp & 3, half = (warp - 2) >> 2;      // half = sub-warp index 0..kEpiSub-1 within the quadrant
+        const int quad = warp & 3, half = (warp - 2) >> 2;      // half = sub-warp index 0..ES-1 within the quadrant
         const int row = quad * 32 + lane;                // point (row of the tile) owned by this thread
         const uint32_t a_base = smem_u32(sm.a);
         const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
             const int Pg = n_rays * S;
             const int n_tiles = tiles_per_group;
             // ---- per-ray tables: sun / embedding terms of the first head layers, sky colour ----
-            for (int idx = tid_e; idx < n_rays * H2; idx += kEpiThreads) {
+            for (int idx = tid_e; idx < n_rays * H2; idx += ET) {
                 int gr = idx / H2, n = idx - gr * H2;
                 const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
                 float v = T[P.sunw + 3 * H2 + n];
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     sm.betab[gr * H2 + n] = b;
                 }
             }
-            for (int gr = warp - 2; gr < n_rays; gr += kEpiWarps) {          // sky_color(sun_d): per ray (satnerf.py:201)
+            for (int gr = warp - 2; gr < n_rays; gr += EW) {          // sky_color(sun_d): per ray (satnerf.py:201)
                 const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
                 for (int n = lane; n < H2; n += 32) {
@@ -647,9 +648,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 const uint32_t betab_row = smem_u32(sm.betab) + (uint32_t)(rl * H2) * 4u;
                 // ---- trunk layer 0 on CUDA cores: sin(30 (W0 x + b0)), K = 3 (satnerf.py:105-106) ----
                 if (half == 0) { sm.wt[row] = px; sm.wt[kTile + row] = py; sm.wt[2 * kTile + row] = pz; }     // positions of the tile's points
-                table_copy(sm.tblF, T + P.l0_tbl, H * 16, tid_e);
+                table_copy<ET>(sm.tblF, T + P.l0_tbl, H * 16, tid_e);
                 cp_async_wait_all();
-                named_bar_sync(1, kEpiThreads);
+                named_bar_sync(1, ET);
                 const uint32_t tok0 = fresh_token(0xffffu);
                 const int l0_split = P.g[0].k_early * 64;         // columns published with the first ready signal (0: none)
                 // Thread mapping of this layer: 4 rows (lane + 32k) x 8 columns per step, so that one 16-byte table read
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                 for (int k = 0; k < 4; ++k) { rx[k] = sm.wt[lane + 32 * k]; ry[k] = sm.wt[kTile + lane + 32 * k]; rz[k] = sm.wt[2 * kTile + lane + 32 * k]; }
                 for (int pass = 0; pass < 2; ++pass) {
                     const int c_lo = pass ? l0_split : 0, c_hi = pass ? H : l0_split;
-                    for (int n0 = c_lo + (warp - 2) * 8; n0 < c_hi; n0 += 8 * kEpiWarps) {
+                    for (int n0 = c_lo + (warp - 2) * 8; n0 < c_hi; n0 += 8 * EW) {
                         float4 w[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) w[i] = lds128(tF + (uint32_t)(n0 + i) * 16u, tok0);
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     }
                     if (pass == 0 && l0_split > 0) {              // low K-slabs of the first GEMM's input are in place
                         fence_proxy_async_smem();
-                        named_bar_sync(1, kEpiThreads);
+                        named_bar_sync(1, ET);
                         signal_ready(0);
                         // training: activation tiles leave for the stash in two bulk groups (low K-slabs now, the rest when the tile is
                         // complete), so each group has half a layer to drain before its slabs are rewritten
@@ -688,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, kEpiThreads);                  // the whole input tile of the first GEMM is in place; layer-0 table dead
+                named_bar_sync(1, ET);                  // the whole input tile of the first GEMM is in place; layer-0 table dead
                 if (half == 0) {                                 // aux operand row of this point: [1 1 | xyz hi | xyz lo | xyz hi | 0..] (fp16 hi/lo pairs)
                     const __half xh = __float2half_rn(px), yh = __float2half_rn(py), zh = __float2half_rn(pz);
                     const uint32_t one = 0x3c003c00u;
@@ -703,15 +704,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     sts128(base_aux + (16u ^ sw), w4, w5, 0u, 0u);          // k 8..15: x y z hi | 0
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, kEpiThreads);                  // aux rows in place before the second ready signal
+                named_bar_sync(1, ET);                  // aux rows in place before the second ready signal
                 if (sb && tid_e == 0) {
                     const uint32_t lo = (uint32_t)(l0_split >> 6) * kSlabBytes;
                     bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes + lo, sm.a + lo, (uint32_t)P.a_slabs * kSlabBytes - lo); bulk_commit();
                 }
                 bool prev_split = l0_split > 0;                  // the previous activation tile left as two bulk groups
                 {   const TcGemm& g0 = P.g[0];
-                    if (g0.fmt != TF_NONE) table_copy(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
-                    if (g0.has_vec) table_copy(sm.tblV, T + g0.vec_off, g0.N * 4, tid_e); }
+                    if (g0.fmt != TF_NONE) table_copy<ET>(sm.tblF, T + g0.tbl_off, g0.N * g0.fmt * 4, tid_e);
+                    if (g0.has_vec) table_copy<ET>(sm.tblV, T + g0.vec_off, g0.N * 4, tid_e); }
                 if (l0_split == 0) signal_ready(0);
                 signal_ready(1);
                 TC_MARK(60, 1);
@@ -726,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     // the stash copy of the slabs chunk 0 is about to rewrite (low K-slabs) has left shared memory; a HIGH group of
                     // the previous tile may still be draining
                     if (sb && tid_e == 0) { if (prev_split) bulk_wait_read1(); else bulk_wait_read(); }
-                    named_bar_sync(1, kEpiThreads);              // tables of this GEMM are in shared memory
+                    named_bar_sync(1, ET);              // tables of this GEMM are in shared memory
                     TC_MARK(gi, 0);
                     // N-chunks (<=256 columns) complete one after the other: the epilogue of chunk 0 runs while the tensor core
                     // works on chunk 1.  Chunk 1's MMAs walk the K-slabs in order and release each one (slab_free[]) as soon as
@@ -772,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 #ifdef SNB_TC_PROBE
                         if (gi == 1 && ch == 1) TC_MARK(53, 0);
 #endif
-                        named_bar_sync(2, kEpiThreads);
+                        named_bar_sync(2, ET);
 #ifdef SNB_TC_PROBE
                         if (gi == 1 && ch == 1) TC_MARK(53, 1);
 #endif
@@ -798,7 +799,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 epi_cols<16>(tok, A.dbg, KIND, skip, LAST, P.has_beta, n0, H2, reinterpret_cast<float*>(va), a_base, row, tF, tV, sunb_row, betab_row, \
                                              px, py, pz, es, slab_bar, slab_par, sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);                       \
                                 tmem_ld_wait16(vb);                                                                                                   \
-                                const int n1 = n0 + 32 * kEpiSub;                                                                                     \
+                                const int n1 = n0 + 32 * ES;                                                                                     \
                                 const bool more = n1 < n_end;                                                                                         \
                                 if (more) tmem_ld16(tm_row + (uint32_t)n1, va);                                                                       \
                                 epi_cols<16>(tok, A.dbg, KIND, skip, LAST, P.has_beta, n0 + 16, H2, reinterpret_cast<float*>(vb), a_base, row, tF, tV, sunb_row, betab_row, \
@@ -816,7 +817,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                                 // queued right behind this GEMM's chunk 1 -- they touch neither its accumulator columns nor the high
                                 // K-slabs the last chunk's epilogue is about to write -- so the tensor pipe never drains between layers.
                                 if (!(TC_DBG(A.dbg) & 32)) fence_proxy_async_smem();
-                                named_bar_sync(1, kEpiThreads);
+                                named_bar_sync(1, ET);
                                 signal_ready(0);
                                 early_signaled = true;
                                 if (dump_dst && stores && chunk_n % 64 == 0) {          // low K-slabs are final: first bulk group of the stash copy
@@ -837,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
 #ifdef SNB_TC_PROBE
                     if (gi == 1) TC_MARK(52, 2);
 #endif
-                    named_bar_sync(1, kEpiThreads);              // all TMEM reads / A writes / table reads of this GEMM done
+                    named_bar_sync(1, ET);              // all TMEM reads / A writes / table reads of this GEMM done
                     TC_MARK(gi, 2);
                     if (dump_dst && tid_e == 0) {                // dump (the rest of) the activation tile this GEMM produced (A-tile image = atoms)
                         const uint32_t lo = low_dumped ? (uint32_t)(chunk_n >> 6) * kSlabBytes : 0u;
@@ -847,22 +848,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     prev_split = low_dumped;
                     if (gi + 1 < P.n_gemms) {
                         const TcGemm& gn = P.g[gi + 1];
-                        if (gn.fmt != TF_NONE) table_copy(sm.tblF, T + gn.tbl_off, gn.N * gn.fmt * 4, tid_e);
-                        if (gn.has_vec) table_copy(sm.tblV, T + gn.vec_off, gn.N * 4, tid_e);
+                        if (gn.fmt != TF_NONE) table_copy<ET>(sm.tblF, T + gn.tbl_off, gn.N * gn.fmt * 4, tid_e);
+                        if (gn.has_vec) table_copy<ET>(sm.tblV, T + gn.vec_off, gn.N * 4, tid_e);
                         if (!early_signaled) signal_ready(0);
                         signal_ready(1);
                     }
                 }
-                // ---- head outputs of this point: combine the partial dot products of the kEpiSub column interleaves.
+                // ---- head outputs of this point: combine the partial dot products of the ES column interleaves.
                 //      The activation tile is dead here (every MMA that read it has completed), so it is the scratch. ----
                 if (sb && tid_e == 0) bulk_wait_read();
-                named_bar_sync(1, kEpiThreads);
+                named_bar_sync(1, ET);
                 float* dots = reinterpret_cast<float*>(sm.a) + (size_t)((half * kTile + row) * 8);
                 if (half != 0) { dots[0] = sig_dot; dots[1] = beta_dot; dots[2] = rgb0; dots[3] = rgb1; dots[4] = rgb2; dots[5] = sun_dot; }
-                named_bar_sync(1, kEpiThreads);
+                named_bar_sync(1, ET);
                 if (half == 0 && valid) {
 #pragma unroll
-                    for (int h2 = 1; h2 < kEpiSub; ++h2) {
+                    for (int h2 = 1; h2 < ES; ++h2) {
                         const float* d = reinterpret_cast<const float*>(sm.a) + (size_t)((h2 * kTile + row) * 8);
                         sig_dot += d[0]; beta_dot += d[1]; rgb0 += d[2]; rgb1 += d[3]; rgb2 += d[4]; sun_dot += d[5];
                     }
@@ -881,12 +882,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     if (A.albedo) { A.albedo[gp * 3] = sm.al0[p]; A.albedo[gp * 3 + 1] = sm.al1[p]; A.albedo[gp * 3 + 2] = sm.al2[p]; }
                     if (A.sky) { A.sky[gp * 3] = sm.skyc[rl * 4]; A.sky[gp * 3 + 1] = sm.skyc[rl * 4 + 1]; A.sky[gp * 3 + 2] = sm.skyc[rl * 4 + 2]; }
                 }
-                named_bar_sync(1, kEpiThreads);                  // scratch reads done before the next tile's layer 0 overwrites A
+                named_bar_sync(1, ET);                  // scratch reads done before the next tile's layer 0 overwrites A
             }
-            named_bar_sync(1, kEpiThreads);
+            named_bar_sync(1, ET);
             { const bool dbg_on = TC_DBG(blockIdx.x == 0 && tile_counter == 2); TC_MARK(61, 0); }
             // ---- alpha compositing: one warp per ray, transmittance by warp scan (satnerf.py:52-70) ----
-            for (int gr = warp - 2; gr < n_rays; gr += kEpiWarps) {
+            for (int gr = warp - 2; gr < n_rays; gr += EW) {
                 const int ray = r0 + gr;
                 float carry = 1.f, depth = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
                 float xs = 0.f, xa0 = 0.f, xa1 = 0.f, xa2 = 0.f, xb = 0.f, xw = 0.f;      // sum w*{sun, albedo, beta, 1} (aux_sums)
@@ -946,7 +947,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_render_kernel(const __grid_con
                     if (A.rgb) { A.rgb[ray * 3] = fminf(fmaxf(c0, 0.f), 1.f); A.rgb[ray * 3 + 1] = fminf(fmaxf(c1, 0.f), 1.f); A.rgb[ray * 3 + 2] = fminf(fmaxf(c2, 0.f), 1.f); }
                 }
             }
-            named_bar_sync(1, kEpiThreads);                      // group tables are reused by the next group
+            named_bar_sync(1, ET);                      // group tables are reused by the next group
             { const bool dbg_on = TC_DBG(blockIdx.x == 0 && tile_counter == 2); TC_MARK(61, 1); }
         }
     }
@@ -1068,7 +1069,7 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n_pairs = (A.n_groups + 1) / 2, max_pairs = sm_count / 2;
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(kThreads);
+        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(64 + 32 * (train ? kEpiWarpsTrain : kEpiWarps));
         cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1079,7 +1080,7 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         auto kern = train ? tc_render_kernel<1, true> : tc_render_kernel<1, false>;
         SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = A.n_groups < sm_count ? A.n_groups : sm_count;
-        kern<<<grid, kThreads, smem, st>>>(A);
+        kern<<<grid, 64 + 32 * (train ? kEpiWarpsTrain : kEpiWarps), smem, st>>>(A);
         SNB_CHECK_LAUNCH();
     }
     return 0;
