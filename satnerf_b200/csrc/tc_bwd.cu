@@ -58,17 +58,23 @@ __global__ void tc_bwd_pack_kernel(TcProgram P, const float* __restrict__ W, uns
     long long base = 0;
     for (int i = 0; i < gi; ++i) base += (long long)P.g[i].n_chunks * P.g[i].k_slabs * P.g[i].chunk_n * 128;
     __half* out = reinterpret_cast<__half*>(packed + base);
-    const long long total = (long long)g.n_chunks * g.k_slabs * g.chunk_n * 64;
+    // one thread per 16-byte chunk (8 k of one output row n); consecutive threads take consecutive n, so that each of the 8
+    // strided reads W[k][col + n] is coalesced across the warp
+    const long long total = (long long)g.n_chunks * g.k_slabs * g.chunk_n * 8;
     for (long long e = tid; e < total; e += nthr) {
-        int kk = (int)(e & 63); long long r = e >> 6;
-        int nl = (int)(r % g.chunk_n); long long t = r / g.chunk_n;
-        int s = (int)(t % g.k_slabs), j = (int)(t / g.k_slabs);
-        int n = j * g.chunk_n + nl, k = s * 64 + kk;
-        float v = 0.f;
-        if (k < g.K) v = k < g.rows0 ? W[g.src0 + (long long)k * g.ld0 + g.col0 + n]
-                                     : W[g.src1 + (long long)(k - g.rows0) * g.ld1 + g.col1 + n];
-        size_t tile = (size_t)(j * g.k_slabs + s) * g.chunk_n * 64;
-        out[tile + (size_t)nl * 64 + ((((kk >> 3) ^ (nl & 7)) << 3) | (kk & 7))] = __float2half_rn(v);
+        const int nl = (int)(e % g.chunk_n); long long r = e / g.chunk_n;
+        const int c = (int)(r & 7); r >>= 3;
+        const int s = (int)(r % g.k_slabs), j = (int)(r / g.k_slabs);
+        const int n = j * g.chunk_n + nl, k0 = s * 64 + c * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            v[i] = k >= g.K ? 0.f : (k < g.rows0 ? W[g.src0 + (long long)k * g.ld0 + g.col0 + n] : W[g.src1 + (long long)(k - g.rows0) * g.ld1 + g.col1 + n]);
+        }
+        const size_t tile = (size_t)(j * g.k_slabs + s) * g.chunk_n * 64;
+        *reinterpret_cast<uint4*>(out + tile + (size_t)nl * 64 + (size_t)((c ^ (nl & 7)) << 3)) =
+            make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
     }
 }
 
@@ -115,16 +121,17 @@ __device__ __forceinline__ YBuf yb_load(const unsigned char* arr, int gt, int F,
 }
 __device__ __forceinline__ YBuf yb_zero() { YBuf b; for (int c = 0; c < 4; ++c) b.q[c] = make_uint4(0u, 0u, 0u, 0u); return b; }
 // v[i] *= mul * cos(y_i), i < 16: y = columns [16 * hf, 16 * hf + 16) of a 32-column y block
-__device__ __forceinline__ void mul_cos16(float* v, const YBuf& b, int hf, float mul) {
+// (every stashed layer has w0 = 1: the derivative factor is cos(y) alone)
+__device__ __forceinline__ void mul_cos16(float* v, const YBuf& b, int hf) {
     const __half2* h = reinterpret_cast<const __half2*>(&b.q[2 * hf]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float2 y = __half22float2(h[i]);
-        v[2 * i] *= mul * __cosf(y.x);
-        v[2 * i + 1] *= mul * __cosf(y.y);
+        v[2 * i] *= __cosf(y.x);
+        v[2 * i + 1] *= __cosf(y.y);
     }
 }
-__device__ __forceinline__ void mul_cos32(float* v, const YBuf& b, float mul) { mul_cos16(v, b, 0, mul); mul_cos16(v + 16, b, 1, mul); }
+__device__ __forceinline__ void mul_cos32(float* v, const YBuf& b) { mul_cos16(v, b, 0); mul_cos16(v + 16, b, 1); }
 
 // The chain kernel follows the forward's tile pipeline (tc_pipeline.cuh): CTA pairs (CG = 2) or single CTAs, 4-deep half-stage
 // weight ring, two N-chunks per GEMM with the epilogue of chunk 0 under the MMAs of chunk 1, direct stores into released
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                             float4 w = lds128(tF + (uint32_t)(n0 + i) * 4u, tok);
                             v[i] = gsun * w.x; v[i + 1] = gsun * w.y; v[i + 2] = gsun * w.z; v[i + 3] = gsun * w.w;
                         }
-                        mul_cos32(v, yb, 1.f);
+                        mul_cos32(v, yb);
                         store_act32(a_base, row, n0, v);
                     }
                 }
@@ -272,11 +279,11 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                     named_bar_sync(1, ET);
                     const uint32_t tok = fresh_token((uint32_t)gi);
                     // where cos() comes from
-                    const unsigned char* yarr = nullptr; int yF = H; float ymul = 1.f; bool y_l0 = false;
+                    const unsigned char* yarr = nullptr; int yF = H; bool y_l0 = false;
                     if (kind == BK_S2) { yarr = A.fbase + A.fs.s2y; yF = H2; }
                     else if (kind == BK_S1) { yarr = A.fbase + A.fs.s1y; yF = H2; }
                     else if (kind == BK_A7) yarr = A.fbase + A.fs.y[A.n_layers - 1];
-                    else if (kind == BK_TRUNK) { if (trunk_l - 1 == 0) { y_l0 = true; ymul = 30.f; } else yarr = A.fbase + A.fs.y[trunk_l - 1]; }
+                    else if (kind == BK_TRUNK) { if (trunk_l - 1 == 0) y_l0 = true; else yarr = A.fbase + A.fs.y[trunk_l - 1]; }
                     if (!live || (SNB_DEV_DBG(A.dbg) & 512)) yarr = nullptr;
                     const bool stores = !nodrain;
                     const bool next_early = gi + 1 < P.n_gemms && n_chunks > 1 && P.g[gi + 1].k_early > 0;
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                                             const float y = __fmul_rn(30.0f, fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w))));     // as the forward's layer 0
                                             v[i] *= 30.f * __cosf(y);
                                         }
-                                    } else if (yarr) mul_cos16(v, ycur, hf, ymul);
+                                    } else if (yarr) mul_cos16(v, ycur, hf);
                                     else if (kind != BK_FA && kind != BK_FB) {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) v[i] = 0.f;       // idle half of a pair: keep the tile finite
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                                         float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
                                         u[i] = fmaf(g2, w.z, fmaf(g1, w.y, g0 * w.x));
                                     }
-                                    mul_cos32(u, yr, 1.f);
+                                    mul_cos32(u, yr);
                                     store_act32(a_base, row, H2 + n0, u);
                                 }
                                 n0 = n1; have = more;
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                                 float v[32];
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) v[i] = gbeta * lds128(tF + (uint32_t)(n0 + i) * 16u, tok).x;
-                                mul_cos32(v, yb, 1.f);
+                                mul_cos32(v, yb);
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     float4 w = lds128(tF + (uint32_t)(n0 + i) * 16u, tok);
@@ -462,28 +469,35 @@ struct DwOut {
 __global__ void dw_finalize_kernel(const DwOut* __restrict__ outs, const float* __restrict__ partial, const float* __restrict__ absmax, float* __restrict__ G) {
     const DwOut o = outs[blockIdx.x];
     const float inv = 1.0f / loss_scale(*absmax);
-    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 256 * o.N; e += gridDim.y * blockDim.x) {
-        const int r = e / o.N, c = e - r * o.N;
+    // four consecutive columns per thread: one 16-byte load per split-K partial (independent loads in flight), ordered sum
+    const int n4 = 64 * o.N;                                       // 256 rows x N / 4
+    for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < n4; q += gridDim.y * blockDim.x) {
+        const int e = q * 4, r = e / o.N, c0 = e - r * o.N;
         if (o.m0 + r >= o.M) continue;
-        long long dst = -1;
-        if (o.kind == 0) { if (c < o.ncols) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.col_off + o.n0 + c; }
-        else if (o.kind == 1) {
-            if (c < 3) { if (o.xcol >= 0) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.xcol + c; }
-            else if (c < 6) { if (o.suncol >= 0) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.suncol + (c - 3); }
-            else if (c < 10) { if (o.tcol >= 0 && c - 6 < o.tau) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.tcol + (c - 6); }
-            else if (c == 10) dst = o.b_off + o.m0 + r;
-        } else { if (c >= o.hc0 && c < o.hc0 + o.nhc) dst = o.w_off + (long long)(c - o.hc0) * o.ld + o.m0 + r; }
-        if (dst < 0) continue;
-        const float* src = partial + o.part_off + e;
-        float acc = 0.f;
+        if (o.kind == 0 ? c0 >= o.ncols : (o.kind == 1 ? c0 >= 12 : (c0 >= o.hc0 + o.nhc || c0 + 4 <= o.hc0))) continue;
+        const float4* src = reinterpret_cast<const float4*>(partial + o.part_off + e);
+        const long long stride4 = o.part_stride >> 2;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int sp = 0;
-        for (; sp + 4 <= o.ks; sp += 4) {               // four independent loads in flight; the sum keeps the sequential order
-            const float a0 = src[(long long)sp * o.part_stride], a1 = src[(long long)(sp + 1) * o.part_stride];
-            const float a2 = src[(long long)(sp + 2) * o.part_stride], a3 = src[(long long)(sp + 3) * o.part_stride];
-            acc = (((acc + a0) + a1) + a2) + a3;
+        for (; sp + 2 <= o.ks; sp += 2) {
+            const float4 a0 = src[(long long)sp * stride4], a1 = src[(long long)(sp + 1) * stride4];
+            acc.x = (acc.x + a0.x) + a1.x; acc.y = (acc.y + a0.y) + a1.y; acc.z = (acc.z + a0.z) + a1.z; acc.w = (acc.w + a0.w) + a1.w;
         }
-        for (; sp < o.ks; ++sp) acc += src[(long long)sp * o.part_stride];
-        G[dst] += acc * inv;
+        if (sp < o.ks) { const float4 a0 = src[(long long)sp * stride4]; acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w; }
+        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + i;
+            long long dst = -1;
+            if (o.kind == 0) { if (c < o.ncols) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.col_off + o.n0 + c; }
+            else if (o.kind == 1) {
+                if (c < 3) { if (o.xcol >= 0) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.xcol + c; }
+                else if (c < 6) { if (o.suncol >= 0) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.suncol + (c - 3); }
+                else if (c < 10) { if (o.tcol >= 0 && c - 6 < o.tau) dst = o.w_off + (long long)(o.m0 + r) * o.ld + o.tcol + (c - 6); }
+                else if (c == 10) dst = o.b_off + o.m0 + r;
+            } else { if (c >= o.hc0 && c < o.hc0 + o.nhc) dst = o.w_off + (long long)(c - o.hc0) * o.ld + o.m0 + r; }
+            if (dst >= 0) G[dst] += v[i] * inv;
+        }
     }
 }
 
@@ -908,7 +922,7 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     SNB_TRY(launch_dw(d_items, (int)items.size(), nullptr, partial, d_sync, st));
 
     // 4. reductions / scatter into the flat gradient
-    dw_finalize_kernel<<<dim3((unsigned)outs.size(), 64), 256, 0, st>>>(d_outs, partial, absmax, g->g_params);
+    dw_finalize_kernel<<<dim3((unsigned)outs.size(), 32), 256, 0, st>>>(d_outs, partial, absmax, g->g_params);
     SNB_CHECK_LAUNCH();
     BiasDst bd; for (int c = 0; c < 9; ++c) bd.off[c] = -1;
     bd.off[0] = L.rgb2.b; bd.off[1] = L.rgb2.b + 1; bd.off[2] = L.rgb2.b + 2; bd.off[3] = L.sigma.b; bd.off[4] = L.sun[3].b;

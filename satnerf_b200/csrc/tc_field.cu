@@ -151,19 +151,21 @@ __global__ void tc_pack_kernel(TcProgram P, const float* __restrict__ W, unsigne
         for (int i = 0; i < gi; ++i) base += gemm_stream_bytes(P.g[i]);
         __half* out = reinterpret_cast<__half*>(packed + base);
         const size_t chunk_halves = (size_t)(chunk_stream_bytes(g) / 2);
-        // B tiles: for chunk j, slab s: [chunk_n rows][64 k] fp16, 128-byte swizzle
-        const long long total = (long long)g.n_chunks * g.k_slabs * g.chunk_n * 64;
+        // B tiles: for chunk j, slab s: [chunk_n rows][64 k] fp16, 128-byte swizzle.  One thread per 16-byte chunk (8 k of one row):
+        // the 8 threads of a row read 256 contiguous bytes of the fp32 weights and write one 128-byte line.
+        const long long total = (long long)g.n_chunks * g.k_slabs * g.chunk_n * 8;
         for (long long e = tid; e < total; e += nthr) {
-            int kk = (int)(e & 63); long long r = e >> 6;
-            int nl = (int)(r % g.chunk_n); long long t = r / g.chunk_n;
-            int s = (int)(t % g.k_slabs), j = (int)(t / g.k_slabs);
-            int n = j * g.chunk_n + nl, k = s * 64 + kk;
-            float v = 0.f;
-            if (k < g.K) v = n < g.rows0 ? W[g.src0 + (long long)n * g.ld0 + g.col0 + k]
-                                         : W[g.src1 + (long long)(n - g.rows0) * g.ld1 + g.col1 + k];
-            size_t tile = (size_t)j * chunk_halves + (size_t)s * g.chunk_n * 64;
-            size_t off = tile + (size_t)nl * 64 + ((((kk >> 3) ^ (nl & 7)) << 3) | (kk & 7));
-            out[off] = __float2half_rn(v);
+            const int c = (int)(e & 7); long long r = e >> 3;
+            const int nl = (int)(r % g.chunk_n); const long long t = r / g.chunk_n;
+            const int s = (int)(t % g.k_slabs), j = (int)(t / g.k_slabs);
+            const int n = j * g.chunk_n + nl, k0 = s * 64 + c * 8;
+            const float* src = n < g.rows0 ? W + g.src0 + (long long)n * g.ld0 + g.col0 + k0 : W + g.src1 + (long long)(n - g.rows0) * g.ld1 + g.col1 + k0;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = k0 + i < g.K ? src[i] : 0.f;
+            const size_t tile = (size_t)j * chunk_halves + (size_t)s * g.chunk_n * 64;
+            *reinterpret_cast<uint4*>(out + tile + (size_t)nl * 64 + (size_t)((c ^ (nl & 7)) << 3)) =
+                make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
         }
         // aux tile of every chunk: [chunk_n rows][16 k] fp16, 32-byte swizzle.  k = 0,1: bias hi, lo (fp16 pair: exact to 2^-22);
         // skip layer: k = 2..4 W_xyz hi (x A's xyz hi), 5..7 W_xyz hi (x xyz lo), 8..10 W_xyz lo (x xyz hi); the rest 0
