@@ -59,6 +59,15 @@ def peaks():
         return 1590.0, 1400.0, "fallback"
 
 
+def hbm_peak():
+    """Measured HBM copy bandwidth (GB/s) of MEASURED_PEAKS.json, else the profiling recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -174,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
-    ap.add_argument("--only", default="", help="comma list of extra legs to run (train,config3,config4,config5,gpu_eager,cpu); default: all")
+    ap.add_argument("--only", default="", help="comma list of extra legs to run (train,config3,config4,config5,geometry,gpu_eager,cpu); default: all")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     opt = ap.parse_args()
@@ -185,7 +194,7 @@ def main():
     if opt.impl == "reference":
         run_reference(opt, rank, world)
         return
-    legs = set(x for x in opt.only.split(",") if x) or {"train", "config3", "config4", "config5", "gpu_eager", "cpu"}
+    legs = set(x for x in opt.only.split(",") if x) or {"train", "config3", "config4", "config5", "geometry", "gpu_eager", "cpu"}
     if opt.no_train:
         legs.discard("train")
     if opt.no_cpu:
@@ -405,6 +414,44 @@ def main():
             ms5e, _ = measure(e5, 5, 2)
             rec5["e2e"] = {"value": tile / (ms5e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": (hi - lo) * 52, "d2h_bytes_per_step": (hi - lo) * 16}
             extra["config5"] = rec5
+
+        if "geometry" in legs and rank == 0:
+            # SURVEY 8 f3 / f4, the neighbours of the render path in create_satnerf_dsm.py: rays of one 512x512 view from its RPC model
+            # (datasets/satellite.py:18-65, :185-227) and the DSM of the rendered depths (:246-338).  float64 element-wise kernels; the
+            # numpy oracle (the reference's own arithmetic + restated rpcm / pyproj / plyflatten) is timed beside them on a bounded sample.
+            from satnerf_b200 import geo
+            from oracle import geo_oracle as gor
+            import numpy as np
+            rpc = gor.synthetic_rpc(seed=1)
+            center, rng = [799046.0, -5451605.0, 3202158.0], 400.0
+            sg = geo.SatelliteGeometry(center, rng, device=dev)
+            tile = 512 * 512
+
+            def fr():
+                return sg.rays_for_image(rpc, 512, 512, -10.0, 60.0, 50.0, 140.0)
+            rays_g = fr()
+            depth_g = rays_g[:, 7] * 0.5
+            ms_r, l_r = measure(fr, 10, 3)
+
+            def fd():
+                return sg.get_dsm_from_nerf_prediction(rays_g, depth_g)
+            ms_d, l_d = measure(fd, 10, 3)
+            n_s = 16384
+            cols, rows = np.meshgrid(np.arange(128), np.arange(128))
+            t0 = time.perf_counter(); ref_r = gor.normalize_rays(gor.get_rays(cols.ravel(), rows.ravel(), rpc, -10.0, 60.0), center, rng); t_r = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            la, lo_, al = gor.latlonalt_from_prediction(ref_r, 0.5 * ref_r[:, 7], center, rng); e_, n_ = gor.utm_forward(la, lo_, 17)
+            t_d = time.perf_counter() - t0          # (points + projection; the pure-Python raster loop of the oracle is not a baseline)
+            extra["geometry"] = {
+                "workload": "one 512x512 view (262 144 pixels): RPC ray generation; rays + depths -> UTM point cloud -> 0.5 m DSM raster",
+                "rays": {"value": tile / (ms_r * 1e-3), "unit": "pixels/s", "ms_per_tile": ms_r, "gpu_launches": l_r,
+                         "roofline": {"bound": "hbm", "achieved": tile * 44 / (ms_r * 1e-3) / 1e9, "peak": hbm_peak(), "unit": "GB/s",
+                                      "frac": tile * 44 / (ms_r * 1e-3) / 1e9 / hbm_peak(), "traffic": None,
+                                      "note": "44 B written per pixel; the kernel is float64-arithmetic bound (two iterative inverse-RPC solves per pixel), not HBM bound"},
+                         "cpu_baseline": {"value": n_s / t_r, "unit": "pixels/s", "cores": 1, "kind": "port", "sample": f"{n_s} pixels, numpy float64"}},
+                "dsm": {"value": tile / (ms_d * 1e-3), "unit": "points/s", "ms_per_tile": ms_d, "gpu_launches": l_d,
+                        "cpu_baseline": {"value": n_s / t_d, "unit": "points/s", "cores": 1, "kind": "port",
+                                         "sample": f"{n_s} points, numpy float64, ECEF -> geodetic -> UTM only (no raster)"}}}
 
         if "gpu_eager" in legs and rank == 0:
             # the reference's algorithm with stock torch eager on this GPU: same ops as rendering.py + models/satnerf.py

@@ -201,6 +201,36 @@ SNB_API int snb_field_forward(const snb_field_desc* f, const float* params, cons
                       const float* aux_dir, const float* t_emb, float* out, int n_points,
                       int sigma_only, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- geometry either side of the render path -------------------------------------------------
+ * RPC camera model of one satellite image: the fields of rpcm.RPCModel (projection coefficients in RPC00B order; the
+ * reference builds it from the image's json, datasets/satellite.py:191) after sat_utils.rescale_rpc.                  */
+typedef struct snb_rpc_model {
+    double row_num[20], row_den[20], col_num[20], col_den[20];
+    double row_offset, row_scale, col_offset, col_scale, lat_offset, lat_scale, lon_offset, lon_scale, alt_offset, alt_scale;
+} snb_rpc_model;
+
+/* datasets/satellite.py:18-65 get_rays (+ :218-227 normalize_rays when center3 != NULL, + :229-244 sun direction when
+ * sun_dir3 != NULL): rays (n_pixels, ray_cols = 8 | 11) fp32 DEVICE = [origin, unit direction, near = 0, far, (sun)].
+ * Pixels: cols / rows (n_pixels doubles each, DEVICE) or NULL for the row-major grid of `width` columns
+ * (np.meshgrid(arange(w), arange(h)), :193).  rpc, center3, sun_dir3 are HOST pointers (copied into the launch).
+ * max_iters (DEVICE int, optional, zeroed by the caller) receives the largest iteration count of the inverse RPC
+ * (> 100: rpcm raises MaxLocalizationIterationsError).                                                              */
+SNB_API int snb_rpc_rays(const snb_rpc_model* rpc, const double* cols, const double* rows, int width, long long n_pixels,
+                 double min_alt, double max_alt, const double* center3, double range, const float* sun_dir3,
+                 float* rays, int ray_cols, int* max_iters, void* stream);
+
+/* datasets/satellite.py:246-274 get_latlonalt_from_nerf_prediction + sat_utils.utm_from_latlon (:99-113): cloud (n,3)
+ * doubles DEVICE = [east, north, alt] in UTM zone `utm_zone` (<= 0: [lon, lat, alt], no projection); latlon (n,2)
+ * optional [lat, lon] degrees.  center3 HOST.                                                                       */
+SNB_API int snb_dsm_points(const float* rays, int ray_cols, const float* depth, long long n_rays, const double* center3, double range,
+                   int utm_zone, double* cloud, double* latlon, void* stream);
+
+/* plyflatten(cloud, xoff, yoff, resolution, xsize, ysize, radius, sigma=inf) as called at datasets/satellite.py:308:
+ * dsm (ysize, xsize) fp32 DEVICE, mean altitude of the points within `radius` cells of each cell, NaN where none.
+ * Deterministic (fixed-point sums).  workspace: xsize * ysize * 12 + 512 bytes.                                     */
+SNB_API int snb_dsm_rasterize(const double* cloud, long long n_points, double xoff, double yoff, double resolution, int xsize, int ysize,
+                      int radius, float* dsm, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Optimiser step of the training loop on a flat parameter buffer (main.py:81-94 builds torch.optim.Adam(lr, weight_decay=0)
  * through train_utils.py:24-53; Lightning calls its step after every training_step): torch.optim.Adam arithmetic (amsgrad
  * off, L2 weight decay folded into the gradient; hyper-parameters as doubles like torch's Python scalars), `step` = 1-based

@@ -47,6 +47,13 @@ _GRAD_FIELDS = ["g_rgb", "g_depth", "g_weights", "g_transparency", "g_albedo", "
                 "g_params", "g_t_emb"]       # + `loss` (pointer to LossDesc)
 
 
+class RpcModel(C.Structure):
+    """snb_rpc_model: the fields of rpcm.RPCModel (projection direction)."""
+    _fields_ = [(n, C.c_double * 20) for n in ("row_num", "row_den", "col_num", "col_den")] + \
+               [(n, C.c_double) for n in ("row_offset", "row_scale", "col_offset", "col_scale", "lat_offset", "lat_scale",
+                                          "lon_offset", "lon_scale", "alt_offset", "alt_scale")]
+
+
 class RenderIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _IO_FIELDS]
 
@@ -75,6 +82,11 @@ _SIGNATURES = {
     "snb_loss_forward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_loss_backward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "snb_rpc_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double, C.c_void_p, C.c_double,
+                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "snb_dsm_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snb_dsm_rasterize": (C.c_int, [C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int, C.c_void_p]),
     "snb_field_workspace": (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.POINTER(C.c_size_t)]),
