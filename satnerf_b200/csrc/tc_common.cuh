@@ -29,7 +29,7 @@ constexpr int kEpiWarps = SNB_EPI_WARPS;
 constexpr int kEpiWarpsTrain = SNB_EPI_WARPS_TRAIN;
 constexpr int kMaxEpiWarps = kEpiWarps > kEpiWarpsTrain ? kEpiWarps : kEpiWarpsTrain;
 
-enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3 };
+enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3, GK_HEADN };      // HEADN: nerf's rgb_from_xyzdir.0 (per-ray view-direction bias, ReLU)
 enum { TF_NONE = 0, TF_F1 = 1, TF_F4 = 4 };
 
 struct TcGemm {
@@ -40,6 +40,9 @@ struct TcGemm {
     int k_early;                     // K-slabs of the input tile that are valid (and chunk-0 accumulator columns free) at the FIRST
                                      // ready signal; the rest needs the second one
     int accumulate;                  // 1: the MMAs add onto what the previous GEMM left in the accumulator (backward chain)
+    int a_slab0;                     // first K-slab of the A tile this GEMM reads (nerf layer 0 reads only the positional-encoding slab)
+    int relu;                        // activation of a TRUNK GEMM: 0 sin, 1 ReLU (nerf)
+    int kvalid, k2_start, k2_cols, col_k2;   // weight columns along K: k < kvalid -> col0 + k; k2_start <= k < k2_start + k2_cols -> col_k2 + k - k2_start; else 0
     int tbl_off, vec_off;            // float offsets into the packed table area
     // weight sources (flat fp32 params): rows [0,rows0) from src0, the rest from src1
     long long src0, src1; int ld0, ld1, col0, col1, rows0;
@@ -47,7 +50,8 @@ struct TcGemm {
 
 struct TcProgram {
     int H, H2, n_gemms, n_two, n_store2, tau, has_beta, a_slabs, stage_bytes, n_stages;
-    int l0_tbl, consts, sunw, betaw, sky;        // float offsets in the table area
+    int nerf, pe_xyz, pe_dir, pe_slab;           // nerf variant: Mapping frequencies (nerf.py:36-69) and the A-tile slab that holds the encoded position
+    int l0_tbl, consts, sunw, betaw, sky;        // float offsets in the table area (nerf: sunw = rgb_from_xyzdir.0 view-direction columns + bias)
     long long l0_w, l0_b;                        // flat param offsets of trunk layer 0
     long long tables_base;                       // byte offset of the table area in the packed buffer
     TcGemm g[kMaxGemms];
@@ -71,7 +75,7 @@ struct TcArgs {
     TcStash stash; unsigned char* stash_base;    // stash_base == nullptr: inference, nothing is stashed
     const float *params, *rays, *z, *t_emb, *noise, *xyz, *aux;
     float noise_std;
-    float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma, *aux_sums;
+    float *rgb, *depth, *weights, *transparency, *albedo, *sun, *sky, *beta, *sigma, *aux_sums, *nerf_rgb;
     float t_min;
     unsigned char* packed;
     int R, S, ray_cols, dir_col, G, n_groups;

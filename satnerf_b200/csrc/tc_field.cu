@@ -34,7 +34,7 @@ namespace snb {
 // host: build the per-tile GEMM program
 // --------------------------------------------------------------------------------------------------
 static bool tc_supported(const FieldLayout& L, const snb_pass_desc* p) {
-    if (L.variant == SNB_NERF) return false;                 // PE + ReLU variant stays on the fp32 path for now
+    if (L.variant == SNB_NERF && (L.in_xyz > 64 || L.in_xyz % 6 != 0 || L.in_dir > 48 || L.in_dir % 6 != 0 || L.skip < 1)) return false;   // (Mapping off / > 10 frequencies: fp32 path)
     if (L.width % 64 != 0 || L.width > 512 || L.width < 64) return false;
     if (L.n_layers + 4 > kMaxGemms) return false;
     if (p->n_samples > kMaxGroupPts) return false;
@@ -57,6 +57,26 @@ static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = fals
         g.fmt = fmt; g.has_vec = vec; g.tbl_off = tbl; tbl += g.N * (fmt == TF_F4 ? 4 : (fmt == TF_F1 ? 1 : 0));
         g.vec_off = tbl; if (vec) tbl += g.N;
     };
+    P->nerf = L.variant == SNB_NERF;
+    if (P->nerf) {
+        // models/nerf.py:184-227: every trunk layer is a GEMM (the encoded position is 60 wide: one extra K-slab of the A tile that
+        // layer 0 and the skip layer read), ReLU epilogues, biases on the aux K-step; sigma head folded into the last trunk layer;
+        // feats; rgb_from_xyzdir.0 with the encoded view direction as a per-ray bias
+        P->pe_xyz = L.in_xyz / 6; P->pe_dir = L.in_dir / 6; P->pe_slab = H / 64; P->a_slabs = H / 64 + 1;
+        P->l0_tbl = tbl;
+        for (int i = 0; i < L.n_layers; ++i) {
+            const bool skip = i == L.skip;
+            TcGemm& g = add(GK_TRUNK, H, i == 0 ? 64 : (skip ? H + 64 : H));
+            g.relu = 1; g.aux = 1; g.last = i == L.n_layers - 1; g.skip = 0;
+            g.src0 = L.trunk[i].w; g.ld0 = L.trunk[i].n_in; g.rows0 = H;
+            if (i == 0) { g.a_slab0 = P->pe_slab; g.col0 = 0; g.kvalid = L.in_xyz; }
+            else if (skip) { g.col0 = L.in_xyz; g.kvalid = H; g.k2_start = H; g.k2_cols = L.in_xyz; g.col_k2 = 0; }
+            else g.kvalid = H;
+            tables(g, TF_NONE, g.last);
+        }
+        { TcGemm& g = add(GK_FEAT, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; g.aux = 1; g.kvalid = H; tables(g, TF_NONE, 0); }
+        { TcGemm& g = add(GK_HEADN, H2, H); g.src0 = L.rgb0.w; g.ld0 = L.rgb0.n_in; g.rows0 = H2; g.kvalid = H; tables(g, TF_F4, 0); }
+    } else {
     P->l0_tbl = tbl; tbl += H * 4;
     P->l0_w = L.trunk[0].w; P->l0_b = L.trunk[0].b;
     for (int i = 1; i < L.n_layers; ++i) {
@@ -75,6 +95,8 @@ static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = fals
     { TcGemm& g = add(GK_SUN1, H2, H); g.src0 = L.sun[0].w; g.ld0 = L.sun[0].n_in; g.rows0 = H2; tables(g, TF_NONE, 0); }
     { TcGemm& g = add(GK_SUN2, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 0); }
     { TcGemm& g = add(GK_SUN3, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 1); }
+    }
+    for (int i = 0; i < ng; ++i) if (!P->g[i].kvalid) P->g[i].kvalid = P->g[i].K;
     P->n_gemms = ng;
     P->n_two = 0; P->n_store2 = 0;
     for (int i = 0; i < ng; ++i) {
@@ -84,11 +106,12 @@ static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = fals
         // have finished with (released slab by slab through slab_free[])
         const bool st = g.kind == GK_TRUNK || g.kind == GK_FEAT;
         g.store2_idx = P->n_store2; g.free_slabs = 0;
-        if (st && g.n_chunks == 2) { g.free_slabs = (g.chunk_n + 63) / 64; ++P->n_store2; }
+        // (a GEMM that does not read the low K-slabs -- nerf layer 0 -- has nothing to wait for: no slab_free phases)
+        if (st && g.n_chunks == 2 && g.a_slab0 == 0) { g.free_slabs = (g.chunk_n + 63) / 64; ++P->n_store2; }
     }
     // Early start of a GEMM's first K-slabs (see the kernel): after layer 0 / a two-chunk producer the low half of the
     // input tile is published before the high half; HEADA leaves the tile untouched, so SUN1 may start on all of it.
-    P->g[0].k_early = (H % 128 == 0 && H >= 256) ? H / 128 : 0;
+    P->g[0].k_early = (!P->nerf && H % 128 == 0 && H >= 256) ? H / 128 : 0;
     for (int i = 1; i < ng; ++i) {
         const TcGemm& pr = P->g[i - 1];
         const bool pr_stores = pr.kind == GK_TRUNK || pr.kind == GK_FEAT || pr.kind == GK_SUN1 || pr.kind == GK_SUN2;
@@ -104,7 +127,7 @@ static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = fals
     }
     if (dev_knobs().no_early) for (int i = 0; i < ng; ++i) P->g[i].k_early = 0;
     P->consts = tbl; tbl += 8;
-    P->sunw = tbl; tbl += 4 * H2;                 // [3][H2] weights + [H2] bias
+    P->sunw = tbl; tbl += (P->nerf ? L.in_dir + 1 : 4) * H2;      // [3][H2] weights + [H2] bias (nerf: [in_dir][H2] view-direction columns of rgb_from_xyzdir.0 + bias)
     P->betaw = tbl; tbl += (L.t_dims + 1) * H2;   // [tau][H2] weights + [H2] bias
     P->sky = tbl; tbl += 4 * H2 + 3 * H2 + 4;     // sky0 [H2][3]+b[H2] as [H2][4]; sky2 [3][H2]; b2[3]
     long long wbytes = 0; int max_stage = 0;
@@ -159,10 +182,14 @@ __global__ void tc_pack_kernel(TcProgram P, const float* __restrict__ W, unsigne
             const int nl = (int)(r % g.chunk_n); const long long t = r / g.chunk_n;
             const int s = (int)(t % g.k_slabs), j = (int)(t / g.k_slabs);
             const int n = j * g.chunk_n + nl, k0 = s * 64 + c * 8;
-            const float* src = n < g.rows0 ? W + g.src0 + (long long)n * g.ld0 + g.col0 + k0 : W + g.src1 + (long long)(n - g.rows0) * g.ld1 + g.col1 + k0;
+            const float* row = n < g.rows0 ? W + g.src0 + (long long)n * g.ld0 : W + g.src1 + (long long)(n - g.rows0) * g.ld1;
+            const int c0 = n < g.rows0 ? g.col0 : g.col1;
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = k0 + i < g.K ? src[i] : 0.f;
+            for (int i = 0; i < 8; ++i) {
+                const int k = k0 + i;
+                v[i] = k < g.kvalid ? row[c0 + k] : ((k >= g.k2_start && k < g.k2_start + g.k2_cols) ? row[g.col_k2 + k - g.k2_start] : 0.f);
+            }
             const size_t tile = (size_t)j * chunk_halves + (size_t)s * g.chunk_n * 64;
             *reinterpret_cast<uint4*>(out + tile + (size_t)nl * 64 + (size_t)((c ^ (nl & 7)) << 3)) =
                 make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
@@ -170,7 +197,7 @@ __global__ void tc_pack_kernel(TcProgram P, const float* __restrict__ W, unsigne
         // aux tile of every chunk: [chunk_n rows][16 k] fp16, 32-byte swizzle.  k = 0,1: bias hi, lo (fp16 pair: exact to 2^-22);
         // skip layer: k = 2..4 W_xyz hi (x A's xyz hi), 5..7 W_xyz hi (x xyz lo), 8..10 W_xyz lo (x xyz hi); the rest 0
         if (g.aux) {
-            const long long boff = g.kind == GK_FEAT ? g.src0 + (long long)g.N * g.ld0 : g.src0 + (long long)H * g.ld0;   // bias follows the weight block
+            const long long boff = g.src0 + (long long)g.N * g.ld0;   // bias follows the weight block (N x ld0)
             for (int e = tid; e < g.N * 16; e += nthr) {
                 const int n = e >> 4, k = e & 15, j = n / g.chunk_n, nl = n - j * g.chunk_n;
                 float v = 0.f;
@@ -196,12 +223,33 @@ __global__ void tc_pack_kernel(TcProgram P, const float* __restrict__ W, unsigne
 }
 
 struct MiscOffsets { long long sigma_w, sigma_b, rgb0_b, rgb2_w, rgb2_b, sun0_w, sun0_b, sun3_w, sun3_b, sky0_w, sky0_b, sky2_w, sky2_b,
-                               beta0_w, beta0_b, beta2_w, beta2_b; int sun0_ld, beta0_ld; };
+                               beta0_w, beta0_b, beta2_w, beta2_b, rgb0_w; int sun0_ld, beta0_ld, rgb0_ld; };
 
 __global__ void tc_pack_misc_kernel(TcProgram P, MiscOffsets M, const float* __restrict__ W, unsigned char* __restrict__ packed) {
     float* T = reinterpret_cast<float*>(packed + P.tables_base);
     const int H = P.H, H2 = P.H2;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (P.nerf) {
+        // sigma vector, rgb head table [0, w_r, w_g, w_b] per hidden unit, constants, view-direction columns + bias of rgb_from_xyzdir.0
+        const int nd = 6 * P.pe_dir;
+        for (int gi = 0; gi < P.n_gemms; ++gi) {
+            const TcGemm& g = P.g[gi];
+            if (g.kind == GK_TRUNK && g.last) for (int n = tid; n < H; n += nthr) T[g.vec_off + n] = W[M.sigma_w + n];
+            if (g.kind == GK_HEADN) for (int n = tid; n < H2; n += nthr) {
+                float* t = T + g.tbl_off + n * 4;
+                t[0] = 0.f; t[1] = W[M.rgb2_w + n]; t[2] = W[M.rgb2_w + H2 + n]; t[3] = W[M.rgb2_w + 2 * H2 + n];
+            }
+        }
+        if (tid == 0) {
+            float* c = T + P.consts;
+            c[0] = W[M.sigma_b]; c[1] = W[M.rgb2_b]; c[2] = W[M.rgb2_b + 1]; c[3] = W[M.rgb2_b + 2]; c[4] = c[5] = c[6] = c[7] = 0.f;
+        }
+        for (int n = tid; n < H2; n += nthr) {
+            for (int c = 0; c < nd; ++c) T[P.sunw + c * H2 + n] = W[M.rgb0_w + (long long)n * M.rgb0_ld + H + c];
+            T[P.sunw + nd * H2 + n] = W[M.rgb0_b + n];
+        }
+        return;
+    }
     // layer-0 table [H][4] = (wx, wy, wz, b)
     for (int n = tid; n < H; n += nthr) {
         float* t = T + P.l0_tbl + n * 4;
@@ -271,12 +319,30 @@ __device__ __forceinline__ void sin_cols(int dbg, float* v, unsigned char* yarr,
 }
 #define LDS_T(addr) ((TC_DBG(dbg) & 64) ? make_float4(0.f, 0.f, 0.f, 0.f) : lds128(addr, tok))
 template <int NC>
+__device__ __forceinline__ void relu_cols(float* v) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
+}
+template <int NC, bool NERF = false>
 __device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool skip, bool last, int has_beta, int n0, int H2, float* v,
                                           uint32_t a_base, int row, uint32_t tF, uint32_t tV, uint32_t sunb_row, uint32_t betab_row,
                                           float px, float py, float pz, const EpiStash& es, uint64_t* slab_bar, uint32_t slab_par,
                                           float& sig_dot, float& beta_dot, float& rgb0, float& rgb1, float& rgb2, float& sun_dot) {
     const int H = 2 * H2;
-    if (kind == GK_TRUNK) {          // bias (and the skip layer's xyz term) are already in the accumulator (aux K-step)
+    if (NERF && kind == GK_HEADN) {  // rgb_from_xyzdir.0 (nerf.py:172): + per-ray view-direction term and bias, ReLU, dot with the 3 x H2 output layer
+#pragma unroll
+        for (int i = 0; i < NC; i += 4) {
+            float4 b = LDS_T(sunb_row + (uint32_t)(n0 + i) * 4u);
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+        relu_cols<NC>(v);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            float4 w = LDS_T(tF + (uint32_t)(n0 + i) * 16u);
+            rgb0 = fmaf(w.y, v[i], rgb0); rgb1 = fmaf(w.z, v[i], rgb1); rgb2 = fmaf(w.w, v[i], rgb2);
+        }
+    } else if (kind == GK_TRUNK) {          // bias (and the skip layer's xyz term) are already in the accumulator (aux K-step)
+        if (NERF) relu_cols<NC>(v); else
         sin_cols<NC>(dbg, v, es.y0, es.gt, H, n0, row);
         if (last) {
 #pragma unroll
@@ -348,9 +414,9 @@ __device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool s
 // CG = 1: one CTA per 128-point tile.  CG = 2: CTA pair (cta_group::2): two SMs run two tiles in lockstep, the
 // leader issues M=256 MMAs that read each CTA's own activation tile and HALF of every weight tile from each
 // CTA's shared memory, so each SM streams / buffers only half of the weights.
-template <int CG, bool TRAIN>
-__global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps), 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
-    constexpr int EW = TRAIN ? kEpiWarpsTrain : kEpiWarps, ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
+template <int CG, bool TRAIN, bool NERF>
+__global__ void __launch_bounds__(64 + 32 * ((TRAIN || NERF) ? kEpiWarpsTrain : kEpiWarps), 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
+    constexpr int EW = (TRAIN || NERF) ? kEpiWarpsTrain : kEpiWarps, ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcProgram& P = A.prog;
@@ -447,7 +513,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
 #endif
                     for (int gi = 0; gi < P.n_gemms; ++gi) {
                         const int k_slabs = P.g[gi].k_slabs, n_chunks = P.g[gi].n_chunks, chunk_n = P.g[gi].chunk_n, K = P.g[gi].K;
-                        const int k_early = P.g[gi].k_early, free_slabs = P.g[gi].free_slabs, aux = P.g[gi].aux;
+                        const int k_early = P.g[gi].k_early, free_slabs = P.g[gi].free_slabs, aux = P.g[gi].aux, a_slab0 = P.g[gi].a_slab0;
                         const uint32_t idesc = CG == 2 ? umma_idesc_f16_m256((uint32_t)chunk_n) : umma_idesc_f16((uint32_t)chunk_n);
 #ifdef SNB_TC_PROGRESS
                         if (g_hang_host && blockIdx.x < 16 && lane == 0) ((volatile unsigned int*)g_hang_host)[64 + blockIdx.x * 8 + 3] = (unsigned)(wk << 16 | t << 8 | gi);
@@ -459,7 +525,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                                 if (j == 0 && s == k_early) mbar_wait(sm.a_ready2, ready_ph, 7);     // the rest of the input tile / accumulator columns of the later chunks
                                 const bool pair = deep && s + 1 < k_slabs && !(j == 0 && s + 1 == k_early);
                                 int st1 = st + 1; uint32_t ph1 = ph; if (st1 == P.n_stages) { st1 = 0; ph1 ^= 1; }
-                                const uint64_t da = a_desc0 + (uint64_t)((uint32_t)s * (kSlabBytes >> 4));
+                                const uint64_t da = a_desc0 + (uint64_t)((uint32_t)(a_slab0 + s) * (kSlabBytes >> 4));
                                 const uint64_t db = b_desc0 + (uint64_t)((uint32_t)st * stage_desc);
                                 const uint64_t db1 = b_desc0 + (uint64_t)((uint32_t)st1 * stage_desc);
                                 int ksteps = K - s * 64; ksteps = (ksteps > 64 ? 64 : ksteps) >> 4;
@@ -553,7 +619,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
         const uint32_t tm_row = tmem + ((uint32_t)(quad * 32) << 16);
         const uint32_t tF = smem_u32(sm.tblF), tV = smem_u32(sm.tblV);
         const int H = P.H, H2 = P.H2, S = A.S;
-        const int aux_col = 8;
+        const int aux_col = NERF ? 3 : 8;                // per-ray auxiliary direction in the ray row: sun (8:11), nerf: view direction (3:6)
         int tile_counter = 0;
         const uint32_t ready_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready), 0) : 0u;     // the leader's a_ready barriers
         const uint32_t ready2_bar = CG == 2 ? mapa_u32(smem_u32(sm.a_ready2), 0) : 0u;
@@ -577,8 +643,26 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
             const int n_rays = grp < A.n_groups ? min(A.G, A.R - r0) : 0;        // 0: this CTA only keeps the pair in lockstep
             const int Pg = n_rays * S;
             const int n_tiles = tiles_per_group;
+            if (NERF) {
+                // ---- nerf: encoded view direction (Mapping, nerf.py:60-66: per frequency sin(f d) then cos(f d), f = 2^j) and its
+                //      contribution to rgb_from_xyzdir.0 as a per-ray bias (the direction is constant along the ray) ----
+                const int nd = 6 * P.pe_dir;
+                for (int idx = tid_e; idx < n_rays * nd; idx += ET) {
+                    const int gr = idx / nd, k = idx - gr * nd, j = k / 6, f = k - 6 * j;
+                    const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
+                    const float arg = __fmul_rn((float)(1 << j), sd[f % 3]);
+                    sm.betab[gr * 64 + k] = f < 3 ? sinf(arg) : cosf(arg);
+                }
+                named_bar_sync(1, ET);
+                for (int idx = tid_e; idx < n_rays * H2; idx += ET) {
+                    const int gr = idx / H2, n = idx - gr * H2;
+                    float v = T[P.sunw + nd * H2 + n];
+                    for (int k = 0; k < nd; ++k) v = fmaf(T[P.sunw + k * H2 + n], sm.betab[gr * 64 + k], v);
+                    sm.sunb[gr * H2 + n] = v;
+                }
+            }
             // ---- per-ray tables: sun / embedding terms of the first head layers, sky colour ----
-            for (int idx = tid_e; idx < n_rays * H2; idx += ET) {
+            for (int idx = tid_e; !NERF && idx < n_rays * H2; idx += ET) {
                 int gr = idx / H2, n = idx - gr * H2;
                 const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
                 float v = T[P.sunw + 3 * H2 + n];
@@ -591,7 +675,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                     sm.betab[gr * H2 + n] = b;
                 }
             }
-            for (int gr = warp - 2; gr < n_rays; gr += EW) {          // sky_color(sun_d): per ray (satnerf.py:201)
+            for (int gr = warp - 2; !NERF && gr < n_rays; gr += EW) {          // sky_color(sun_d): per ray (satnerf.py:201)
                 const float* sd = A.aux ? A.aux + (size_t)(r0 + gr) * 3 : A.rays + (size_t)(r0 + gr) * A.ray_cols + aux_col;
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
                 for (int n = lane; n < H2; n += 32) {
@@ -648,13 +732,30 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                 }
                 const uint32_t sunb_row = smem_u32(sm.sunb) + (uint32_t)(rl * H2) * 4u;
                 const uint32_t betab_row = smem_u32(sm.betab) + (uint32_t)(rl * H2) * 4u;
+                const int l0_split = NERF ? 0 : P.g[0].k_early * 64;         // columns published with the first ready signal (0: none)
+                if (NERF) {
+                    // ---- nerf: the encoded position (Mapping, nerf.py:60-66; 6 * pe_xyz <= 64 values, the rest 0) as fp16 into the
+                    //      extra K-slab of the A tile; trunk layer 0 is the first GEMM ----
+                    named_bar_sync(1, ET);                        // (the previous tile's scratch reads of the A tile are done)
+                    const int nx = 6 * P.pe_xyz;
+                    const float pc[3] = {px, py, pz};
+                    for (int c = half; c < 8; c += ES) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int k = c * 8 + i, j = k / 6, f = k - 6 * j;
+                            const float arg = __fmul_rn((float)(1 << j), f % 3 == 0 ? pc[0] : (f % 3 == 1 ? pc[1] : pc[2]));
+                            v[i] = k < nx ? (f < 3 ? sinf(arg) : cosf(arg)) : 0.f;
+                        }
+                        sts128(a_chunk_addr(a_base, row, P.pe_slab * 64 + c * 8), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+                    }
+                } else {
                 // ---- trunk layer 0 on CUDA cores: sin(30 (W0 x + b0)), K = 3 (satnerf.py:105-106) ----
                 if (half == 0) { sm.wt[row] = px; sm.wt[kTile + row] = py; sm.wt[2 * kTile + row] = pz; }     // positions of the tile's points
                 table_copy<ET>(sm.tblF, T + P.l0_tbl, H * 16, tid_e);
                 cp_async_wait_all();
                 named_bar_sync(1, ET);
                 const uint32_t tok0 = fresh_token(0xffffu);
-                const int l0_split = P.g[0].k_early * 64;         // columns published with the first ready signal (0: none)
                 // Thread mapping of this layer: 4 rows (lane + 32k) x 8 columns per step, so that one 16-byte table read
                 // ([wx wy wz b] of a column: a 512-byte register fill per warp) feeds 4 outputs instead of 1 -- with one row per
                 // thread the table reads alone took ~8 000 cycles of the shared-memory pipe per tile.
@@ -689,6 +790,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                         // complete), so each group has half a layer to drain before its slabs are rewritten
                         if (sb && tid_e == 0) { bulk_s2g(sb + A.stash.a[0] + (size_t)gt * P.a_slabs * kSlabBytes, sm.a, (uint32_t)(l0_split >> 6) * kSlabBytes); bulk_commit(); }
                     }
+                }
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, ET);                  // the whole input tile of the first GEMM is in place; layer-0 table dead
@@ -789,27 +891,28 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                             int n0 = ch * chunk_n + half * 32;
                             bool have = n0 < n_end;
                             uint32_t va[16], vb[16];
-                            uint64_t* const slab_bar = (stores && !final_chunk) ? sm.slab_free : nullptr;
+                            uint64_t* const slab_bar = (stores && !final_chunk && g.free_slabs > 0) ? sm.slab_free : nullptr;      // (free_slabs = 0: the GEMM does not read the slabs chunk 0 rewrites)
                             const uint32_t slab_par = (uint32_t)((tile_counter - 1) * P.n_store2 + g.store2_idx) & 1u;
                             // (the plain trunk layers -- 6 of the 12 GEMMs -- take a copy of the loop with the layer kind as a compile-time
                             //  constant: the epilogue is bound by instruction issue, and the per-call kind dispatch is ~5 % of its instructions)
-#define SNB_BLOCK_LOOP(KIND, LAST)                                                                                                                    \
+#define SNB_BLOCK_LOOP(KIND, LAST, NERF_)                                                                                                             \
                             if (have) tmem_ld16(tm_row + (uint32_t)n0, va);                                                                           \
                             while (have) {                                                                                                            \
                                 tmem_ld_wait16(va);                                                                                                   \
                                 tmem_ld16(tm_row + (uint32_t)(n0 + 16), vb);                                                                          \
-                                epi_cols<16>(tok, A.dbg, KIND, skip, LAST, P.has_beta, n0, H2, reinterpret_cast<float*>(va), a_base, row, tF, tV, sunb_row, betab_row, \
+                                epi_cols<16, NERF_>(tok, A.dbg, KIND, skip, LAST, P.has_beta, n0, H2, reinterpret_cast<float*>(va), a_base, row, tF, tV, sunb_row, betab_row, \
                                              px, py, pz, es, slab_bar, slab_par, sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);                       \
                                 tmem_ld_wait16(vb);                                                                                                   \
                                 const int n1 = n0 + 32 * ES;                                                                                     \
                                 const bool more = n1 < n_end;                                                                                         \
                                 if (more) tmem_ld16(tm_row + (uint32_t)n1, va);                                                                       \
-                                epi_cols<16>(tok, A.dbg, KIND, skip, LAST, P.has_beta, n0 + 16, H2, reinterpret_cast<float*>(vb), a_base, row, tF, tV, sunb_row, betab_row, \
+                                epi_cols<16, NERF_>(tok, A.dbg, KIND, skip, LAST, P.has_beta, n0 + 16, H2, reinterpret_cast<float*>(vb), a_base, row, tF, tV, sunb_row, betab_row, \
                                              px, py, pz, es, slab_bar, slab_par, sig_dot, beta_dot, rgb0, rgb1, rgb2, sun_dot);                       \
                                 n0 = n1; have = more;                                                                                                 \
                             }
-                            if (kind == GK_TRUNK && !last) { SNB_BLOCK_LOOP(GK_TRUNK, false) }
-                            else { SNB_BLOCK_LOOP(kind, last) }
+                            if (NERF) { SNB_BLOCK_LOOP(kind, last, true) }
+                            else if (kind == GK_TRUNK && !last) { SNB_BLOCK_LOOP(GK_TRUNK, false, false) }
+                            else { SNB_BLOCK_LOOP(kind, last, false) }
 #undef SNB_BLOCK_LOOP
                         }
                         if (!final_chunk) {
@@ -869,6 +972,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                         const float* d = reinterpret_cast<const float*>(sm.a) + (size_t)((h2 * kTile + row) * 8);
                         sig_dot += d[0]; beta_dot += d[1]; rgb0 += d[2]; rgb1 += d[3]; rgb2 += d[4]; sun_dot += d[5];
                     }
+                    if (NERF) { sun_dot = 0.f; beta_dot = 0.f; }
                     sm.sg[p] = softplus_f(sig_dot + sm.consts[0]);                                    // satnerf.py:183
                     sm.al0[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb0 + sm.consts[1]), 1.002f), 0.001f);  // :193-195
                     sm.al1[p] = __fsub_rn(__fmul_rn(sigmoid_f(rgb1 + sm.consts[2]), 1.002f), 0.001f);
@@ -879,6 +983,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                     // from the one warp per ray that composites
                     const size_t gp = (size_t)r0 * S + p;
                     if (A.sigma) A.sigma[gp] = sm.sg[p];
+                    if (NERF && A.nerf_rgb) { A.nerf_rgb[gp * 3] = sm.al0[p]; A.nerf_rgb[gp * 3 + 1] = sm.al1[p]; A.nerf_rgb[gp * 3 + 2] = sm.al2[p]; }
                     if (A.sun) A.sun[gp] = sm.sn[p];
                     if (A.beta && P.has_beta) A.beta[gp] = sm.bt[p];
                     if (A.albedo) { A.albedo[gp * 3] = sm.al0[p]; A.albedo[gp * 3 + 1] = sm.al1[p]; A.albedo[gp * 3 + 2] = sm.al2[p]; }
@@ -893,7 +998,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                 const int ray = r0 + gr;
                 float carry = 1.f, depth = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
                 float xs = 0.f, xa0 = 0.f, xa1 = 0.f, xa2 = 0.f, xb = 0.f, xw = 0.f;      // sum w*{sun, albedo, beta, 1} (aux_sums)
-                const float k0 = sm.skyc[gr * 4], k1 = sm.skyc[gr * 4 + 1], k2 = sm.skyc[gr * 4 + 2];
+                const float k0 = NERF ? 0.f : sm.skyc[gr * 4], k1 = NERF ? 0.f : sm.skyc[gr * 4 + 1], k2 = NERF ? 0.f : sm.skyc[gr * 4 + 2];
                 for (int b0 = 0; b0 < S; b0 += 32) {
                     const int i = b0 + lane, p = gr * S + i;
                     const bool ok = i < S;
@@ -919,7 +1024,7 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                         const size_t gp = (size_t)ray * S + i;
                         if (A.weights) A.weights[gp] = w;
                         if (A.transparency) A.transparency[gp] = Tr;
-                        const float s = sm.sn[p];
+                        const float s = NERF ? 1.f : sm.sn[p];                  // nerf: rgb = sum w * rgb_i (nerf.py:128): irradiance factor 1
                         depth = fmaf(w, zi, depth);
                         c0 += w * sm.al0[p] * (s + (1.f - s) * k0);
                         c1 += w * sm.al1[p] * (s + (1.f - s) * k1);
@@ -946,7 +1051,8 @@ __global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsTrain : kEpiWarps)
                 }
                 if (lane == 0) {
                     if (A.depth) A.depth[ray] = depth;
-                    if (A.rgb) { A.rgb[ray * 3] = fminf(fmaxf(c0, 0.f), 1.f); A.rgb[ray * 3 + 1] = fminf(fmaxf(c1, 0.f), 1.f); A.rgb[ray * 3 + 2] = fminf(fmaxf(c2, 0.f), 1.f); }
+                    if (A.rgb && NERF) { A.rgb[ray * 3] = c0; A.rgb[ray * 3 + 1] = c1; A.rgb[ray * 3 + 2] = c2; }      // (no clamp in nerf's inference)
+                    else if (A.rgb) { A.rgb[ray * 3] = fminf(fmaxf(c0, 0.f), 1.f); A.rgb[ray * 3 + 1] = fminf(fmaxf(c1, 0.f), 1.f); A.rgb[ray * 3 + 2] = fminf(fmaxf(c2, 0.f), 1.f); }
                 }
             }
             named_bar_sync(1, ET);                      // group tables are reused by the next group
@@ -1045,11 +1151,11 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     A.params = io->params; A.rays = io->rays; A.z = io->z_vals; A.t_emb = io->t_emb; A.noise = p->noise_std != 0.f ? io->noise : nullptr;
     A.noise_std = p->noise_std; A.xyz = io->xyz; A.aux = io->aux_dir;
     A.rgb = io->rgb; A.depth = io->depth; A.weights = io->weights; A.transparency = io->transparency; A.albedo = io->albedo;
-    A.sun = io->sun; A.sky = io->sky; A.beta = io->beta; A.sigma = io->sigma; A.aux_sums = io->aux_sums; A.t_min = p->t_min;
+    A.sun = io->sun; A.sky = io->sky; A.beta = io->beta; A.sigma = io->sigma; A.aux_sums = io->aux_sums; A.t_min = p->t_min; A.nerf_rgb = io->nerf_rgb;
     A.packed = (unsigned char*)workspace;
     A.R = p->n_rays; A.S = p->n_samples; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
     A.G = choose_group(A.S); A.n_groups = (A.R + A.G - 1) / A.G;
-    A.stash_base = (unsigned char*)io->stash;
+    A.stash_base = L.variant == SNB_NERF ? nullptr : (unsigned char*)io->stash;      // (nerf: no tensor-core backward, nothing to stash)
     if (A.stash_base) { int tpg = (A.G * A.S + kTile - 1) / kTile; stash_layout(L, A.n_groups * tpg, tpg, &A.stash); }
     A.dbg = dev_knobs().dbg;
 
@@ -1058,6 +1164,7 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     M.sun0_w = L.sun[0].w; M.sun0_b = L.sun[0].b; M.sun0_ld = L.sun[0].n_in; M.sun3_w = L.sun[3].w; M.sun3_b = L.sun[3].b;
     M.sky0_w = L.sky0.w; M.sky0_b = L.sky0.b; M.sky2_w = L.sky2.w; M.sky2_b = L.sky2.b;
     M.beta0_w = L.beta0.w; M.beta0_b = L.beta0.b; M.beta0_ld = L.beta0.n_in; M.beta2_w = L.beta2.w; M.beta2_b = L.beta2.b;
+    M.rgb0_w = L.rgb0.w; M.rgb0_ld = L.rgb0.n_in;
 
     if (!p->weights_packed) {      // (caller's promise otherwise: same parameter values, workspace untouched since we packed them)
         tc_pack_kernel<<<dim3(64, P.n_gemms), 256, 0, st>>>(P, io->params, A.packed);
@@ -1067,11 +1174,11 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
     }
     const bool train = A.stash_base != nullptr;
     if (cg == 2) {
-        auto kern = train ? tc_render_kernel<2, true> : tc_render_kernel<2, false>;
+        auto kern = P.nerf ? tc_render_kernel<2, false, true> : (train ? tc_render_kernel<2, true, false> : tc_render_kernel<2, false, false>);
         SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n_pairs = (A.n_groups + 1) / 2, max_pairs = sm_count / 2;
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(64 + 32 * (train ? kEpiWarpsTrain : kEpiWarps));
+        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(64 + 32 * ((train || P.nerf) ? kEpiWarpsTrain : kEpiWarps));
         cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1079,10 +1186,10 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         SNB_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
         ++g_launches;
     } else {
-        auto kern = train ? tc_render_kernel<1, true> : tc_render_kernel<1, false>;
+        auto kern = P.nerf ? tc_render_kernel<1, false, true> : (train ? tc_render_kernel<1, true, false> : tc_render_kernel<1, false, false>);
         SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = A.n_groups < sm_count ? A.n_groups : sm_count;
-        kern<<<grid, 64 + 32 * (train ? kEpiWarpsTrain : kEpiWarps), smem, st>>>(A);
+        kern<<<grid, 64 + 32 * ((train || P.nerf) ? kEpiWarpsTrain : kEpiWarps), smem, st>>>(A);
         SNB_CHECK_LAUNCH();
     }
     return 0;
