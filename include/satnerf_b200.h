@@ -201,6 +201,15 @@ SNB_API int snb_field_forward(const snb_field_desc* f, const float* params, cons
                       const float* aux_dir, const float* t_emb, float* out, int n_points,
                       int sigma_only, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradient of snb_field_forward (autograd of <Field>.forward, satnerf.py:156-208): d_out (B,C | B,1) = gradient w.r.t. the
+ * outputs, out = the outputs the forward returned; ACCUMULATES into g_params (flat, like the parameters) and writes g_t_emb
+ * (B,t_dims; optional).  fp32 CUDA-core path (the forward is recomputed chunk by chunk with its buffers kept).  No gradient
+ * w.r.t. xyz / directions (the render path never needs one).                                                          */
+SNB_API int snb_field_backward_workspace(const snb_field_desc* f, int n_points, size_t* bytes);
+SNB_API int snb_field_backward(const snb_field_desc* f, const float* params, const float* xyz, const float* aux_dir, const float* t_emb,
+                       const float* out, const float* d_out, float* g_params, float* g_t_emb, int n_points, int sigma_only,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- geometry either side of the render path -------------------------------------------------
  * RPC camera model of one satellite image: the fields of rpcm.RPCModel (projection coefficients in RPC00B order; the
  * reference builds it from the image's json, datasets/satellite.py:191) after sat_utils.rescale_rpc.                  */

@@ -82,6 +82,9 @@ _SIGNATURES = {
     "snb_loss_forward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_loss_backward": (C.c_int, [C.POINTER(PassDesc), C.POINTER(RenderIO), C.POINTER(LossDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "snb_field_backward_workspace": (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.POINTER(C.c_size_t)]),
+    "snb_field_backward": (C.c_int, [C.POINTER(FieldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_rpc_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double, C.c_void_p, C.c_double,
                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "snb_dsm_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -321,3 +324,16 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
         _check(lib().snb_adam_step(C.c_void_p(params.data_ptr()), C.c_void_p(grads.data_ptr()), C.c_void_p(exp_avg.data_ptr()),
                                    C.c_void_p(exp_avg_sq.data_ptr()), params.numel(), lr, beta1, beta2, eps, weight_decay, int(step),
                                    _stream(params.device)), "snb_adam_step")
+
+
+def field_backward(desc: FieldDesc, params, xyz, aux_dir, t_emb, out, d_out, g_params, sigma_only: bool):
+    """Accumulates d(loss)/d(params) of <Field>.forward into g_params (flat); returns d(loss)/d(input_t) (B,tau) or None."""
+    B = xyz.shape[0]
+    g_t = torch.empty_like(t_emb) if (t_emb is not None and not sigma_only) else None
+    n = C.c_size_t(0)
+    with torch.cuda.device(xyz.device):
+        _check(lib().snb_field_backward_workspace(C.byref(desc), B, C.byref(n)), "snb_field_backward_workspace")
+        ws = _workspace(xyz.device, n.value)
+        _check(lib().snb_field_backward(C.byref(desc), _ptr(params), _ptr(xyz), _ptr(aux_dir), _ptr(t_emb), _ptr(out), _ptr(d_out), _ptr(g_params),
+                                        _ptr(g_t), B, int(sigma_only), C.c_void_p(ws.data_ptr()), ws.numel(), _stream(xyz.device)), "snb_field_backward")
+    return g_t

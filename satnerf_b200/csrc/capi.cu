@@ -219,6 +219,64 @@ extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* p
     return 0;
 }
 
+// d(loss)/d(pre-activation head outputs) from d(loss)/d(outputs) and the outputs themselves (satnerf.py:183-206): softplus' =
+// 1 - exp(-out), sigmoid' = s (1 - s), the colour padding contributes 1.002 (rgb = s * 1.002 - 0.001)
+__global__ void field_head_grad_kernel(const float* __restrict__ d_out, const float* __restrict__ out, float* __restrict__ d_head, long long n_points,
+                                       int C, int sigma_only) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_points * C; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / C; const int c = (int)(i - p * C);
+        float g = 0.f;
+        if (sigma_only) { if (c == 3) { const float o = out[p]; g = d_out[p] * (1.f - expf(-o)); } }
+        else {
+            const float o = out[i], d = d_out[i];
+            if (c < 3) { const float sgm = (o + 0.001f) / 1.002f; g = d * 1.002f * sgm * (1.f - sgm); }
+            else if (c == 3 || c == 8) g = d * (1.f - expf(-o));
+            else g = d * o * (1.f - o);
+        }
+        d_head[i] = g;
+    }
+}
+
+extern "C" SNB_API int snb_field_backward_workspace(const snb_field_desc* f, int n_points, size_t* bytes) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L));
+    if (!bytes || n_points < 0) SNB_FAIL(-1, "snb_field_backward_workspace: bad arguments");
+    int pc = n_points < kChunkPoints ? (n_points > 0 ? n_points : 1) : kChunkPoints;
+    Arena ar(nullptr, 0); FieldChunk c; c.plan(ar, L, pc, pc, true);
+    ar.take<float>((size_t)pc * L.n_channels * 2);
+    *bytes = ar.off + 512;
+    return 0;
+}
+
+extern "C" SNB_API int snb_field_backward(const snb_field_desc* f, const float* params, const float* xyz, const float* aux_dir, const float* t_emb,
+                                          const float* out, const float* d_out, float* g_params, float* g_t_emb, int n_points, int sigma_only,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+    FieldLayout L; SNB_TRY(build_layout(f, &L));
+    if (!params || !xyz || !out || !d_out || !g_params || n_points < 0) SNB_FAIL(-1, "snb_field_backward: bad arguments");
+    if (!aux_dir && L.variant != SNB_NERF) SNB_FAIL(-1, "snb_field_backward: input_sun_dir is required");
+    if (!aux_dir && L.variant == SNB_NERF && L.in_dir) SNB_FAIL(-1, "snb_field_backward: input_dir is required");
+    if (L.t_dims && !t_emb) SNB_FAIL(-1, "snb_field_backward: input_t is required");
+    if (n_points == 0) return 0;
+    if (!workspace) SNB_FAIL(-1, "snb_field_backward: null workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pc = n_points < kChunkPoints ? n_points : kChunkPoints, C = L.n_channels, Co = sigma_only ? 1 : C;
+    Arena ar(workspace, workspace_bytes); FieldChunk c; c.plan(ar, L, pc, pc, true);
+    float* raw = ar.take<float>((size_t)pc * C);
+    float* d_head = ar.take<float>((size_t)pc * C);
+    if (ar.overflow) SNB_FAIL(-4, "snb_field_backward: workspace too small");
+    for (int p0 = 0; p0 < n_points; p0 += pc) {
+        const int n = n_points - p0 < pc ? n_points - p0 : pc;
+        FieldInputs in; in.n_points = n;
+        in.xyz = Src{xyz + (size_t)p0 * 3, 3, 3, 1};
+        in.aux = aux_dir ? Src{aux_dir + (size_t)p0 * 3, 3, 3, 1} : Src{nullptr, 0, 0, 1};
+        in.temb = (L.t_dims && t_emb) ? Src{t_emb + (size_t)p0 * L.t_dims, L.t_dims, L.t_dims, 1} : Src{nullptr, 0, 0, 1};
+        SNB_TRY(field_forward_chunk(L, params, c, in, raw, false, st));            // recompute with the per-layer buffers kept
+        field_head_grad_kernel<<<148 * 4, 256, 0, st>>>(d_out + (size_t)p0 * Co, out + (size_t)p0 * Co, d_head, n, C, sigma_only);
+        SNB_CHECK_LAUNCH();
+        SNB_TRY(field_backward_chunk(L, params, g_params, c, in, d_head, (L.t_dims && g_t_emb) ? g_t_emb + (size_t)p0 * L.t_dims : nullptr, 1, st));
+    }
+    return 0;
+}
+
 #ifdef SNB_DEV_BUILD
 #include "satnerf_b200_dev.h"
 // Developer aid (libsatnerf_b200_dev.so only): phase timestamps recorded by the fused kernel (see tc_field.cu); host buffer of int64.

@@ -185,8 +185,44 @@ class _Field(nn.Module):
                 raise TypeError("direction input is required" if self.variant == "nerf" else "input_sun_dir is required")
             if self.variant == "sat-nerf" and input_t is None:
                 raise TypeError("sat-nerf needs input_t (torch.cat with None in the reference, models/satnerf.py:204)")
-        return capi.field_forward(self._desc, self.flat_params(), f32(input_xyz), f32(aux), f32(input_t),
-                                  sigma_only, self.number_of_outputs)
+        xyz, aux_, t_ = f32(input_xyz), f32(aux), f32(input_t)
+        if sigma_only and aux_ is None:
+            aux_ = torch.zeros_like(xyz)                     # (unused by the sigma head; the backward's buffers want a direction)
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or (input_t is not None and input_t.requires_grad))
+        if not needs_grad:
+            return capi.field_forward(self._desc, self.flat_params(), xyz, aux_, t_, sigma_only, self.number_of_outputs)
+        if sigma_only and self.variant == "sat-nerf" and t_ is None:
+            t_ = torch.zeros(xyz.shape[0], self._desc.t_dims, device=xyz.device)
+        t_in = input_t if (input_t is not None and not sigma_only) else None
+        return _PointsFn.apply(self, xyz, aux_, t_, sigma_only, t_in, *self.ordered_params())
+
+
+class _PointsFn(torch.autograd.Function):
+    """<Field>.forward on B points, differentiable w.r.t. the field parameters and input_t (models/satnerf.py:156-208 under
+    autograd).  fp32 CUDA-core path: the backward recomputes the forward chunk by chunk (snb_field_backward).  No gradient flows
+    to input_xyz / the directions -- the reference's training never asks for one (rays are data)."""
+
+    @staticmethod
+    def forward(ctx, field, xyz, aux, t_emb, sigma_only, t_in, *params):
+        out = capi.field_forward(field._desc, field.flat_params(), xyz, aux, t_emb, sigma_only, field.number_of_outputs)
+        ctx.field, ctx.sigma_only, ctx.has_t = field, sigma_only, t_in is not None
+        ctx.save_for_backward(xyz, aux, out, *([t_emb] if t_emb is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        field = ctx.field
+        xyz, aux, out, *rest = ctx.saved_tensors
+        t_emb = rest[0] if rest else None
+        flat = field.flat_params()
+        g_flat = torch.zeros_like(flat)
+        g_t = capi.field_backward(field._desc, flat, xyz, aux, t_emb, out, d_out.to(torch.float32).contiguous(), g_flat, ctx.sigma_only)
+        gp, off = [], 0
+        for p in field.ordered_params():
+            n = p.numel()
+            gp.append(g_flat[off:off + n].view(p.shape))
+            off += n
+        return (None, None, None, None, None, g_t if ctx.has_t else None, *gp)
 
 
 class NeRF(_Field):

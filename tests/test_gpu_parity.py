@@ -242,6 +242,51 @@ def test_field_forward_matches_oracle():
     assert sig.shape == (333, 1) and rel_err(sig.cpu(), want[:, 3:4]) < 2e-5
 
 
+@pytest.mark.parametrize("model", ["sat-nerf", "s-nerf", "nerf"])
+def test_field_forward_is_differentiable(model):
+    """<Field>.forward under autograd (models/satnerf.py:156-208, snerf.py:148-196, nerf.py:184-227): parameter gradients and the
+    input_t gradient against float64 autograd of the oracle's field.  fp32 path: 2e-4 of each tensor's max |grad|."""
+    import satnerf_b200 as sb
+    args = make_args(model=model, fc_units=64)
+    torch.manual_seed(15)
+    m = sb.load_model(args)
+    p64 = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(16)
+    B = 257
+    xyz, aux, t = torch.rand(B, 3, generator=g) * 2 - 1, torch.rand(B, 3, generator=g), torch.randn(B, 4, generator=g)
+    C = m.number_of_outputs
+    wgt = torch.randn(B, C, generator=g)
+    t64 = t.double().requires_grad_(True)
+    if model == "nerf":
+        want = orc.field_nerf(p64, xyz.double(), aux.double())
+    else:
+        want = orc.field_satnerf(p64, xyz.double(), aux.double(), t64 if model == "sat-nerf" else None, with_beta=model == "sat-nerf")
+    (want * wgt.double()).sum().backward()
+    m = m.cuda()
+    tc = t.cuda().requires_grad_(True)
+    if model == "nerf":
+        got = m(xyz.cuda(), input_dir=aux.cuda())
+    elif model == "s-nerf":
+        got = m(xyz.cuda(), input_sun_dir=aux.cuda())
+    else:
+        got = m(xyz.cuda(), input_sun_dir=aux.cuda(), input_t=tc)
+    assert got.requires_grad and rel_err(got.detach().cpu(), want.detach().float()) < 2e-5
+    (got * wgt.cuda()).sum().backward()
+    for name, prm in m.named_parameters():
+        ref = p64[name].grad
+        err = float((prm.grad.cpu().double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        assert err < 2e-4, (name, err)
+    if model == "sat-nerf":
+        err = float((tc.grad.cpu().double() - t64.grad).abs().max() / t64.grad.abs().max())
+        assert err < 2e-4, err
+    # sigma_only under autograd: only the trunk and the sigma head receive gradients
+    m.zero_grad(set_to_none=True)
+    sig = m(xyz.cuda(), sigma_only=True)
+    sig.sum().backward()
+    names = dict(m.named_parameters())
+    assert float(names["sigma_from_xyz.0.weight"].grad.abs().max()) > 0 and float(names["rgb_from_xyzdir.0.weight"].grad.abs().max()) == 0
+
+
 @pytest.mark.parametrize("model,h,n_rays,S", [("sat-nerf", 128, 50, 64), ("sat-nerf", 256, 33, 96), ("s-nerf", 128, 20, 64), ("sat-nerf", 384, 17, 48)])
 def test_tc_backward_matches_fp64_oracle(model, h, n_rays, S):
     """Tensor-core backward (fused input-gradient chain + split-K weight-gradient GEMMs, fp16 gradients with a loss scale)
