@@ -36,8 +36,6 @@ struct TcBwdArgs {
     const float* absmax;                          // device scalar: max |d_head|
     float* d_t;                                   // (P, tau) fp32, unscaled; or null
     unsigned char* packed;
-    const float *rays, *z, *xyz;                  // sample positions (layer 0's pre-activation is recomputed from them)
-    int ray_cols, dir_col;
     int n_layers, R, S, G, n_groups, tiles_per_group;
     int dbg;                                      // developer what-if knobs (dev library only, see tc_common.cuh)
 };
@@ -78,7 +76,7 @@ __global__ void tc_bwd_pack_kernel(TcProgram P, const float* __restrict__ W, uns
     }
 }
 
-struct BwdMisc { long long s3_w, r2_w, b2_w, b0_w, sigma_w, l0_w, l0_b; int b0_ld, H, H2, tau, has_beta; int t_seed, t_r2, t_beta, t_betav, t_sigma, t_l0; };
+struct BwdMisc { long long s3_w, r2_w, b2_w, b0_w, sigma_w; int b0_ld, H, H2, tau, has_beta; int t_seed, t_r2, t_beta, t_betav, t_sigma; };
 
 __global__ void tc_bwd_tables_kernel(BwdMisc M, long long tables_base, const float* __restrict__ W, unsigned char* __restrict__ packed) {
     float* T = reinterpret_cast<float*>(packed + tables_base);
@@ -96,8 +94,6 @@ __global__ void tc_bwd_tables_kernel(BwdMisc M, long long tables_base, const flo
     }
     for (int n = tid; n < M.H; n += nthr) {
         T[M.t_sigma + n] = W[M.sigma_w + n];
-        float* t = T + M.t_l0 + n * 4;                                         // trunk layer 0: [wx wy wz b] (its pre-activation is recomputed)
-        t[0] = W[M.l0_w + n * 3]; t[1] = W[M.l0_w + n * 3 + 1]; t[2] = W[M.l0_w + n * 3 + 2]; t[3] = W[M.l0_b + n];
     }
 }
 
@@ -121,17 +117,29 @@ __device__ __forceinline__ YBuf yb_load(const unsigned char* arr, int gt, int F,
 }
 __device__ __forceinline__ YBuf yb_zero() { YBuf b; for (int c = 0; c < 4; ++c) b.q[c] = make_uint4(0u, 0u, 0u, 0u); return b; }
 // v[i] *= mul * cos(y_i), i < 16: y = columns [16 * hf, 16 * hf + 16) of a 32-column y block
-// (every stashed layer has w0 = 1: the derivative factor is cos(y) alone)
+// v[i] *= c_i, i < 16: c = the stashed activation derivatives of columns [16 * hf, 16 * hf + 16) of a 32-column block
 __device__ __forceinline__ void mul_cos16(float* v, const YBuf& b, int hf) {
     const __half2* h = reinterpret_cast<const __half2*>(&b.q[2 * hf]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float2 y = __half22float2(h[i]);
-        v[2 * i] *= __cosf(y.x);
-        v[2 * i + 1] *= __cosf(y.y);
+        const float2 c = __half22float2(h[i]);
+        v[2 * i] *= c.x; v[2 * i + 1] *= c.y;
     }
 }
 __device__ __forceinline__ void mul_cos32(float* v, const YBuf& b) { mul_cos16(v, b, 0); mul_cos16(v + 16, b, 1); }
+// The common case: the 16 fp32 accumulator values go to the next dY tile as fp16(v) * c -- one pack and one packed half multiply
+// per pair (two roundings of 2^-11 instead of one; the tile is fp16 anyway), stored straight into the swizzled A tile.
+__device__ __forceinline__ void store_mul_cos16(uint32_t a_base, int row, int c0, const float* v, const YBuf& b, int hf) {
+    const __half2* h = reinterpret_cast<const __half2*>(&b.q[2 * hf]);
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const __half2 p = __hmul2(__floats2half2_rn(v[2 * i], v[2 * i + 1]), h[i]);
+        o[i] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    sts128(a_chunk_addr(a_base, row, c0), o[0], o[1], o[2], o[3]);
+    sts128(a_chunk_addr(a_base, row, c0 + 8), o[4], o[5], o[6], o[7]);
+}
 
 // The chain kernel follows the forward's tile pipeline (tc_pipeline.cuh): CTA pairs (CG = 2) or single CTAs, 4-deep half-stage
 // weight ring, two N-chunks per GEMM with the epilogue of chunk 0 under the MMAs of chunk 1, direct stores into released
@@ -146,7 +154,7 @@ __device__ __forceinline__ void mul_cos32(float* v, const YBuf& b) { mul_cos16(v
 //   FB     D += A W_b0[:, :H] ;  A = D                                                          -> dump d feat
 //   A7     D = A W_feats ;  A = (D + g_sigma w_sigma) cos(y_7)                                  -> dump d y_7
 //   TRUNK  l = L-1 .. 1:  D = A W_l[:, skip:] ;  A = D w0_{l-1} cos(y_{l-1})                    -> dump d y_{l-1}
-// (y_0 = 30 (W_0 x + b_0) is recomputed from the sample position; every other y comes from the forward's fp16 stash.)
+// (cos(y) stands for the stashed activation derivative: cos(y), and 30 cos(30 y) for trunk layer 0.)
 template <int CG>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(const __grid_constant__ TcBwdArgs A) {
     constexpr int EW = kEpiWarpsTrain, ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
@@ -212,20 +220,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                 const int gt = grp * tpg + t;
                 const int p = t * kTile + row;
                 const bool valid = p < Pg;
-                float g0 = 0.f, g1 = 0.f, g2 = 0.f, gsig = 0.f, gsun = 0.f, gbeta = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, gsig = 0.f, gsun = 0.f, gbeta = 0.f;
                 if (valid) {
                     const size_t gp = (size_t)r0 * S + p;
                     const float* dh = A.d_head + gp * A.C;
                     g0 = dh[0] * scale; g1 = dh[1] * scale; g2 = dh[2] * scale; gsig = dh[3] * scale; gsun = dh[4] * scale;
                     if (P.has_beta) gbeta = dh[8] * scale;
-                    if (A.xyz) { px = A.xyz[gp * 3]; py = A.xyz[gp * 3 + 1]; pz = A.xyz[gp * 3 + 2]; }
-                    else {
-                        const float zz = A.z[gp];
-                        const float* ray = A.rays + (size_t)(r0 + p / S) * A.ray_cols;       // same rounding as the forward (rendering.py:81)
-                        px = __fadd_rn(ray[0], __fmul_rn(ray[A.dir_col], zz));
-                        py = __fadd_rn(ray[1], __fmul_rn(ray[A.dir_col + 1], zz));
-                        pz = __fadd_rn(ray[2], __fmul_rn(ray[A.dir_col + 2], zz));
-                    }
                 }
                 if (half == 0 && live) {                          // head-gradient block for the tiny-N weight gradients
                     unsigned char* da = A.bbase + A.bs.dhead;
@@ -270,7 +270,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                     if (kind == BK_S1) table_copy<ET>(sm.tblF, T + g.tbl_off, H2 * 16, tid_e);
                     else if (nodrain) { table_copy<ET>(sm.tblF, T + g.tbl_off, H2 * 16, tid_e); table_copy<ET>(sm.tblV, T + g.vec_off, H2 * 4, tid_e); }
                     else if (kind == BK_A7) table_copy<ET>(sm.tblF, T + g.tbl_off, H * 4, tid_e);
-                    else if (kind == BK_TRUNK && trunk_l - 1 == 0) table_copy<ET>(sm.tblF, T + g.tbl_off, H * 16, tid_e);
                     cp_async_wait_all();
                     // Dumps of a two-chunk GEMM leave in two bulk groups (low K-slabs after chunk 0's epilogue, the rest after
                     // chunk 1's), so each group has half a layer to drain before its slabs are rewritten: chunk 0 of this GEMM
@@ -279,11 +278,11 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                     named_bar_sync(1, ET);
                     const uint32_t tok = fresh_token((uint32_t)gi);
                     // where cos() comes from
-                    const unsigned char* yarr = nullptr; int yF = H; bool y_l0 = false;
+                    const unsigned char* yarr = nullptr; int yF = H;
                     if (kind == BK_S2) { yarr = A.fbase + A.fs.s2y; yF = H2; }
                     else if (kind == BK_S1) { yarr = A.fbase + A.fs.s1y; yF = H2; }
                     else if (kind == BK_A7) yarr = A.fbase + A.fs.y[A.n_layers - 1];
-                    else if (kind == BK_TRUNK) { if (trunk_l - 1 == 0) y_l0 = true; else yarr = A.fbase + A.fs.y[trunk_l - 1]; }
+                    else if (kind == BK_TRUNK) yarr = A.fbase + A.fs.y[trunk_l - 1];        // (layer 0's entry already holds 30 cos(30 y))
                     if (!live || (SNB_DEV_DBG(A.dbg) & 512)) yarr = nullptr;
                     const bool stores = !nodrain;
                     const bool next_early = gi + 1 < P.n_gemms && n_chunks > 1 && P.g[gi + 1].k_early > 0;
@@ -301,7 +300,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                         if (kn == BK_S1) { ya = A.fbase + A.fs.s1y; yb_bytes >>= 1; bulk_prefetch_l2(A.fbase + A.fs.r1y + (size_t)gt * yb_bytes, yb_bytes); }
                         else if (kn == BK_FA && P.has_beta) { ya = A.fbase + A.fs.b1y; yb_bytes >>= 1; }
                         else if (kn == BK_A7) ya = A.fbase + A.fs.y[A.n_layers - 1];
-                        else if (kn == BK_TRUNK) { const int ln = (kind == BK_TRUNK ? trunk_l - 1 : trunk_l) - 1; if (ln > 0) ya = A.fbase + A.fs.y[ln]; }
+                        else if (kn == BK_TRUNK) { const int ln = (kind == BK_TRUNK ? trunk_l - 1 : trunk_l) - 1; ya = A.fbase + A.fs.y[ln]; }
                         if (ya) bulk_prefetch_l2(ya + (size_t)gt * yb_bytes, yb_bytes);
                     }
                     // first y block of chunk 0 in flight while the MMAs run
@@ -346,19 +345,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                                             v[i] = fmaf(gsig, w.x, v[i]); v[i + 1] = fmaf(gsig, w.y, v[i + 1]); v[i + 2] = fmaf(gsig, w.z, v[i + 2]); v[i + 3] = fmaf(gsig, w.w, v[i + 3]);
                                         }
                                     }
-                                    if (y_l0) {
-#pragma unroll
-                                        for (int i = 0; i < 16; ++i) {
-                                            const float4 w = lds128(tF + (uint32_t)(c0 + i) * 16u, tok);
-                                            const float y = __fmul_rn(30.0f, fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w))));     // as the forward's layer 0
-                                            v[i] *= 30.f * __cosf(y);
-                                        }
-                                    } else if (yarr) mul_cos16(v, ycur, hf);
-                                    else if (kind != BK_FA && kind != BK_FB) {
+                                    if (slab_bar) mbar_wait(slab_bar + (c0 >> 6), slab_par, 28);
+                                    if (yarr) { store_mul_cos16(a_base, row, c0, v, ycur, hf); continue; }
+                                    if (kind != BK_FA && kind != BK_FB) {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) v[i] = 0.f;       // idle half of a pair: keep the tile finite
                                     }
-                                    if (slab_bar) mbar_wait(slab_bar + (c0 >> 6), slab_par, 28);
                                     store_act_cols<16>(a_base, row, c0, v);
                                 }
                                 if (kind == BK_S1) {
@@ -621,7 +613,6 @@ static int build_bwd_program(const FieldLayout& L, TcProgram* P, BwdMisc* M) {
     { TcGemm& g = add(BK_A7, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; g.tbl_off = tbl; M->t_sigma = tbl; tbl += H; }
     for (int l = L.n_layers - 1; l >= 1; --l) {
         TcGemm& g = add(BK_TRUNK, H, H); g.src0 = L.trunk[l].w; g.ld0 = L.trunk[l].n_in; g.col0 = l == L.skip ? L.in_xyz : 0; g.rows0 = H;
-        if (l == 1) { g.tbl_off = tbl; M->t_l0 = tbl; tbl += 4 * H; }          // [wx wy wz b] of trunk layer 0: its pre-activation is recomputed
     }
     P->n_gemms = ng;
     // pipeline fields (tc_pipeline.cuh): every GEMM rewrites the tile from its accumulator except FA when a beta head follows
@@ -636,7 +627,6 @@ static int build_bwd_program(const FieldLayout& L, TcProgram* P, BwdMisc* M) {
     }
     P->stage_bytes = max_stage; P->tables_base = (wbytes + 255) & ~255LL;
     M->s3_w = L.sun[3].w; M->r2_w = L.rgb2.w; M->b2_w = L.beta2.w; M->b0_w = L.beta0.w; M->b0_ld = L.beta0.n_in; M->sigma_w = L.sigma.w;
-    M->l0_w = L.trunk[0].w; M->l0_b = L.trunk[0].b;
     M->H = H; M->H2 = H2; M->tau = L.t_dims; M->has_beta = P->has_beta;
     return tbl;
 }
@@ -648,7 +638,7 @@ static void fwd_stash_layout(const FieldLayout& L, int n_tiles, int tpg, TcStash
     const long long yH = (long long)kTile * H * 2, yH2 = (long long)kTile * H2 * 2;
     long long off = 0;
     auto take = [&](long long per_tile) { long long o = off; off += per_tile * n_tiles; off = (off + 1023) & ~1023LL; return o; };
-    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(l == 0 ? 0 : yH); }
+    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(yH); }
     S->feat = take(tH);
     S->r1 = take(tH2); S->s1 = take(tH2); S->s2 = take(tH2); S->s3 = take(tH2); S->b1 = take(tH2);
     S->r1y = take(yH2); S->s1y = take(yH2); S->s2y = take(yH2); S->s3y = take(yH2); S->b1y = take(yH2);
@@ -885,7 +875,6 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     fwd_stash_layout(L, B.n_tiles, B.tpg, &A.fs); A.fbase = (const unsigned char*)io->stash;
     A.bs = B.bs; A.bbase = ws + B.off_bstash;
     A.d_head = d_head; A.C = C; A.absmax = absmax; A.d_t = (L.t_dims && g->g_t_emb) ? d_t : nullptr;
-    A.rays = io->rays; A.z = io->z_vals; A.xyz = io->xyz; A.ray_cols = p->ray_cols; A.dir_col = p->march_along_sun ? 8 : 3;
     A.n_layers = L.n_layers; A.R = R; A.S = S; A.G = B.G; A.n_groups = B.groups; A.tiles_per_group = B.tpg;
     A.dbg = dev_knobs().dbg;
     if (cg == 2) {

@@ -60,7 +60,7 @@ struct TcProgram {
 // Activation stash written by the training-mode forward (byte offsets from the stash base; every array is indexed
 // by the global tile id gt = group * tiles_per_group + tile).
 //   atoms : [gt][fg = f/64][pg][8 points][64 features] fp16, 128B-swizzled (see tc_backward.cu) — A-tile images
-//   yb    : [gt][f/8][128 rows][8] fp16 pre-activations y (cos() argument of the backward); layer 0 is recomputed, not stashed
+//   yb    : [gt][f/8][128 rows][8] fp16 activation DERIVATIVES w0 cos(w0 y) of the sine layers (what the backward multiplies by)
 struct TcStash {
     long long a[kMaxTrunk];                 // a_l = sin(.) outputs of trunk layer l (atoms, H wide)
     long long feat, r1, s1, s2, s3, b1;     // feats_from_xyz output; first-layer activations of the rgb / sun / beta heads
@@ -172,9 +172,9 @@ __device__ __forceinline__ void store_act_cols(uint32_t a_base, int row, int k0,
     }
 }
 // ---- training stash helpers -------------------------------------------------------------------------------
-// Pre-activations of the sine layers are stashed as plain fp16 (one pack per pair of elements: the training forward's epilogue is
-// bound by instruction issue).  |y| < 8 for SIREN layers with w0 = 1 (fp16 ulp <= 3.9e-3 rad, <= 2e-3 rad rounding error on
-// cos'); the first layer (w0 = 30, |y| up to ~50 rad) is NOT stashed: the backward recomputes 30 (W0 x + b0) exactly from x.
+// The forward stashes the derivative of every sine activation, w0 cos(w0 y) (w0 = 30 for trunk layer 0, 1 elsewhere), as fp16: the
+// range reduction is shared with the sine, the value is in [-30, 30] whatever |y| is (relative error 2^-11), and the backward's
+// epilogue becomes one packed half multiply per pair of elements -- no conversion, no range reduction, no MUFU.
 // yb arrays: [tile gt][8-column block n/8][row 0..127][8 fp16] -- the 32 lanes of a warp (consecutive rows) write / read 512
 // contiguous bytes per 16-byte access (the round-1 layout [n/32][row][32] made every access a 64-byte-strided scatter and
 // the training forward 3x slower than inference).

@@ -148,7 +148,7 @@ static void stash_layout(const FieldLayout& L, int n_tiles, int tiles_per_group,
     const long long yH = (long long)kTile * H * 2, yH2 = (long long)kTile * H2 * 2;                           // yb bytes per tile
     long long off = 0;
     auto take = [&](long long per_tile) { long long o = off; off += per_tile * n_tiles; off = (off + 1023) & ~1023LL; return o; };
-    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(l == 0 ? 0 : yH); }      // (layer 0's pre-activation is recomputed by the backward)
+    for (int l = 0; l < L.n_layers; ++l) { S->a[l] = take(tH); S->y[l] = take(yH); }
     S->feat = take(tH);
     S->r1 = take(tH2); S->s1 = take(tH2); S->s2 = take(tH2); S->s3 = take(tH2); S->b1 = take(tH2);
     S->r1y = take(yH2); S->s1y = take(yH2); S->s2y = take(yH2); S->s3y = take(yH2); S->b1y = take(yH2);
@@ -313,7 +313,12 @@ struct EpiStash { unsigned char *y0, *y1, *act0, *act1; int gt; };     // 0: fir
 #define SIN_(x) ((TC_DBG(dbg) & 1) ? (x) : __sinf(x))
 template <int NC>
 __device__ __forceinline__ void sin_cols(int dbg, float* v, unsigned char* yarr, int gt, int F, int n0, int row) {
-    if (yarr) yb_store_cols<NC>(yarr, gt, F, n0, row, v);
+    if (yarr) {                      // training: the derivative cos(y) goes to the stash (same range reduction as the sine)
+        float c[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) c[i] = __cosf(v[i]);
+        yb_store_cols<NC>(yarr, gt, F, n0, row, c);
+    }
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] = SIN_(v[i]);
 }
@@ -776,6 +781,12 @@ __global__ void __launch_bounds__(64 + 32 * ((TRAIN || NERF) ? kEpiWarpsTrain : 
                             for (int i = 0; i < 8; ++i) {
                                 float y = fmaf(w[i].z, rz[k], fmaf(w[i].y, ry[k], fmaf(w[i].x, rx[k], w[i].w)));
                                 v[i] = __fmul_rn(30.0f, y);
+                            }
+                            if (sb) {                       // d sin(30 y) / dy = 30 cos(30 y)
+                                float c[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) c[i] = 30.0f * __cosf(v[i]);
+                                yb_store_cols<8>(sb + A.stash.y[0], gt, H, n0, r, c);
                             }
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = __sinf(v[i]);

@@ -14,7 +14,7 @@ def layout(n_layers, H, n_tiles):
         off = (off + per_tile * n_tiles + 1023) & ~1023
 
     for l in range(n_layers):
-        take(f"a{l}", tH); take(f"y{l}", 0 if l == 0 else yH)      # layer 0's pre-activation is recomputed by the backward
+        take(f"a{l}", tH); take(f"y{l}", yH)
     take("feat", tH)
     for k in ("r1", "s1", "s2", "s3", "b1"):
         take(k, tH2)
@@ -38,6 +38,6 @@ def unpack_atoms(buf, off, n_tiles, F):
 
 
 def unpack_yb(buf, off, n_tiles, F):
-    """yb [gt][F/8][128][8] fp16 pre-activations -> (n_tiles*128, F) float."""
+    """yb [gt][F/8][128][8] fp16 activation derivatives w0 cos(w0 y) -> (n_tiles*128, F) float."""
     raw = buf[off:off + n_tiles * 128 * F * 2].view(torch.float16).view(n_tiles, F // 8, 128, 8)
     return raw.permute(0, 2, 1, 3).reshape(n_tiles * 128, F).float()
