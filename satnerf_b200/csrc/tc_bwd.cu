@@ -155,6 +155,14 @@ __device__ __forceinline__ void store_mul_cos16(uint32_t a_base, int row, int c0
 //   A7     D = A W_feats ;  A = (D + g_sigma w_sigma) cos(y_7)                                  -> dump d y_7
 //   TRUNK  l = L-1 .. 1:  D = A W_l[:, skip:] ;  A = D w0_{l-1} cos(y_{l-1})                    -> dump d y_{l-1}
 // (cos(y) stands for the stashed activation derivative: cos(y), and 30 cos(30 y) for trunk layer 0.)
+// Phase probe (dev library, SNB_TC_DBG bit 4096; profiles/dev/chain_probe.sh): clock64 stamps of block 0's second tile, printed by
+// the kernel.  Per GEMM: [section entered, cp.async drained, bulk dump drained] barrier passed, accumulator chunk 0 ready,
+// chunk 0 stored, accumulator chunk 1 ready, GEMM done.  Findings: profiles/r2_chain_probe.md.
+#ifdef SNB_DEV_BUILD
+#define CH_MARK(g, k) do { if (probe) stamps[(g) * 8 + (k)] = clock64(); } while (0)
+#else
+#define CH_MARK(g, k) do { } while (0)
+#endif
 template <int CG>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(const __grid_constant__ TcBwdArgs A) {
     constexpr int EW = kEpiWarpsTrain, ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
@@ -217,6 +225,11 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
             const int n_rays = live ? min(A.G, A.R - r0) : 0;
             const int Pg = n_rays * S;
             for (int t = 0; t < tpg; ++t, ++tile_seq) {
+#ifdef SNB_DEV_BUILD
+                const bool probe = (A.dbg & 4096) && blockIdx.x == 0 && tile_seq == 1 && tid_e == 0;
+                long long stamps[kMaxGemms * 8 + 8]; const long long t_tile = clock64();
+                if (probe) for (int i = 0; i < kMaxGemms * 8 + 8; ++i) stamps[i] = t_tile;
+#endif
                 const int gt = grp * tpg + t;
                 const int p = t * kTile + row;
                 const bool valid = p < Pg;
@@ -234,10 +247,14 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                     for (int c = 1; c < 8; ++c) *reinterpret_cast<uint4*>(atom_chunk(da, gt, 1, row, c * 8)) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 // ---- seed: d s3y = g_sun * w_s3 * cos(s3y)  ->  A[:, 0:H2) ----
+                CH_MARK(kMaxGemms, 0);
                 table_copy<ET>(sm.tblF, T + P.l0_tbl, H2 * 4, tid_e);
                 cp_async_wait_all();
+                CH_MARK(kMaxGemms, 1);
                 if (tid_e == 0) bulk_wait_read();                 // the previous tile's last dump has left shared memory
+                CH_MARK(kMaxGemms, 2);
                 named_bar_sync(1, ET);
+                CH_MARK(kMaxGemms, 3);
                 {
                     const uint32_t tok = fresh_token(0x7fffu);
                     for (int n0 = half * 32; n0 < H2; n0 += 32 * ES) {
@@ -259,6 +276,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                     (void)gn; }
                 signal_ready(0);
                 signal_ready(1);
+                CH_MARK(kMaxGemms, 4);
 
                 int trunk_l = A.n_layers - 1;                     // layer whose dY the next BK_TRUNK GEMM consumes
                 bool prev_split = false;                          // the previous GEMM's dump left as two bulk groups
@@ -270,12 +288,16 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                     if (kind == BK_S1) table_copy<ET>(sm.tblF, T + g.tbl_off, H2 * 16, tid_e);
                     else if (nodrain) { table_copy<ET>(sm.tblF, T + g.tbl_off, H2 * 16, tid_e); table_copy<ET>(sm.tblV, T + g.vec_off, H2 * 4, tid_e); }
                     else if (kind == BK_A7) table_copy<ET>(sm.tblF, T + g.tbl_off, H * 4, tid_e);
+                    CH_MARK(gi, 5);
                     cp_async_wait_all();
+                    CH_MARK(gi, 6);
                     // Dumps of a two-chunk GEMM leave in two bulk groups (low K-slabs after chunk 0's epilogue, the rest after
                     // chunk 1's), so each group has half a layer to drain before its slabs are rewritten: chunk 0 of this GEMM
                     // rewrites the low slabs (the previous GEMM's HIGH group may still be reading), chunk 1 the high ones.
                     if (tid_e == 0) { if (prev_split) bulk_wait_read1(); else bulk_wait_read(); }
+                    CH_MARK(gi, 7);
                     named_bar_sync(1, ET);
+                    CH_MARK(gi, 0);
                     const uint32_t tok = fresh_token((uint32_t)gi);
                     // where cos() comes from
                     const unsigned char* yarr = nullptr; int yF = H;
@@ -316,6 +338,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                         }
                         named_bar_sync(2, ET);
                         tc_fence_after();
+                        CH_MARK(gi, ch == 0 ? 1 : 3);
                         const bool final_chunk = ch == n_chunks - 1;
                         if (!nodrain) {
                             const int n_end = min((ch + 1) * chunk_n, N);
@@ -390,6 +413,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                         }
                         if (!final_chunk) {
                             tc_fence_before();
+                            CH_MARK(gi, 2);
                             if (next_early) {
                                 fence_proxy_async_smem();
                                 named_bar_sync(1, ET);
@@ -409,6 +433,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                         sc[0] = dt0; sc[1] = dt1; sc[2] = dt2; sc[3] = dt3;
                     }
                     named_bar_sync(1, ET);              // all TMEM reads / A writes / table reads of this GEMM done
+                    CH_MARK(gi, 4);
                     if (nodrain && A.d_t && half == 0 && valid) {
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -437,6 +462,17 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsTrain, 1) tc_chain_kernel(c
                     }
                     if (kind == BK_TRUNK) --trunk_l;
                 }
+#ifdef SNB_DEV_BUILD
+                if (probe) {
+                    printf("chain tile probe (cycles from tile start; kind: [in cp.async-drained dump-drained] top acc0 st0 acc1 done)\n");
+                    for (int gi = 0; gi < P.n_gemms; ++gi)
+                        printf("  g%02d k%d: [in %7lld cpw %7lld blk %7lld] %7lld %7lld %7lld %7lld %7lld\n", gi, P.g[gi].kind, stamps[gi * 8 + 5] - t_tile,
+                               stamps[gi * 8 + 6] - t_tile, stamps[gi * 8 + 7] - t_tile, stamps[gi * 8] - t_tile, stamps[gi * 8 + 1] - t_tile,
+                               stamps[gi * 8 + 2] - t_tile, stamps[gi * 8 + 3] - t_tile, stamps[gi * 8 + 4] - t_tile);
+                    printf("  seed: entered %lld tables %lld dump-drained %lld barrier %lld signalled %lld\n", stamps[kMaxGemms * 8] - t_tile, stamps[kMaxGemms * 8 + 1] - t_tile,
+                           stamps[kMaxGemms * 8 + 2] - t_tile, stamps[kMaxGemms * 8 + 3] - t_tile, stamps[kMaxGemms * 8 + 4] - t_tile);
+                }
+#endif
             }
         }
         if (tid_e == 0) bulk_wait_read();
