@@ -74,8 +74,12 @@ typedef struct snb_pass_desc {
 
 /* snb_pass_desc.flags */
 enum { SNB_PASS_SINGLE_CTA = 1,   /* tensor-core path: one CTA per 128-point tile instead of CTA pairs (A/B testing; bit-identical) */
-       SNB_PASS_NO_BETA    = 2 }; /* sat-nerf, inference: the caller does not consume the uncertainty head (create_satnerf_dsm.py:78
+       SNB_PASS_NO_BETA    = 2,   /* sat-nerf, inference: the caller does not consume the uncertainty head (create_satnerf_dsm.py:78
                                      uses depth only): beta_from_xyz is not evaluated; io->beta must be NULL and aux_sums[4] is 0  */
+       SNB_PASS_SIGMA_ONLY = 4 }; /* inference: only the density is evaluated (the fields' `sigma_only=True`, satnerf.py:184-185):
+                                     trunk + sigma head, no feature / colour / sun / sky / uncertainty layers.  Outputs: depth,
+                                     weights, transparency, sigma; every other output pointer must be NULL.  Tensor-core path,
+                                     s-nerf / sat-nerf                                                                          */
 
 typedef struct snb_render_io {
     /* inputs */

@@ -32,7 +32,7 @@ class PassDesc(C.Structure):
                 ("flags", C.c_int32), ("t_min", C.c_float)]
 
 
-PASS_SINGLE_CTA, PASS_NO_BETA = 1, 2
+PASS_SINGLE_CTA, PASS_NO_BETA, PASS_SIGMA_ONLY = 1, 2, 4
 LOSS_COLOR_MSE, LOSS_COLOR_BETA, LOSS_DEPTH, LOSS_SOLAR = 1, 2, 3, 4
 
 

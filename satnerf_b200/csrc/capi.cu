@@ -90,6 +90,7 @@ extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pas
         if (r != 1) return r;      // 1 = configuration not covered by the tensor-core kernel: fp32 CUDA-core path below
     }
 
+    if (p->flags & SNB_PASS_SIGMA_ONLY) SNB_FAIL(-1, "SNB_PASS_SIGMA_ONLY is provided by the tensor-core path only (precision SNB_FP16_TC, a shape it covers)");
     Arena ar(workspace, workspace_bytes); PassPlan pl; plan_pass(ar, L, p, false, &pl);
     if (ar.overflow) SNB_FAIL(-4, "snb_render_forward: workspace too small (%zu bytes given)", workspace_bytes);
     const int S = p->n_samples, C = L.n_channels;

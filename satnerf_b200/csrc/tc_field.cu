@@ -42,7 +42,7 @@ static bool tc_supported(const FieldLayout& L, const snb_pass_desc* p) {
     return true;
 }
 
-static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = false) {
+static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = false, bool sigma_only = false) {
     memset(P, 0, sizeof(*P));
     const int H = L.width, H2 = H / 2;
     P->H = H; P->H2 = H2; P->tau = L.t_dims; P->has_beta = L.variant == SNB_SATNERF && !no_beta;
@@ -86,6 +86,7 @@ static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = fals
         g.aux = g.skip ? 2 : 1;                  // bias (+ xyz term of the skip layer) ride on the aux K-step: no epilogue table
         tables(g, TF_NONE, g.last);
     }
+    if (!sigma_only) {
     { TcGemm& g = add(GK_FEAT, H, H); g.src0 = L.feats.w; g.ld0 = H; g.rows0 = H; g.aux = 1; tables(g, TF_NONE, 0); }
     { int nb = P->has_beta ? H2 : 0;
       TcGemm& g = add(GK_HEADA, nb + H2, H);
@@ -95,6 +96,7 @@ static int build_program(const FieldLayout& L, TcProgram* P, bool no_beta = fals
     { TcGemm& g = add(GK_SUN1, H2, H); g.src0 = L.sun[0].w; g.ld0 = L.sun[0].n_in; g.rows0 = H2; tables(g, TF_NONE, 0); }
     { TcGemm& g = add(GK_SUN2, H2, H2); g.src0 = L.sun[1].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 0); }
     { TcGemm& g = add(GK_SUN3, H2, H2); g.src0 = L.sun[2].w; g.ld0 = H2; g.rows0 = H2; tables(g, TF_F1, 1); }
+    }      // (sigma_only: the program ends with the last trunk layer, whose epilogue carries the density head)
     }
     for (int i = 0; i < ng; ++i) if (!P->g[i].kvalid) P->g[i].kvalid = P->g[i].K;
     P->n_gemms = ng;
@@ -1138,11 +1140,17 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         SNB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     if (dev_knobs().hang_mirror) { int rc = hang_mirror_init(); if (rc) return rc; }
-    const bool no_beta = (p->flags & SNB_PASS_NO_BETA) != 0 && L.variant == SNB_SATNERF;
+    const bool sigma_only = (p->flags & SNB_PASS_SIGMA_ONLY) != 0;
+    if (sigma_only) {
+        if (L.variant == SNB_NERF) SNB_FAIL(-1, "SNB_PASS_SIGMA_ONLY: s-nerf / sat-nerf only");
+        if (io->stash) SNB_FAIL(-1, "SNB_PASS_SIGMA_ONLY is an inference option");
+        if (io->rgb || io->albedo || io->sun || io->sky || io->beta || io->aux_sums) SNB_FAIL(-1, "SNB_PASS_SIGMA_ONLY: only depth / weights / transparency / sigma are produced");
+    }
+    const bool no_beta = ((p->flags & SNB_PASS_NO_BETA) != 0 || sigma_only) && L.variant == SNB_SATNERF;
     if (no_beta && io->stash) SNB_FAIL(-1, "SNB_PASS_NO_BETA is an inference option (a training pass needs the beta head)");
     if (no_beta && io->beta) SNB_FAIL(-1, "SNB_PASS_NO_BETA: io->beta must be NULL");
     TcArgs A; memset(&A, 0, sizeof(A));
-    int nfl = build_program(L, &A.prog, no_beta);
+    int nfl = build_program(L, &A.prog, no_beta, sigma_only);
     TcProgram& P = A.prog;
     size_t need = (size_t)P.tables_base + (size_t)nfl * 4;
     if (need > workspace_bytes) SNB_FAIL(-4, "tensor-core path: workspace too small (%zu < %zu)", workspace_bytes, need);

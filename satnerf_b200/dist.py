@@ -62,9 +62,9 @@ def broadcast_parameters(models: Dict[str, torch.nn.Module], src: int = 0) -> in
 
 
 def all_reduce_gradients(models: Dict[str, torch.nn.Module], average: bool = True) -> int:
-    """Sums gradients across ranks with ONE collective per step: when every gradient already lives in one bucket (a single field
-    and no embedding) the flat buffer is reduced in place; otherwise the flat gradient buffers of the fields and the (tiny)
-    embedding gradient are packed into one bucket, reduced, and unpacked.  `average=False` when 1/world is already folded into
+    """Sums gradients across ranks with ONE collective launch per step: when every gradient already lives in one bucket (a single
+    field and no embedding) the flat buffer is reduced in place; with several buffers NCCL reduces them in place inside one group
+    launch (other backends: packed into one bucket, reduced, unpacked).  `average=False` when 1/world is already folded into
     the loss seed (render_loss_backward(n_rays_mean = global batch)).  Returns the number of collectives issued (0 or 1)."""
     r, w = world()
     if w == 1:
@@ -79,6 +79,15 @@ def all_reduce_gradients(models: Dict[str, torch.nn.Module], average: bool = Tru
                     parts.append(p.grad)
     if not parts:
         return 0
+    if len(parts) > 1 and parts[0].is_cuda and dist.get_backend() == "nccl":
+        # several buffers (field gradient + embedding, or coarse + fine): one NCCL group launch reduces them in place -- no pack /
+        # unpack copies of the 10 MB buffers (the bucket path below cost ~50 us per step on top of the collective)
+        with dist._coalescing_manager(device=parts[0].device):
+            for g in parts:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        if average:
+            torch._foreach_div_(parts, float(w))
+        return 1
     if len(parts) == 1:
         bucket = parts[0].view(-1)
     else:

@@ -12,6 +12,8 @@ sampling, the MLP, compositing and their gradients run in libsatnerf_b200.so thr
                    'eval'  (no_grad only) per-ray outputs: rgb_*, depth_* and the weighted images eval_satnerf.py:125-146 builds
                            from the per-sample tensors -- sun_w_*, albedo_w_*, beta_w_*, sky_w_* = sum_i w_i x_i -- computed in-kernel
                    'depth' (no_grad only) rgb_*, depth_* only; sat-nerf skips the uncertainty head (create_satnerf_dsm.py:78)
+                   'depth_only' (no_grad only, tensor-core path) depth_* only: density trunk + sigma head, what the fields'
+                           `sigma_only=True` evaluates (satnerf.py:184-185) -- all a DSM needs
   args.t_min     : > 0 stops compositing along a ray once its transmittance is below t_min (dropped weights sum to < t_min)
   args.tc_cta_group : 1 forces single-CTA tiles on the tensor-core path (default 2: CTA pairs; results are bit-identical)
 """
@@ -54,7 +56,8 @@ def _packed_workspace(field, pd, params, dev):
     batched_inference / DSM extraction render many ray batches per weight set.  Sets pd.weights_packed; returns the buffer."""
     flat = field.flat_params()
     # (the parameters alias `flat` through `.data`, so each keeps its own version counter)
-    key = (flat.data_ptr(), flat._version, tuple(p._version for p in params), str(dev), field._packed_epoch, pd.flags & capi.PASS_NO_BETA)
+    key = (flat.data_ptr(), flat._version, tuple(p._version for p in params), str(dev), field._packed_epoch,
+           pd.flags & (capi.PASS_NO_BETA | capi.PASS_SIGMA_ONLY))
     need = capi.render_workspace_bytes(field.desc, pd)
     cache = getattr(field, "_tc_packed", None)
     if cache is None or cache[0].device != dev or cache[0].numel() < need:
@@ -136,16 +139,22 @@ def _run_pass_lite(field, args, rays, z, t_emb, noise, mode, want_weights=False)
     sum_i w_i * {sun, albedo, beta, sky} that eval_satnerf.py:125-146 forms from the (R,S,.) tensors; none of those tensors is
     written.  mode 'depth' (create_satnerf_dsm.py:78 consumes the depth only) also skips the uncertainty head."""
     if torch.is_grad_enabled() and any(p.requires_grad for p in field.parameters()):
-        raise RuntimeError("render_outputs='eval'/'depth' are inference modes: call under torch.no_grad()")
+        raise RuntimeError("render_outputs='eval'/'depth'/'depth_only' are inference modes: call under torch.no_grad()")
     if field.variant == "nerf":
         raise NotImplementedError("render_outputs='eval'/'depth' exist for s-nerf / sat-nerf (the outputs of eval_satnerf.py:125-146)")
     R, S = z.shape
     dev = z.device
     flags = _flags(args) | (capi.PASS_NO_BETA if (mode == "depth" and field.variant == "sat-nerf") else 0)
+    if mode == "depth_only":
+        if _precision(args) != capi.FP16_TC:
+            raise NotImplementedError("render_outputs='depth_only' runs on the tensor-core path (args.precision='tc')")
+        flags |= capi.PASS_SIGMA_ONLY
     cfg = {"sc": False, "precision": _precision(args), "noise_std": float(args.noise_std), "flags": flags, "t_min": float(getattr(args, "t_min", 0.0))}
     pd = _pass_desc(cfg, R, S, rays.shape[1])
     f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
-    outs = {"rgb": torch.empty(R, 3, device=dev), "depth": torch.empty(R, device=dev)}
+    outs = {"depth": torch.empty(R, device=dev)}
+    if mode != "depth_only":
+        outs["rgb"] = torch.empty(R, 3, device=dev)
     if want_weights:
         outs["weights"] = torch.empty(R, S, device=dev)
     aux = torch.empty(R, 8, device=dev) if mode == "eval" else None
@@ -261,8 +270,8 @@ def render_rays(models, args, rays, ts, _draws: Optional[List[torch.Tensor]] = N
     z = capi.stratified_depths(rays, steps, draw("u", R, S).contiguous())         # :67-78
 
     mode = getattr(args, "render_outputs", "full")
-    if mode not in ("full", "eval", "depth"):
-        raise ValueError(f"render_outputs {mode!r} is not valid (full | eval | depth)")
+    if mode not in ("full", "eval", "depth", "depth_only"):
+        raise ValueError(f"render_outputs {mode!r} is not valid (full | eval | depth | depth_only)")
 
     def level(name, zz):
         if mode != "full":                     # per-ray outputs only; the solar-correction pass feeds the loss alone and is not evaluated

@@ -77,6 +77,32 @@ def test_depth_mode_skips_beta_head_bit_identically(precision):
         sb.render_rays(ms, args, rays.cuda(), ts.cuda())          # inference modes refuse to run under autograd
 
 
+@pytest.mark.parametrize("model,n_imp", [("sat-nerf", 0), ("sat-nerf", 32), ("s-nerf", 0)])
+def test_depth_only_mode_equals_full_depth_bit_for_bit(model, n_imp):
+    """render_outputs='depth_only' (SNB_PASS_SIGMA_ONLY: trunk + density head only, the fields' sigma_only=True, satnerf.py:184-185):
+    the density path is the same sequence of GEMMs, so depth (and the coarse weights the fine sampler reads) equal the full
+    pass bit for bit; and against the oracle within 1e-3."""
+    import satnerf_b200 as sb
+    from satnerf_b200 import capi
+    args = make_args(model=model, fc_units=512, n_importance=n_imp, precision="tc")
+    ms, params, rays, ts, draws = _setup(args, 515, 71)
+    tsd = None if ts is None else ts.cuda()
+    with torch.no_grad():
+        full = sb.render_rays(ms, args, rays.cuda(), tsd, _draws=draws)
+        args.render_outputs = "depth_only"
+        capi.launch_count(reset=True)
+        lite = sb.render_rays(ms, args, rays.cuda(), tsd, _draws=draws)
+    lvl = ("coarse", "fine") if n_imp else ("coarse",)
+    assert set(lite) == {f"depth_{l}" for l in lvl} | ({"weights_coarse"} if n_imp else set())
+    for l in lvl:
+        assert torch.equal(lite[f"depth_{l}"], full[f"depth_{l}"]), l
+    want = orc.render_rays(params, make_args(**{k: v for k, v in vars(args).items() if k != "render_outputs"}), rays, ts, orc.Draws([d.clone() for d in draws]))
+    assert rel_err(lite["depth_coarse"].cpu(), want["depth_coarse"]) < 1e-3
+    args.precision = "fp32"
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        sb.render_rays(ms, args, rays.cuda(), tsd, _draws=draws)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
 def test_early_termination_tail_is_bounded(precision):
     """Dense medium (sigma head x64, bias 30): most rays are absorbed within the first 32 samples; with t_min = 1e-2 the samples
