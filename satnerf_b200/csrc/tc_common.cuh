@@ -27,6 +27,10 @@ constexpr int kTblF = 8192, kTblV = 2048;    // epilogue table region: [N][4] or
 #endif
 constexpr int kEpiWarps = SNB_EPI_WARPS;
 constexpr int kEpiWarpsTrain = SNB_EPI_WARPS_TRAIN;
+#ifndef SNB_EPI_WARPS_FWD_TRAIN
+#define SNB_EPI_WARPS_FWD_TRAIN SNB_EPI_WARPS_TRAIN
+#endif
+constexpr int kEpiWarpsFwdTrain = SNB_EPI_WARPS_FWD_TRAIN;      // training-mode forward (the chain and the nerf kernel use kEpiWarpsTrain)
 constexpr int kMaxEpiWarps = kEpiWarps > kEpiWarpsTrain ? kEpiWarps : kEpiWarpsTrain;
 
 enum { GK_TRUNK = 0, GK_FEAT, GK_HEADA, GK_SUN1, GK_SUN2, GK_SUN3, GK_HEADN };      // HEADN: nerf's rgb_from_xyzdir.0 (per-ray view-direction bias, ReLU)

@@ -422,8 +422,8 @@ __device__ __forceinline__ void epi_cols(uint32_t tok, int dbg, int kind, bool s
 // leader issues M=256 MMAs that read each CTA's own activation tile and HALF of every weight tile from each
 // CTA's shared memory, so each SM streams / buffers only half of the weights.
 template <int CG, bool TRAIN, bool NERF>
-__global__ void __launch_bounds__(64 + 32 * ((TRAIN || NERF) ? kEpiWarpsTrain : kEpiWarps), 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
-    constexpr int EW = (TRAIN || NERF) ? kEpiWarpsTrain : kEpiWarps, ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
+__global__ void __launch_bounds__(64 + 32 * (TRAIN ? kEpiWarpsFwdTrain : (NERF ? kEpiWarpsTrain : kEpiWarps)), 1) tc_render_kernel(const __grid_constant__ TcArgs A) {
+    constexpr int EW = TRAIN ? kEpiWarpsFwdTrain : (NERF ? kEpiWarpsTrain : kEpiWarps), ES = EW / 4, ET = EW * 32;      // epilogue warps, column-block interleave per quadrant, epilogue threads
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const TcProgram& P = A.prog;
@@ -1197,7 +1197,7 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n_pairs = (A.n_groups + 1) / 2, max_pairs = sm_count / 2;
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(64 + 32 * ((train || P.nerf) ? kEpiWarpsTrain : kEpiWarps));
+        cfg.gridDim = dim3(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)); cfg.blockDim = dim3(64 + 32 * (train ? kEpiWarpsFwdTrain : (P.nerf ? kEpiWarpsTrain : kEpiWarps)));
         cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1208,7 +1208,7 @@ int tc_render_forward(const FieldLayout& L, const snb_pass_desc* p, const snb_re
         auto kern = P.nerf ? tc_render_kernel<1, false, true> : (train ? tc_render_kernel<1, true, false> : tc_render_kernel<1, false, false>);
         SNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = A.n_groups < sm_count ? A.n_groups : sm_count;
-        kern<<<grid, 64 + 32 * ((train || P.nerf) ? kEpiWarpsTrain : kEpiWarps), smem, st>>>(A);
+        kern<<<grid, 64 + 32 * (train ? kEpiWarpsFwdTrain : (P.nerf ? kEpiWarpsTrain : kEpiWarps)), smem, st>>>(A);
         SNB_CHECK_LAUNCH();
     }
     return 0;
