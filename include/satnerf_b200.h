@@ -252,6 +252,16 @@ SNB_API int snb_dsm_rasterize(const double* cloud, long long n_points, double xo
 SNB_API int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                   double lr, double beta1, double beta2, double eps, double weight_decay, int step, void* stream);
 
+/* Data-parallel optimiser step fused with its collective (multi-GPU training; the reference is single-GPU): rank
+ * `rank` of `world` (<= 8) owns a contiguous shard of the n floats (n % 4 == 0); for its shard it sums the gradient shards of ALL
+ * ranks through peer_grads[r] (device pointers valid on this GPU: symmetric / peer-mapped memory over NVLink; fixed order), applies
+ * snb_adam_step's arithmetic with its own moments, and stores the new parameters into peer_params[r] of every rank.  peer_params /
+ * peer_grads are HOST arrays of `world` device pointers.  The caller provides the two cross-rank barriers around it (all gradients
+ * final before; all parameters delivered after).  Replaces all-reduce + Adam: replicas stay bit-identical.                    */
+SNB_API int snb_adam_step_sharded(float* const* peer_params, const float* const* peer_grads, int world, int rank,
+                          float* exp_avg, float* exp_avg_sq, long long n,
+                          double lr, double beta1, double beta2, double eps, double weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,8 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int, C.c_void_p]),
+    "snb_adam_step_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double,
+                                        C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]),
     "snb_field_workspace": (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.POINTER(C.c_size_t)]),
     "snb_field_forward": (C.c_int, [C.POINTER(FieldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -337,3 +339,13 @@ def field_backward(desc: FieldDesc, params, xyz, aux_dir, t_emb, out, d_out, g_p
         _check(lib().snb_field_backward(C.byref(desc), _ptr(params), _ptr(xyz), _ptr(aux_dir), _ptr(t_emb), _ptr(out), _ptr(d_out), _ptr(g_params),
                                         _ptr(g_t), B, int(sigma_only), C.c_void_p(ws.data_ptr()), ws.numel(), _stream(xyz.device)), "snb_field_backward")
     return g_t
+
+
+def adam_step_sharded(peer_param_ptrs, peer_grad_ptrs, rank, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, device):
+    """One rank's part of the fused reduce-scatter + Adam + all-gather step (snb_adam_step_sharded); the caller issues the barriers."""
+    world = len(peer_param_ptrs)
+    pp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_param_ptrs])
+    gp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_grad_ptrs])
+    with torch.cuda.device(device):
+        _check(lib().snb_adam_step_sharded(pp, gp, world, int(rank), C.c_void_p(exp_avg.data_ptr()), C.c_void_p(exp_avg_sq.data_ptr()), int(n),
+                                           lr, beta1, beta2, eps, weight_decay, int(step), _stream(device)), "snb_adam_step_sharded")

@@ -1,6 +1,8 @@
 // Optimiser step on the flat parameter buffer (the reference trains with torch.optim.Adam(lr, weight_decay=0), main.py:81-94
 // via train_utils.py:24-53).  One elementwise pass over params / grads / exp_avg / exp_avg_sq: HBM-bound, 28 bytes per parameter.
 #include "common.cuh"
+#include <cstring>
+#include <cmath>
 
 namespace snb {
 
@@ -26,9 +28,69 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         upd(p[i], g[i], m[i], v[i]);
 }
 
+// Data-parallel step fused with its collective (ZeRO-1 style, one kernel per flat buffer): every rank owns a contiguous shard of the
+// parameters; for its shard it SUMS the gradient shards of all ranks straight from their memory (NVLink peer loads through the
+// symmetric-memory mapping, fixed rank order: deterministic, and every element is reduced by exactly one rank, so replicas stay
+// bit-identical), applies Adam with its own moments, and writes the updated parameters into every rank's parameter buffer (peer
+// stores).  Replaces all-reduce (10.5 MB through NCCL: ~50 us on 2 GPUs) + Adam; the caller brackets it with two device barriers
+// (gradients final on every rank before; parameters delivered after).
+constexpr int kMaxRanks = 8;
+struct ShardedAdamArgs {
+    float* params[kMaxRanks]; const float* grads[kMaxRanks];
+    float *m, *v; long long lo4, hi4; int world, rank; AdamArgs a;
+};
+__global__ void adam_sharded_kernel(const __grid_constant__ ShardedAdamArgs A) {
+    const float step_size = A.a.lr / A.a.bc1;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        if (A.a.wd != 0.f) gg = fmaf(A.a.wd, pp, gg);
+        mm = fmaf(A.a.b1, mm, A.a.omb1 * gg);
+        vv = fmaf(A.a.b2, vv, A.a.omb2 * (gg * gg));
+        pp -= step_size * (mm / (sqrtf(vv) / A.a.bc2_sqrt + A.a.eps));
+    };
+    for (long long i = A.lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.hi4; i += (long long)gridDim.x * blockDim.x) {
+        float4 g[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) if (r < A.world) g[r] = reinterpret_cast<const float4*>(A.grads[r])[i];      // all peer loads in flight
+        float4 gs = g[0];
+#pragma unroll
+        for (int r = 1; r < kMaxRanks; ++r) if (r < A.world) { gs.x += g[r].x; gs.y += g[r].y; gs.z += g[r].z; gs.w += g[r].w; }
+        float4 pp = reinterpret_cast<const float4*>(A.params[A.rank])[i], mm = reinterpret_cast<float4*>(A.m)[i], vv = reinterpret_cast<float4*>(A.v)[i];
+        upd(pp.x, gs.x, mm.x, vv.x); upd(pp.y, gs.y, mm.y, vv.y); upd(pp.z, gs.z, mm.z, vv.z); upd(pp.w, gs.w, mm.w, vv.w);
+        reinterpret_cast<float4*>(A.m)[i] = mm; reinterpret_cast<float4*>(A.v)[i] = vv;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) if (r < A.world) reinterpret_cast<float4*>(A.params[r])[i] = pp;
+    }
+}
+
 }  // namespace snb
 
 using namespace snb;
+
+extern "C" SNB_API int snb_adam_step_sharded(float* const* peer_params, const float* const* peer_grads, int world, int rank,
+                                             float* exp_avg, float* exp_avg_sq, long long n,
+                                             double lr, double beta1, double beta2, double eps, double weight_decay, int step, void* stream) {
+    if (!peer_params || !peer_grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) SNB_FAIL(-1, "snb_adam_step_sharded: bad argument");
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) SNB_FAIL(-1, "snb_adam_step_sharded: world %d / rank %d unsupported (<= %d ranks)", world, rank, kMaxRanks);
+    if (n % 4) SNB_FAIL(-1, "snb_adam_step_sharded: the buffers must hold a multiple of 4 floats (pad them)");
+    ShardedAdamArgs A; memset(&A, 0, sizeof(A));
+    for (int r = 0; r < world; ++r) {
+        if (!peer_params[r] || !peer_grads[r] || (((uintptr_t)peer_params[r] | (uintptr_t)peer_grads[r]) & 15)) SNB_FAIL(-1, "snb_adam_step_sharded: null / unaligned peer buffer %d", r);
+        A.params[r] = peer_params[r]; A.grads[r] = peer_grads[r];
+    }
+    if (((uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) SNB_FAIL(-1, "snb_adam_step_sharded: moments must be 16-byte aligned");
+    const long long n4 = n / 4, base = n4 / world, rem = n4 % world;            // contiguous shards; the first `rem` ranks take one extra float4
+    A.lo4 = rank * base + (rank < rem ? rank : rem); A.hi4 = A.lo4 + base + (rank < rem ? 1 : 0);
+    A.m = exp_avg; A.v = exp_avg_sq; A.world = world; A.rank = rank;
+    A.a.lr = (float)lr; A.a.b1 = (float)beta1; A.a.b2 = (float)beta2; A.a.eps = (float)eps; A.a.wd = (float)weight_decay;
+    A.a.omb1 = (float)(1.0 - beta1); A.a.omb2 = (float)(1.0 - beta2);
+    A.a.bc1 = (float)(1.0 - pow(beta1, (double)step)); A.a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+    if (A.hi4 == A.lo4) return 0;
+    long long cnt = A.hi4 - A.lo4; int blocks = (int)((cnt + 255) / 256); if (blocks > 148 * 4) blocks = 148 * 4;
+    adam_sharded_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
 
 extern "C" SNB_API int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                                      double lr, double beta1, double beta2, double eps, double weight_decay, int step, void* stream) {

@@ -101,3 +101,46 @@ def all_reduce_gradients(models: Dict[str, torch.nn.Module], average: bool = Tru
             g.copy_(bucket[off:off + g.numel()].view_as(g))
             off += g.numel()
     return 1
+
+
+class SymmetricBuffer:
+    """One flat parameter buffer and its gradient buffer living in symmetric memory: every rank can address every rank's copy
+    (NVLink peer loads / stores), which is what the fused reduce-scatter + Adam + all-gather step (snb_adam_step_sharded) runs on."""
+
+    def __init__(self, n: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.n = n
+        self.n_pad = (n + 3) // 4 * 4                       # the kernel works on float4s; pad elements stay zero
+        group = dist.group.WORLD.group_name
+        self.params = symm.empty(self.n_pad, dtype=torch.float32, device=device)
+        self.grads = symm.empty(self.n_pad, dtype=torch.float32, device=device)
+        self.params.zero_(); self.grads.zero_()
+        self.hp = symm.rendezvous(self.params, group)
+        self.hg = symm.rendezvous(self.grads, group)
+        self.param_ptrs = [int(x) for x in self.hp.buffer_ptrs]
+        self.grad_ptrs = [int(x) for x in self.hg.buffer_ptrs]
+
+    def barrier(self):
+        """Device-side barrier among the ranks on the current stream (signal pads of the symmetric allocation)."""
+        self.hp.barrier()
+
+
+def make_symmetric(models: Dict[str, torch.nn.Module]) -> Dict[int, "SymmetricBuffer"]:
+    """Re-homes the flat parameter / gradient buffers of the fields (and the embedding table) in symmetric memory.  Returns
+    {id(parameter the optimizer steps): SymmetricBuffer}; collective: every rank must call it with the same models."""
+    out = {}
+    for m in models.values():
+        if hasattr(m, "adopt_flat_storage"):
+            n = m.flat_params().numel()
+            sb = SymmetricBuffer(n, m.flat_params().device)
+            m.adopt_flat_storage(sb.params[:n], sb.grads[:n])
+            out[id(m.flat_parameter())] = sb
+        else:
+            for p in m.parameters():
+                sb = SymmetricBuffer(p.numel(), p.device)
+                with torch.no_grad():
+                    sb.params[:p.numel()].copy_(p.data.reshape(-1))
+                    p.data = sb.params[:p.numel()].view(p.shape)
+                    p.grad = sb.grads[:p.numel()].view(p.shape)
+                out[id(p)] = sb
+    return out

@@ -133,6 +133,25 @@ class _Field(nn.Module):
             self._packed_epoch += 1
         return flat
 
+    def adopt_flat_storage(self, flat_new: torch.Tensor, grad_new: torch.Tensor) -> None:
+        """Moves the parameters (values kept) and their gradients into caller-provided flat buffers of the same size -- e.g.
+        symmetric memory that the other ranks of a data-parallel job can address (dist.make_symmetric)."""
+        old = self.flat_params()
+        if flat_new.numel() != old.numel() or grad_new.numel() != old.numel():
+            raise ValueError("adopt_flat_storage: buffers must hold exactly the field's parameters")
+        with torch.no_grad():
+            flat_new.copy_(old)
+            grad_new.zero_()
+            off = 0
+            for p in self.ordered_params():
+                n = p.numel()
+                p.data = flat_new[off:off + n].view(p.shape)
+                p.grad = grad_new[off:off + n].view(p.shape)
+                off += n
+        self._flat, self._flat_grad = flat_new, grad_new
+        object.__setattr__(self, "_flat_param", None)
+        self._packed_epoch += 1
+
     def flat_parameter(self) -> nn.Parameter:
         """The flat buffer as ONE nn.Parameter (shares storage and version counter with `flat_params()`; `.grad` aliases
         `flat_grads()`): what the training harness hands to Adam, so the update is one launch over one tensor.  The module's own

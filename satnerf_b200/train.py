@@ -24,8 +24,35 @@ class FlatAdam(torch.optim.Optimizer):
     fused multi-tensor Adam runs a single large tensor on ~40 CTAs (84 us for 2.6 M parameters against ~12 us here).
     State keys are torch's (`step`, `exp_avg`, `exp_avg_sq`), so optimizer checkpoints interchange with torch.optim.Adam."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, shards=None):
+        """shards: {id(param): dist.SymmetricBuffer} (dist.make_symmetric) switches to the data-parallel step fused with its
+        collective: every rank reduces and updates its shard of each buffer through peer memory and delivers the new parameters to
+        all ranks (snb_adam_step_sharded) -- no all-reduce; each rank keeps the Adam moments of its own shard only."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.shards = shards
+
+    @property
+    def sharded(self) -> bool:
+        return bool(self.shards)
+
+    def _step_sharded(self):
+        rank, _ = sdist.world()
+        first = next(iter(self.shards.values()))
+        first.barrier()                                  # every rank's gradients are final
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                sb = self.shards[id(p)]
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros(sb.n_pad, device=p.device, dtype=torch.float32)
+                    st["exp_avg_sq"] = torch.zeros(sb.n_pad, device=p.device, dtype=torch.float32)
+                st["step"] = int(st["step"]) + 1
+                capi.adam_step_sharded(sb.param_ptrs, sb.grad_ptrs, rank, st["exp_avg"], st["exp_avg_sq"], sb.n_pad,
+                                       float(group["lr"]), b1, b2, group["eps"], group["weight_decay"], st["step"], p.device)
+                torch.autograd.graph.increment_version(p)
+        first.barrier()                                  # every rank's parameters have been delivered (and nobody reads our gradients any more)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -33,6 +60,9 @@ class FlatAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if self.shards:
+            self._step_sharded()
+            return loss
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -113,7 +143,15 @@ class NeRFSystem:
             else:
                 groups += list(m.parameters())
         if groups[0].is_cuda:
-            self.optimizer = FlatAdam(groups, lr=self.args.lr, weight_decay=0)      # one library launch per flat buffer
+            shards = None
+            if sdist.world()[1] > 1 and self.fused and getattr(self.args, "sharded_adam", True) and torch.distributed.get_backend() == "nccl":
+                # data-parallel: parameters and gradients move to symmetric memory; the step reduces / updates / delivers shard-wise
+                # through NVLink peer memory in one kernel per buffer instead of all-reduce + Adam
+                shards = sdist.make_symmetric(self.models)
+                groups = []
+                for m in self.models.values():
+                    groups += [m.flat_parameter()] if hasattr(m, "flat_parameter") else list(m.parameters())
+            self.optimizer = FlatAdam(groups, lr=self.args.lr, weight_decay=0, shards=shards)      # one library launch per flat buffer
         else:
             self.optimizer = torch.optim.Adam(groups, lr=self.args.lr, weight_decay=0)
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=1, gamma=0.9)   # stepped per epoch
@@ -212,7 +250,8 @@ class NeRFSystem:
         if self.fused:
             self.zero_grad()
             loss, info = self.training_step(batch)
-            sdist.all_reduce_gradients(self.models, average=False)       # 1/world is already in the loss seed (n_rays_mean)
+            if not getattr(self.optimizer, "sharded", False):            # (the sharded step reduces the gradients itself, through peer memory)
+                sdist.all_reduce_gradients(self.models, average=False)   # 1/world is already in the loss seed (n_rays_mean)
         else:
             for m in self.models.values():      # grads are (re)assigned as slices of one flat buffer by the render backward
                 for p in m.parameters():
@@ -289,7 +328,9 @@ def bench_training_step(args, dev, rank, world, n_rays, warm, steps, flush, dept
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    what = "DeviceRaySampler batch + render forward + loss seeded in the compositing backward + backward + one flat-gradient all-reduce + Adam"
+    what = "DeviceRaySampler batch + render forward + loss seeded in the compositing backward + backward + " + (
+        "gradient reduction, Adam and parameter delivery fused over NVLink peer memory (snb_adam_step_sharded)" if getattr(system.optimizer, "sharded", False)
+        else "one flat-gradient all-reduce + Adam")
     if depth_batch:
         what += " (colour batch + depth-supervision batch, both coarse + fine)"
     return {"value": world * n_rays * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps, "rays_per_gpu": n_rays,

@@ -81,6 +81,72 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_sharded(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from satnerf_b200 import train as trn
+        from satnerf_b200 import dist as sdist
+        from satnerf_b200.synth import synthetic_sat_rays
+        from gpu_util import make_args
+        R = 256                                             # global batch; every rank takes its shard
+        rays, ts = synthetic_sat_rays(3 * R, seed=17)
+        g = torch.Generator().manual_seed(18)
+        rgbs = torch.rand(3 * R, 3, generator=g)
+        finals = []
+        for sharded in (True, False):
+            a = make_args(fc_units=128, precision="tc", lr=5e-4, batch_size=R, sharded_adam=sharded)
+            torch.manual_seed(5)                            # same initialisation and noise on both runs
+            system = trn.NeRFSystem(a, dev, train_len=3 * R)
+            system.configure_optimizers()
+            assert system.optimizer.sharded == sharded
+            for it in range(3):
+                lo, hi = sdist.shard_bounds(R, rank, world)
+                sl = slice(it * R + lo, it * R + hi)
+                torch.manual_seed(100 + it)                 # the render draws its jitter from the global generator
+                batch = {"color": {"rays": rays[sl].to(dev), "rgbs": rgbs[sl].to(dev), "ts": ts[sl].reshape(-1, 1).to(dev)}}
+                system.optimization_step(batch)
+            torch.cuda.synchronize()
+            finals.append((system.models["coarse"].flat_params().clone(), system.models["t"].weight.detach().clone()))
+        (pa, ta), (pb, tb) = finals
+        ok, msg = True, ""
+        # fused reduce + Adam + deliver step == all-reduce + Adam: the same sum of two ranks' gradients, the same update arithmetic
+        e1 = float((pa - pb).abs().max()); e2 = float((ta - tb).abs().max())
+        if e1 > 1e-7 or e2 > 1e-7:
+            ok, msg = False, f"sharded vs all-reduce: params {e1}, embedding {e2}"
+        ref = pa.clone(); dist.broadcast(ref, 0)
+        if not torch.equal(ref, pa):
+            ok, msg = False, "replicas differ after the sharded step"
+        if float((pa - finals[0][0]).abs().max()) != 0:
+            ok = False
+        q.put((rank, ok, msg))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_adam_step_equals_all_reduce_plus_adam():
+    """The data-parallel step fused with its collective (snb_adam_step_sharded over symmetric memory: peer loads of the gradient
+    shards, Adam, peer stores of the parameters) against all-reduce + snb_adam_step over three steps: <= 1e-7 on parameters of
+    O(0.1) (two ranks: the same two-term sums), replicas bit-identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(r[:2] for r in res) == [(0, True), (1, True)], res
+
+
 @pytest.mark.timeout(300)
 def test_two_gpu_shards_equal_single_gpu():
     if torch.cuda.device_count() < 2:
