@@ -244,6 +244,13 @@ SNB_API int snb_dsm_points(const float* rays, int ray_cols, const float* depth, 
 SNB_API int snb_dsm_rasterize(const double* cloud, long long n_points, double xoff, double yoff, double resolution, int xsize, int ysize,
                       int radius, float* dsm, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batch assembly of the GPU-resident ray sampler (replaces the per-ray DataLoader of main.py:96-110 over the dataset's
+ * __getitem__, datasets/satellite.py:347-350 / satellite_depth.py:138-141): outs[t][i, :] = tables[t][idx[i], :] for up to 4
+ * row-major DEVICE tables (all_rays, all_rgbs | all_depths, all_ids ...) that share the int64 index vector idx (n_rows, DEVICE);
+ * row_bytes[t] multiples of 4.  tables / outs / row_bytes are HOST arrays.  One launch.                                   */
+SNB_API int snb_gather_rows(const void* const* tables, void* const* outs, const int32_t* row_bytes, int n_tables,
+                    const int64_t* idx, long long n_rows, long long n_src_rows, void* stream);
+
 /* Optimiser step of the training loop on a flat parameter buffer (main.py:81-94 builds torch.optim.Adam(lr, weight_decay=0)
  * through train_utils.py:24-53; Lightning calls its step after every training_step): torch.optim.Adam arithmetic (amsgrad
  * off, L2 weight decay folded into the gradient; hyper-parameters as doubles like torch's Python scalars), `step` = 1-based

@@ -90,6 +90,7 @@ _SIGNATURES = {
     "snb_dsm_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snb_dsm_rasterize": (C.c_int, [C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p]),
     "snb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_int, C.c_void_p]),
     "snb_adam_step_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double,
@@ -349,3 +350,26 @@ def adam_step_sharded(peer_param_ptrs, peer_grad_ptrs, rank, exp_avg, exp_avg_sq
     with torch.cuda.device(device):
         _check(lib().snb_adam_step_sharded(pp, gp, world, int(rank), C.c_void_p(exp_avg.data_ptr()), C.c_void_p(exp_avg_sq.data_ptr()), int(n),
                                            lr, beta1, beta2, eps, weight_decay, int(step), _stream(device)), "snb_adam_step_sharded")
+
+
+def gather_rows(tables: Dict[str, torch.Tensor], idx: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """{k: tables[k][idx]} for up to 4 contiguous row-major CUDA tables of 4- or 8-byte elements sharing the int64 index `idx`, in
+    one launch (the batch assembly of data.DeviceRaySampler)."""
+    keys = list(tables)
+    if not 1 <= len(keys) <= 4:
+        raise ValueError("gather_rows: 1..4 tables")
+    dev = idx.device
+    idx = idx.to(torch.int64).contiguous()
+    n, n_src = idx.numel(), tables[keys[0]].shape[0]
+    outs = {}
+    for k in keys:
+        t = tables[k]
+        if not (t.is_cuda and t.is_contiguous() and t.shape[0] == n_src and t.element_size() in (4, 8)):
+            raise ValueError(f"gather_rows: table {k!r} must be a contiguous CUDA tensor of 4- or 8-byte elements with {n_src} rows")
+        outs[k] = torch.empty((n, *t.shape[1:]), dtype=t.dtype, device=dev)
+    src = (C.c_void_p * len(keys))(*[C.c_void_p(tables[k].data_ptr()) for k in keys])
+    dst = (C.c_void_p * len(keys))(*[C.c_void_p(outs[k].data_ptr()) for k in keys])
+    rb = (C.c_int32 * len(keys))(*[int(tables[k][0].numel() * tables[k].element_size()) if n_src else 4 for k in keys])
+    with torch.cuda.device(dev):
+        _check(lib().snb_gather_rows(src, dst, rb, len(keys), C.c_void_p(idx.data_ptr()), n, n_src, _stream(dev)), "snb_gather_rows")
+    return outs

@@ -226,6 +226,7 @@ __global__ void composite_bwd_warp_kernel(CompositeBwdArgs a, float* __restrict_
     }
     float carry = 0.f;                                  // sum over samples beyond the current 32-sample window
     float sums[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float amax = 0.f;
     for (int hi = ((S + 31) / 32) * 32; hi > 0; hi -= 32) {
         const int i = hi - 32 + lane;
         const bool ok = i < S;
@@ -264,6 +265,7 @@ __global__ void composite_bwd_warp_kernel(CompositeBwdArgs a, float* __restrict_
             float o3 = d_sigma * (-expm1f(-sg));
             out[0] = o0; out[1] = o1; out[2] = o2; out[3] = o3;
             sums[0] += o0; sums[1] += o1; sums[2] += o2; sums[3] += o3;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o0), fabsf(o1)), fmaxf(fabsf(o2), fabsf(o3))));
             if (sat) {
                 float ds = g0 * w * c_r * (1.f - k0) + g1 * w * c_g * (1.f - k1) + g2 * w * c_b * (1.f - k2);
                 if (fused) ds += seed.sun_a * (s - T) + seed.sun_b * w;
@@ -274,9 +276,14 @@ __global__ void composite_bwd_warp_kernel(CompositeBwdArgs a, float* __restrict_
                 float o5 = dk0 * k0 * (1.f - k0), o6 = dk1 * k1 * (1.f - k1), o7 = dk2 * k2 * (1.f - k2);
                 out[4] = o4; out[5] = o5; out[6] = o6; out[7] = o7;
                 sums[4] += o4; sums[5] += o5; sums[6] += o6; sums[7] += o7;
-                if (C == 9) { float b = a.beta[p]; float o8 = (fused ? seed.dbeta * w : (a.g_beta ? a.g_beta[p] : 0.f)) * (-expm1f(-b)); out[8] = o8; sums[8] += o8; }
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o4), fabsf(o5)), fmaxf(fabsf(o6), fabsf(o7))));
+                if (C == 9) { float b = a.beta[p]; float o8 = (fused ? seed.dbeta * w : (a.g_beta ? a.g_beta[p] : 0.f)) * (-expm1f(-b)); out[8] = o8; sums[8] += o8; amax = fmaxf(amax, fabsf(o8)); }
             }
         }
+    }
+    if (a.absmax) {                                     // (order-independent: exact max; NaN / Inf leave the scale at 1, see loss_scale)
+        for (int off = 16; off; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(~0u, amax, off));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(a.absmax), __float_as_uint(amax));
     }
     if (ray_sums) {
 #pragma unroll

@@ -22,6 +22,7 @@ struct CompositeBwdArgs {
     const float *weights, *transparency, *sigma, *albedo, *sun, *sky, *beta, *nerf_rgb;          // saved forward results
     const float *g_rgb, *g_depth, *g_weights, *g_transparency, *g_albedo, *g_sun, *g_sky, *g_beta;  // upstream (nullable)
     float* d_head;               // (R*S, C) gradient w.r.t. pre-activation head outputs
+    float* absmax;               // optional device scalar (zeroed by the caller): max |d_head| (bit pattern, atomicMax) -- the loss scale of the fp16 backward
     // fused loss seed (snb_loss_desc): loss_kind != 0 replaces the upstream g_* by dL/d(outputs) computed per ray
     int loss_kind; float lambda, beta_min, inv_n;       // inv_n = 1 / n_rays_mean
     const float *target, *target_w, *g_terms;

@@ -131,3 +131,42 @@ extern "C" SNB_API int snb_importance_depths(const float* z_coarse, const float*
     SNB_CHECK_LAUNCH();
     return 0;
 }
+
+// ---- per-ray batch gather of the GPU-resident ray sampler --------------------------------------------------
+// out_t[i, :] = table_t[idx[i], :] for up to 4 row-major tables sharing one index vector (the reference's
+// DataLoader.__getitem__ + collate over all_rays / all_rgbs | all_depths / all_ids, datasets/satellite.py:347-350), one launch:
+// a thread per 4-byte word of the concatenated output row.
+namespace snb {
+struct GatherArgs { const unsigned int* src[4]; unsigned int* dst[4]; int words[4], first[5]; int n_tables; const long long* idx; long long n_rows, n_src_rows; };
+__global__ void gather_rows_kernel(const __grid_constant__ GatherArgs A) {
+    const int wpr = A.first[A.n_tables];                   // words per concatenated row
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < A.n_rows * wpr; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / wpr; const int w = (int)(e - r * wpr);
+        long long s = A.idx[r];
+        if (s < 0) s += A.n_src_rows;                      // (torch indexing semantics for negative indices)
+        int t = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) if (k < A.n_tables && w >= A.first[k]) t = k;
+        const int c = w - A.first[t];
+        A.dst[t][r * A.words[t] + c] = A.src[t][s * A.words[t] + c];
+    }
+}
+}  // namespace snb
+
+extern "C" SNB_API int snb_gather_rows(const void* const* tables, void* const* outs, const int32_t* row_bytes, int n_tables,
+                                       const int64_t* idx, long long n_rows, long long n_src_rows, void* stream) {
+    using namespace snb;
+    if (!tables || !outs || !row_bytes || n_tables < 1 || n_tables > 4 || n_rows < 0 || (!idx && n_rows)) SNB_FAIL(-1, "snb_gather_rows: bad argument");
+    if (n_rows == 0) return 0;
+    GatherArgs A; memset(&A, 0, sizeof(A));
+    int first = 0;
+    for (int t = 0; t < n_tables; ++t) {
+        if (!tables[t] || !outs[t] || row_bytes[t] < 4 || row_bytes[t] % 4) SNB_FAIL(-1, "snb_gather_rows: table %d: null pointer or row size not a multiple of 4 bytes", t);
+        A.src[t] = (const unsigned int*)tables[t]; A.dst[t] = (unsigned int*)outs[t]; A.words[t] = row_bytes[t] / 4; A.first[t] = first; first += A.words[t];
+    }
+    A.first[n_tables] = first; A.n_tables = n_tables; A.idx = (const long long*)idx; A.n_rows = n_rows; A.n_src_rows = n_src_rows;
+    long long total = n_rows * first; int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}

@@ -97,13 +97,6 @@ __global__ void tc_bwd_tables_kernel(BwdMisc M, long long tables_base, const flo
     }
 }
 
-__global__ void absmax_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
-    float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
-    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(~0u, m, off));
-    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));     // order-independent: exact max
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // the fused input-gradient chain
 // ---------------------------------------------------------------------------------------------------------------
@@ -532,9 +525,7 @@ __global__ void dw_finalize_kernel(const DwOut* __restrict__ outs, const float* 
 // biases of the N<=3 heads: sums over the rays of the per-ray channel sums (fixed-order tree, double accumulation).
 // block c handles channel c of ray_sums (R,16); dst[c] < 0: channel not wanted.
 struct BiasDst { long long off[9]; };
-__global__ void head_bias_kernel(const float* __restrict__ ray_sums, int R, BiasDst d, float* __restrict__ G) {
-    __shared__ double sh[256];
-    const int c = blockIdx.x;
+__device__ __forceinline__ void head_bias_block(double* sh, int c, const float* __restrict__ ray_sums, int R, const BiasDst& d, float* __restrict__ G) {
     if (d.off[c] < 0) return;
     double acc = 0.0;
     for (int r = threadIdx.x; r < R; r += blockDim.x) acc += (double)ray_sums[(size_t)r * 16 + c];
@@ -546,10 +537,9 @@ __global__ void head_bias_kernel(const float* __restrict__ ray_sums, int R, Bias
 // sky_color MLP (per ray, satnerf.py:138-143): gradients of sky0 (H2 x 3) and sky2 (3 x H2) from the per-ray sums of the
 // sky channels.  One block per hidden unit n; its threads stride over the rays and a fixed-order tree combines them
 // (deterministic).
-__global__ void sky_bwd_kernel(const float* __restrict__ ray_sums, const float* __restrict__ rays, int ray_cols, const float* __restrict__ aux,
-                               int R, int H2, const float* __restrict__ W, long long w0, long long b0, long long w2, float* __restrict__ G) {
-    __shared__ float sh[7][128];
-    const int n = blockIdx.x;
+__device__ __forceinline__ void sky_bwd_block(float (*sh)[256], int n, const float* __restrict__ ray_sums, const float* __restrict__ rays, int ray_cols,
+                                              const float* __restrict__ aux, int R, int H2, const float* __restrict__ W, long long w0, long long b0, long long w2,
+                                              float* __restrict__ G) {
     const float w0x = W[w0 + n * 3], w0y = W[w0 + n * 3 + 1], w0z = W[w0 + n * 3 + 2], bb = W[b0 + n];
     const float v0 = W[w2 + n], v1 = W[w2 + H2 + n], v2 = W[w2 + 2 * H2 + n];
     float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // gw2[0..2], gw0[x,y,z], gb0
@@ -565,7 +555,7 @@ __global__ void sky_bwd_kernel(const float* __restrict__ ray_sums, const float* 
 #pragma unroll
     for (int q = 0; q < 7; ++q) sh[q][threadIdx.x] = acc[q];
     __syncthreads();
-    for (int st = 64; st; st >>= 1) {
+    for (int st = 128; st; st >>= 1) {
         if ((int)threadIdx.x < st) {
 #pragma unroll
             for (int q = 0; q < 7; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + st];
@@ -578,13 +568,28 @@ __global__ void sky_bwd_kernel(const float* __restrict__ ray_sums, const float* 
     }
 }
 
-__global__ void ray_sum_t_kernel(const float* __restrict__ per_point, float* __restrict__ per_ray, int n_rays, int S, int D) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void ray_sum_t_block(int blk, const float* __restrict__ per_point, float* __restrict__ per_ray, int n_rays, int S, int D) {
+    int idx = blk * blockDim.x + threadIdx.x;
     if (idx >= n_rays * D) return;
     int r = idx / D, d = idx - r * D;
     float acc = 0.f;
     for (int i = 0; i < S; ++i) acc += per_point[((size_t)r * S + i) * D + d];
     per_ray[idx] = acc;
+}
+
+// The small per-ray remainders of the backward in ONE launch (256 threads per block): blocks [0, 9) the biases of the N <= 3 heads,
+// [9, 9 + H2) the hidden units of the sky-colour MLP, the rest the per-ray sums of the embedding gradient.
+struct TailArgs {
+    const float *ray_sums, *rays, *aux, *W, *d_t; float *G, *g_t_emb;
+    int R, S, H2, ray_cols, t_dims; long long sky0_w, sky0_b, sky2_w; BiasDst bd;
+};
+__global__ void __launch_bounds__(256) bwd_tail_kernel(const __grid_constant__ TailArgs A) {
+    __shared__ double shd[256];
+    __shared__ float shf[7][256];
+    const int b = blockIdx.x;
+    if (b < 9) head_bias_block(shd, b, A.ray_sums, A.R, A.bd, A.G);
+    else if (b < 9 + A.H2) sky_bwd_block(shf, b - 9, A.ray_sums, A.rays, A.ray_cols, A.aux, A.R, A.H2, A.W, A.sky0_w, A.sky0_b, A.sky2_w, A.G);
+    else if (A.d_t) ray_sum_t_block(b - 9 - A.H2, A.d_t, A.g_t_emb, A.R, A.S, A.t_dims);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -888,10 +893,10 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     b.g_albedo = g->g_albedo; b.g_sun = g->g_sun; b.g_sky = g->g_sky; b.g_beta = g->g_beta; b.d_head = d_head;
     SNB_TRY(fill_loss(b, g->loss));
     float* ray_sums = (float*)(ws + B.off_raysums);
-    SNB_TRY(launch_composite_bwd_warp(b, ray_sums, st));
     SNB_CUDA(cudaMemsetAsync(absmax, 0, 256, st));
-    absmax_kernel<<<148, 256, 0, st>>>(d_head, Ptot * C, absmax);
-    SNB_CHECK_LAUNCH();
+    b.absmax = absmax;                                   // max |d_head| is taken while d_head is written
+    SNB_TRY(launch_composite_bwd_warp(b, ray_sums, st));
+    (void)Ptot;
 
     // 2. packed transposed weights + tables, then the input-gradient chain
     A.packed = ws + B.off_packed;
@@ -953,13 +958,13 @@ int tc_render_backward(const FieldLayout& L, const snb_pass_desc* p, const snb_r
     bd.off[0] = L.rgb2.b; bd.off[1] = L.rgb2.b + 1; bd.off[2] = L.rgb2.b + 2; bd.off[3] = L.sigma.b; bd.off[4] = L.sun[3].b;
     bd.off[5] = L.sky2.b; bd.off[6] = L.sky2.b + 1; bd.off[7] = L.sky2.b + 2;
     if (L.variant == SNB_SATNERF) bd.off[8] = L.beta2.b;
-    head_bias_kernel<<<9, 256, 0, st>>>(ray_sums, R, bd, g->g_params); SNB_CHECK_LAUNCH();
-    sky_bwd_kernel<<<H2, 128, 0, st>>>(ray_sums, io->rays, p->ray_cols, io->aux_dir, R, H2, io->params, L.sky0.w, L.sky0.b, L.sky2.w, g->g_params);
+    TailArgs ta; memset(&ta, 0, sizeof(ta));
+    ta.ray_sums = ray_sums; ta.rays = io->rays; ta.aux = io->aux_dir; ta.W = io->params; ta.G = g->g_params; ta.R = R; ta.S = S; ta.H2 = H2;
+    ta.ray_cols = p->ray_cols; ta.sky0_w = L.sky0.w; ta.sky0_b = L.sky0.b; ta.sky2_w = L.sky2.w; ta.bd = bd;
+    ta.d_t = A.d_t; ta.g_t_emb = g->g_t_emb; ta.t_dims = L.t_dims;
+    const int t_blocks = A.d_t ? (R * L.t_dims + 255) / 256 : 0;
+    bwd_tail_kernel<<<9 + H2 + t_blocks, 256, 0, st>>>(ta);
     SNB_CHECK_LAUNCH();
-    if (A.d_t) {
-        ray_sum_t_kernel<<<(R * L.t_dims + 127) / 128, 128, 0, st>>>(d_t, g->g_t_emb, R, S, L.t_dims);
-        SNB_CHECK_LAUNCH();
-    }
     return 0;
 }
 

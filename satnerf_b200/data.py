@@ -6,7 +6,8 @@ num_workers=4, pin_memory=True)` (main.py:96-110) whose dataset answers `__getit
 depth set: `"depths": all_depths[idx]`, datasets/satellite_depth.py:138-141).  That is B Python `__getitem__` calls plus a
 collate per step in worker processes — 1e4-1e5 rays/s, far below the fused render kernel.  `DeviceRaySampler` keeps the
 same tensors resident on the GPU and yields the same batches — a fresh random permutation every epoch, consecutive slices
-of B rays, last batch short (`drop_last=False`) — by indexing on the device.  No kernels of its own: torch indexing only.
+of B rays, last batch short (`drop_last=False`) — assembling each batch on the device with one gather launch over all per-ray
+tables (`snb_gather_rows`).
 """
 from __future__ import annotations
 
@@ -14,6 +15,7 @@ from typing import Dict, Iterator, Optional
 
 import torch
 
+from . import capi
 from .dist import shard_bounds
 
 
@@ -47,7 +49,10 @@ class DeviceRaySampler:
             if self.world > 1:                      # contiguous ray shard of the global batch per rank: the split of dist.shard_bounds
                 lo, hi = shard_bounds(idx.numel(), self.rank, self.world)
                 idx = idx[lo:hi]
-            yield {k: v[idx] for k, v in self.data.items()}
+            if self.device.type == "cuda" and len(self.data) <= 4:
+                yield capi.gather_rows(self.data, idx)       # one launch for all per-ray tables (snb_gather_rows)
+            else:
+                yield {k: v[idx] for k, v in self.data.items()}
 
 
 def combined_loader(loaders: Dict[str, DeviceRaySampler]) -> Iterator[Dict[str, Dict[str, torch.Tensor]]]:

@@ -220,7 +220,8 @@ class NeRFSystem:
 
         loss_dict.update(run(rays, ts, True, color=(kind, rgbs)))
         typ = "fine" if a.n_importance > 0 else "coarse"
-        rgb = torch.cat([r[f"rgb_{typ}"] for r in rgb_parts], 0)
+        colour_mse = loss_dict.get(f"{typ}_color") if (kind == "mse" and world == 1) else None      # = mse(rgb, target) of this batch
+        rgb = rgb_parts[0][f"rgb_{typ}"] if len(rgb_parts) == 1 else torch.cat([r[f"rgb_{typ}"] for r in rgb_parts], 0)
         loss = sum(loss_dict.values())
         a.noise_std *= 0.9
         if self.depth:
@@ -232,7 +233,8 @@ class NeRFSystem:
             if use:
                 loss = loss + sum(tmp.values())
             loss_dict.update(tmp)
-        loss_dict["psnr"] = metrics.psnr(rgb, rgbs)
+        # metrics.py:113-114: psnr = -10 log10(mse(rgb, target)); with the plain colour loss that mse is the term computed above
+        loss_dict["psnr"] = -10.0 * torch.log10(colour_mse) if colour_mse is not None else metrics.psnr(rgb, rgbs)
         del n_mean
         return loss, loss_dict
 
