@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
+    ap.add_argument("--precision", default="tc", choices=["tc", "tcx3", "fp32"])
     ap.add_argument("--only", default="", help="comma list of extra legs to run (train,config3,config4,config5,geometry,gpu_eager,cpu); default: all")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -41,8 +41,11 @@ extern "C" {
 enum { SNB_NERF = 0, SNB_SNERF = 1, SNB_SATNERF = 2 };
 /* arithmetic of the MLP contractions */
 enum { SNB_FP32_SIMT = 0,   /* fp32 FFMA on CUDA cores: the exactness path                        */
-       SNB_FP16_TC = 1 };   /* fp16 operands / fp32 accumulate on tcgen05 tensor cores (sm_100a);
+       SNB_FP16_TC = 1,     /* fp16 operands / fp32 accumulate on tcgen05 tensor cores (sm_100a);
                                first trunk layer and all head outputs stay fp32                    */
+       SNB_FP16X3_TC = 2 }; /* forward: the layer-by-layer path with every wide contraction on the tensor cores at fp16 hi+lo
+                               operand precision (3 MMAs per K-step, 2^-22 relative; ~14x the FFMA path); backward: as
+                               SNB_FP32_SIMT                                                        */
 
 /* Field architecture = constructor arguments of models.load_model (models/__init__.py:6-15). */
 typedef struct snb_field_desc {
@@ -61,7 +64,7 @@ typedef struct snb_pass_desc {
     int32_t n_samples;       /* S (coarse: args.n_samples; fine: n_samples + n_importance)      */
     int32_t ray_cols;        /* 8 (nerf) or 11: o(3) d(3) near far [sun(3)]  (rendering.py:62)  */
     int32_t march_along_sun; /* 1 = solar-correction pass, points = o + sun_d*z (rendering.py:104) */
-    int32_t precision;       /* SNB_FP32_SIMT | SNB_FP16_TC                                     */
+    int32_t precision;       /* SNB_FP32_SIMT | SNB_FP16_TC | SNB_FP16X3_TC                     */
     float   noise_std;       /* args.noise_std; multiplies `noise` (satnerf.py:57-58)           */
     int32_t weights_packed;  /* SNB_FP16_TC forward only: 1 = `workspace` still holds the packed fp16 weight tiles this
                                 library wrote there on an earlier call with the SAME parameter values (the caller
@@ -199,7 +202,8 @@ SNB_API int snb_loss_backward(const snb_pass_desc* p, const snb_render_io* io, c
 
 /* <Field>.forward on B independent points (satnerf.py:156-208): xyz (B,3); aux_dir (B,3) = sun
  * direction (sat-nerf / s-nerf) or view direction (nerf); t_emb (B,t_dims); out (B,C) with
- * C = 9 / 8 / 4 = [rgb3, sigma, sun, sky3, beta]; sigma_only -> out (B,1) (satnerf.py:184-185). */
+ * C = 9 / 8 / 4 = [rgb3, sigma, sun, sky3, beta]; sigma_only -> out (B,1) (satnerf.py:184-185).
+ * precision: SNB_FP32_SIMT or SNB_FP16X3_TC (tensor cores, fp16 hi+lo operands; per-POINT sun / embedding inputs). */
 SNB_API int snb_field_workspace(const snb_field_desc* f, int n_points, size_t* bytes);
 SNB_API int snb_field_forward(const snb_field_desc* f, const float* params, const float* xyz,
                       const float* aux_dir, const float* t_emb, float* out, int n_points,

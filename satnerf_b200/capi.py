@@ -15,7 +15,7 @@ import torch
 _LIB_PATH = os.environ.get("SNB_LIBRARY_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsatnerf_b200.so")   # (override: developer A/B builds)
 
 NERF, SNERF, SATNERF = 0, 1, 2
-FP32_SIMT, FP16_TC = 0, 1
+FP32_SIMT, FP16_TC, FP16X3_TC = 0, 1, 2
 VARIANTS = {"nerf": NERF, "s-nerf": SNERF, "sat-nerf": SATNERF}
 
 c_float_p = C.POINTER(C.c_float)

@@ -25,7 +25,7 @@ int check_pass(const FieldLayout& L, const snb_pass_desc* p) {
     int need = L.variant == SNB_NERF ? 8 : 11;
     if (p->ray_cols != 0 && p->ray_cols < need) SNB_FAIL(-1, "rays need %d columns for this variant, got %d", need, p->ray_cols);
     if (p->march_along_sun && L.variant == SNB_NERF) SNB_FAIL(-1, "solar-correction pass is undefined for nerf");
-    if (p->precision != SNB_FP32_SIMT && p->precision != SNB_FP16_TC) SNB_FAIL(-1, "unknown precision %d", p->precision);
+    if (p->precision != SNB_FP32_SIMT && p->precision != SNB_FP16_TC && p->precision != SNB_FP16X3_TC) SNB_FAIL(-1, "unknown precision %d", p->precision);
     if ((int64_t)p->n_rays * p->n_samples > (int64_t)1 << 30) SNB_FAIL(-1, "too many points in one pass");
     return 0;
 }
@@ -90,7 +90,7 @@ extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pas
         if (r != 1) return r;      // 1 = configuration not covered by the tensor-core kernel: fp32 CUDA-core path below
     }
 
-    if (p->flags & SNB_PASS_SIGMA_ONLY) SNB_FAIL(-1, "SNB_PASS_SIGMA_ONLY is provided by the tensor-core path only (precision SNB_FP16_TC, a shape it covers)");
+    if (p->flags & SNB_PASS_SIGMA_ONLY) SNB_FAIL(-1, "SNB_PASS_SIGMA_ONLY is provided by the fused tensor-core path only (precision SNB_FP16_TC, a shape it covers)");
     Arena ar(workspace, workspace_bytes); PassPlan pl; plan_pass(ar, L, p, false, &pl);
     if (ar.overflow) SNB_FAIL(-4, "snb_render_forward: workspace too small (%zu bytes given)", workspace_bytes);
     const int S = p->n_samples, C = L.n_channels;
@@ -99,6 +99,7 @@ extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pas
         int rc = p->n_rays - r0 < pl.rays_per_chunk ? p->n_rays - r0 : pl.rays_per_chunk;
         if (!io->xyz) SNB_TRY(launch_points(io->rays, p->ray_cols, dir_col, io->z_vals, pl.xyz, r0, rc, S, st));
         FieldInputs in = chunk_inputs(L, p, io, pl.xyz, r0, rc);
+        in.x3 = p->precision == SNB_FP16X3_TC;
         SNB_TRY(field_forward_chunk(L, io->params, pl.chunk, in, pl.raw + (size_t)r0 * S * C, false, st));
     }
     CompositeArgs a{};
@@ -142,6 +143,7 @@ extern "C" SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pa
         int rc = p->n_rays - r0 < pl.rays_per_chunk ? p->n_rays - r0 : pl.rays_per_chunk;
         if (!io->xyz) SNB_TRY(launch_points(io->rays, p->ray_cols, dir_col, io->z_vals, pl.xyz, r0, rc, S, st));
         FieldInputs in = chunk_inputs(L, p, io, pl.xyz, r0, rc);
+        in.x3 = p->precision == SNB_FP16X3_TC;       // the recompute runs the arithmetic the forward ran
         SNB_TRY(field_forward_chunk(L, io->params, pl.chunk, in, pl.raw_chunk, false, st));
         float* gt = (g->g_t_emb && L.t_dims) ? g->g_t_emb + (size_t)r0 * L.t_dims : nullptr;
         SNB_TRY(field_backward_chunk(L, io->params, g->g_params, pl.chunk, in, pl.d_head + (size_t)r0 * S * C, gt, S, st));
@@ -202,7 +204,8 @@ extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* p
     if (!sigma_only && L.variant != SNB_NERF && !aux_dir) SNB_FAIL(-1, "snb_field_forward: input_sun_dir is required");
     if (!sigma_only && L.variant == SNB_NERF && !aux_dir) SNB_FAIL(-1, "snb_field_forward: input_dir is required");
     if (!sigma_only && L.t_dims && !t_emb) SNB_FAIL(-1, "snb_field_forward: input_t is required (satnerf.py:204)");
-    if (precision != SNB_FP32_SIMT) SNB_FAIL(-1, "snb_field_forward: only SNB_FP32_SIMT is provided for the per-point API");
+    if (precision != SNB_FP32_SIMT && precision != SNB_FP16X3_TC)
+        SNB_FAIL(-1, "snb_field_forward: the per-point API runs at SNB_FP32_SIMT or SNB_FP16X3_TC (the fused SNB_FP16_TC kernel takes per-ray inputs)");
     if (n_points == 0) return 0;
     if (!workspace) SNB_FAIL(-1, "snb_field_forward: null workspace");
     int pc = n_points < kChunkPoints ? n_points : kChunkPoints;
@@ -215,6 +218,7 @@ extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* p
         in.xyz = Src{xyz + (size_t)p0 * 3, 3, 3, 1};
         in.aux = aux_dir ? Src{aux_dir + (size_t)p0 * 3, 3, 3, 1} : Src{nullptr, 0, 0, 1};
         in.temb = (L.t_dims && t_emb) ? Src{t_emb + (size_t)p0 * L.t_dims, L.t_dims, L.t_dims, 1} : Src{nullptr, 0, 0, 1};
+        in.x3 = precision == SNB_FP16X3_TC;
         SNB_TRY(field_forward_chunk(L, params, c, in, out + (size_t)p0 * C, sigma_only != 0, (cudaStream_t)stream));
     }
     return 0;

@@ -6,6 +6,7 @@
 // Restates SatNeRF.forward (models/satnerf.py:156-208), ShadowNeRF.forward (models/snerf.py:148-196),
 // NeRF.forward + Mapping (models/nerf.py:184-227, :36-69); the backward is what autograd derives.
 #include "simt_field.cuh"
+#include "sm100_ptx.cuh"
 
 namespace snb {
 
@@ -219,10 +220,266 @@ __global__ void __launch_bounds__(NT) linear_bwd_w_kernel(LinBwdW p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow heads (N <= 4: sigma, rgb, sun, sky, beta outputs): one warp per row, the row read once with coalesced loads, the N
+// dot products reduced with shuffles.  fp32 FFMA like the tiled kernel (which would idle 60 of its 64 tile columns here).
+// ------------------------------------------------------------------------------------------------
+constexpr int NARROW_MAX_N = 4, NARROW_MAX_K = 1024;
+template <int ACT>
+__global__ void __launch_bounds__(256) linear_fwd_narrow_kernel(LinFwd p) {
+    __shared__ float Ws[NARROW_MAX_N * NARROW_MAX_K];
+    const int K = p.a0.k + p.a1.k;
+    for (int i = threadIdx.x; i < NARROW_MAX_N * K; i += 256) Ws[i] = i < p.N * K ? p.W[(size_t)(i / K) * p.ldw + (i % K)] : 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int m = blockIdx.x * 8 + warp; m < p.M; m += gridDim.x * 8) {
+        float acc[NARROW_MAX_N] = {};
+        if (p.a1.k == 0 && p.a0.div == 1) {                       // (every head of the three fields: one plain row-major source)
+            const float* row = p.a0.p + (size_t)m * p.a0.ld;
+#pragma unroll 4
+            for (int k = lane; k < K; k += 32) {
+                const float a = row[k];
+#pragma unroll
+                for (int n = 0; n < NARROW_MAX_N; ++n) acc[n] = fmaf(a, Ws[n * K + k], acc[n]);
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) {
+                const float a = src_at(p.a0, p.a1, m, k);
+#pragma unroll
+                for (int n = 0; n < NARROW_MAX_N; ++n) acc[n] = fmaf(a, Ws[n * K + k], acc[n]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NARROW_MAX_N; ++n)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+        if (lane < p.N) {
+            float y = 0.f;
+#pragma unroll
+            for (int n = 0; n < NARROW_MAX_N; ++n) if (n == lane) y = acc[n];
+            y += p.b[lane];
+            if (p.pre) p.pre[(size_t)m * p.N + lane] = y;
+            p.out[(size_t)m * p.ldo + lane] = act_fwd<ACT>(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SNB_FP16X3_TC: the same Y = act(cat(A0,A1) W^T + b) on the tensor cores at (almost) fp32 operand precision.
+// Every fp32 operand is split on the fly into fp16 hi + lo (x = hi + lo to 2^-22 |x|, or 2^-25 absolute below the fp16 normal
+// range) and the contraction is issued as three tcgen05 MMAs per K-step -- A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulation
+// in TMEM (the lo x lo term is 2^-22 of the product and dropped).  One CTA = 128 rows x `nt` <= 256 columns.  K runs over the
+// two sources one after the other (each padded to whole 64-wide slabs, so the loads of the wide source stay aligned whatever
+// the width of the narrow one).  Per slab the 256 threads read the fp32 operands from global memory -- one warp instruction =
+// one 256-byte row segment, two floats per lane -- split them and write the four 128B-swizzled fp16 tiles of a 2-stage ring;
+// one thread issues the 12 MMAs, and the next slab is converted while they run.  The epilogue transposes the accumulator
+// through shared memory (32 x 32 blocks per warp) so that rows leave as 128-byte stores.
+// For deep optical depths (trained scenes) the plain fp16-operand kernel reaches 1e-2 on the weights; this path
+// stays at the fp32 level.
+// ------------------------------------------------------------------------------------------------
+using namespace ptx;
+constexpr int X3_NT = 256;                      // columns per CTA at most (UMMA N)
+constexpr int X3_STAGE = 2 * 16384 + 2 * X3_NT * 128;      // A_hi | A_lo | W_hi | W_lo
+constexpr int X3_THREADS = 512;                // 16 warps: the split / store stream is latency-bound with fewer
+constexpr int X3_RPT = 64 * 32 / X3_THREADS;     // rows of a 64-row batch per thread
+
+constexpr float X3_WSCALE = 256.f;             // weights enter as 256 w (exact), the accumulator leaves as acc / 256: SIREN-scale weights
+                                                // (|w| ~ 4e-3 at h = 512) keep a NORMAL fp16 lo part; |w| < 255 is required (inf otherwise)
+
+__device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// Work of one CTA = a stream of BATCHES: 64 rows x 64 columns of fp32 (one warp instruction = one 256-byte row segment, two floats
+// per lane; X3_RPT rows per thread).  Slab `it` = 2 batches of A rows + ceil(nt / 64) batches of W rows.  Three batches are in flight
+// in registers while a fourth is split and stored (48 KB of loads outstanding per SM, which covers the L2 latency).
+struct X3Cursor {            // (slab, batch-in-slab) of the next batch, advanced without divisions
+    int it = 0, b = 0;
+    __device__ __forceinline__ void next(int bps) { if (++b == bps) { b = 0; ++it; } }
+};
+
+__device__ __forceinline__ void x3_load(const LinFwd& p, int m0, int n0, int s0, int n_slabs, const X3Cursor& c, float2 (&v)[X3_RPT]) {
+    if (c.it >= n_slabs) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool second = c.it >= s0;
+    const float* ap = second ? p.a1.p : p.a0.p;
+    const int a_ld = second ? p.a1.ld : p.a0.ld, a_div = second ? p.a1.div : p.a0.div, k_end = second ? p.a1.k : p.a0.k;
+    const int k = (second ? c.it - s0 : c.it) * 64 + 2 * lane;
+    const float* base; int ld, div, row0, row_end;
+    if (c.b < 2) { base = ap; ld = a_ld; div = a_div; row0 = m0 + 64 * c.b + warp; row_end = p.M; }
+    else { base = p.W + (second ? p.a0.k : 0); ld = p.ldw; div = 1; row0 = n0 + 64 * (c.b - 2) + warp; row_end = p.N; }
+    const bool in2 = k + 1 < k_end, in1 = k < k_end;
+    if (div == 1 && (ld & 1) == 0 && (((uintptr_t)base & 7u) == 0) && in2) {            // the wide sources: 8-byte loads, rows ld apart
+        const float* q = base + (size_t)row0 * ld + k;
+#pragma unroll
+        for (int j = 0; j < X3_RPT; ++j) {
+            v[j] = make_float2(0.f, 0.f);
+            if (row0 + (X3_THREADS / 32) * j < row_end) v[j] = *reinterpret_cast<const float2*>(q + (size_t)((X3_THREADS / 32) * j) * ld);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < X3_RPT; ++j) {
+            const int r = row0 + (X3_THREADS / 32) * j;
+            v[j] = make_float2(0.f, 0.f);
+            if (r < row_end && in1) {
+                const float* q = base + (size_t)(div == 1 ? r : r / div) * ld + k;
+                v[j].x = q[0];
+                if (in2) v[j].y = q[1];
+            }
+        }
+    }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(X3_THREADS, 1) linear_fwd_x3_kernel(LinFwd p, int nt_tile) {
+    extern __shared__ unsigned char x3_raw[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)x3_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * X3_STAGE);       // [0,1]: stage consumed by its MMAs; [2]: accumulator complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+    const int s0 = (p.a0.k + 63) / 64, s1 = (p.a1.k + 63) / 64, n_slabs = s0 + s1;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * nt_tile;
+    int nv = p.N - n0; if (nv > nt_tile) nv = nt_tile;                           // valid columns of this CTA
+    const int nt = (nv + 15) & ~15;                                              // UMMA N: multiple of 16
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(tmem_ptr, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t idesc = umma_idesc_f16((uint32_t)nt);
+    const int bps = 2 + (nt + 63) / 64;
+    const uint32_t sbase = smem_u32(base);
+    // this thread's rows of a batch are warp + 16 j: (row & 7) == (warp & 7), so the swizzle term of its tile offsets is a constant
+    const uint32_t lane_off = (uint32_t)warp * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+
+    auto process = [&](const X3Cursor& c, float2 (&v)[X3_RPT]) {
+        if (c.it >= n_slabs) return;
+        const int it = c.it, b = c.b, st = it & 1;
+        const uint32_t stage = sbase + (uint32_t)st * X3_STAGE;
+        if (b == 0 && it >= 2) mbar_wait(&bars[st], (uint32_t)((it >> 1) - 1) & 1u, 31);   // the MMAs that read this stage two slabs ago are done
+        const bool is_a = b < 2;
+        const uint32_t hi_t = stage + (is_a ? 0u : 32768u) + (uint32_t)(is_a ? b : b - 2) * 8192u + lane_off;
+        const uint32_t lo_d = is_a ? 16384u : (uint32_t)X3_NT * 128u;                       // lo tile - hi tile
+        const int rows_left = (is_a ? 128 : nt) - 64 * (is_a ? b : b - 2) - warp;          // rows warp + 16 j of this batch below the tile's end
+        const float scale = is_a ? 1.f : X3_WSCALE;
+#pragma unroll
+        for (int j = 0; j < X3_RPT; ++j) {
+            if ((X3_THREADS / 32) * j < rows_left) {
+                const float x0 = v[j].x * scale, x1 = v[j].y * scale;
+                const __half2 hh = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                sts_b32(hi_t + (uint32_t)j * (X3_THREADS / 32 * 128u), *reinterpret_cast<const uint32_t*>(&hh));
+                sts_b32(hi_t + lo_d + (uint32_t)j * (X3_THREADS / 32 * 128u), *reinterpret_cast<const uint32_t*>(&ll));
+            }
+        }
+        if (b == bps - 1) {
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (t == 0) {
+                tc_fence_after();
+                const bool second = it >= s0;
+                const int k_left = (second ? p.a1.k : p.a0.k) - (second ? it - s0 : it) * 64;
+                int ks = (k_left + 15) / 16; if (ks > 4) ks = 4;                           // K-steps of this slab that hold data
+                const uint32_t a_hi = stage, a_lo = stage + 16384u, w_hi = stage + 32768u, w_lo = w_hi + (uint32_t)X3_NT * 128u;
+                for (int k = 0; k < ks; ++k) {
+                    umma_f16_ss(tmem, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(w_hi + k * 32), idesc, (it | k) != 0);
+                    umma_f16_ss(tmem, umma_desc_k_sw128(a_lo + k * 32), umma_desc_k_sw128(w_hi + k * 32), idesc, 1u);
+                    umma_f16_ss(tmem, umma_desc_k_sw128(a_hi + k * 32), umma_desc_k_sw128(w_lo + k * 32), idesc, 1u);
+                }
+                umma_commit(&bars[st]);
+                if (it == n_slabs - 1) umma_commit(&bars[2]);
+            }
+        }
+    };
+    {
+        float2 v0[X3_RPT], v1[X3_RPT], v2[X3_RPT];
+        X3Cursor lc, pc;                                     // load cursor runs three batches ahead of the process cursor
+        x3_load(p, m0, n0, s0, n_slabs, lc, v0); lc.next(bps);
+        x3_load(p, m0, n0, s0, n_slabs, lc, v1); lc.next(bps);
+        x3_load(p, m0, n0, s0, n_slabs, lc, v2); lc.next(bps);
+        while (pc.it < n_slabs) {
+            process(pc, v0); pc.next(bps); x3_load(p, m0, n0, s0, n_slabs, lc, v0); lc.next(bps);
+            process(pc, v1); pc.next(bps); x3_load(p, m0, n0, s0, n_slabs, lc, v1); lc.next(bps);
+            process(pc, v2); pc.next(bps); x3_load(p, m0, n0, s0, n_slabs, lc, v2); lc.next(bps);
+        }
+    }
+    mbar_wait(&bars[2], 0u, 32);
+    tc_fence_after();
+    // epilogue: warp w reads TMEM lanes 32 (w % 4) ..; the warps of a lane quadrant take the 32-column blocks in turn.  Each
+    // block goes through a 32 x 33 shared-memory scratch (the ring is free now) so that one store instruction = one row segment.
+    {
+        float* scratch = reinterpret_cast<float*>(base) + warp * (32 * 33);
+        const int quad = warp & 3;
+        for (int c0 = (warp >> 2) * 32; c0 < nt; c0 += (X3_THREADS / 128) * 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = v[i];
+            __syncwarp();
+            const int n = n0 + c0 + lane;
+            const bool col_ok = c0 + lane < nv;
+            const float bias = col_ok ? p.b[n] : 0.f;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const int m = m0 + quad * 32 + r;
+                if (m < p.M && col_ok) {
+                    const float y = fmaf(scratch[r * 33 + lane], 1.f / X3_WSCALE, bias);
+                    if (p.pre) p.pre[(size_t)m * p.N + n] = y;
+                    p.out[(size_t)m * p.ldo + n] = act_fwd<ACT>(y);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <int ACT>
+static int launch_x3(const LinFwd& p, cudaStream_t st) {
+    const size_t smem = 2 * (size_t)X3_STAGE + 1024 + 64;
+    static bool attr_set = false;
+    if (!attr_set) { SNB_CUDA(cudaFuncSetAttribute(linear_fwd_x3_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    // 256-column tiles unless that leaves most SMs without a CTA (the h/2-wide head layers of one chunk)
+    const int nt_tile = (p.N > 128 && ceil_div(p.M, 128) * ceil_div(p.N, X3_NT) < 100) ? 128 : X3_NT;
+    dim3 g(ceil_div(p.M, 128), ceil_div(p.N, nt_tile));
+    linear_fwd_x3_kernel<ACT><<<g, X3_THREADS, smem, st>>>(p, nt_tile);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+template <int ACT>
+static int launch_narrow(const LinFwd& p, cudaStream_t st) {
+    int blocks = ceil_div(p.M, 8); if (blocks > 148 * 4) blocks = 148 * 4;
+    linear_fwd_narrow_kernel<ACT><<<blocks, 256, 0, st>>>(p);
+    SNB_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static int run_fwd(int act, const LinFwd& p, cudaStream_t st) {
+static int run_fwd(int act, const LinFwd& p, cudaStream_t st, int x3 = 0) {
     if (p.M == 0) return 0;
+    if (p.N <= NARROW_MAX_N && p.a0.k + p.a1.k <= NARROW_MAX_K && p.a0.k + p.a1.k >= 64) {
+        switch (act) {
+            case ACT_NONE: return launch_narrow<ACT_NONE>(p, st);
+            case ACT_SIGMOID: return launch_narrow<ACT_SIGMOID>(p, st);
+            case ACT_SOFTPLUS: return launch_narrow<ACT_SOFTPLUS>(p, st);
+            case ACT_SIGMOID_PAD: return launch_narrow<ACT_SIGMOID_PAD>(p, st);
+            default: break;
+        }
+    }
+    if (x3 && p.N >= 32 && p.a0.k + p.a1.k >= 16) {          // (short contractions -- K = 3 inputs -- stay on the FFMA kernel)
+        switch (act) {
+            case ACT_NONE: return launch_x3<ACT_NONE>(p, st);
+            case ACT_SIN: return launch_x3<ACT_SIN>(p, st);
+            case ACT_SIN30: return launch_x3<ACT_SIN30>(p, st);
+            case ACT_RELU: return launch_x3<ACT_RELU>(p, st);
+            default: break;
+        }
+    }
     dim3 g(ceil_div(p.M, BM), ceil_div(p.N, BN));
     switch (act) {
         case ACT_NONE: linear_fwd_kernel<ACT_NONE><<<g, NT, 0, st>>>(p); break;
@@ -321,7 +578,7 @@ int field_forward_chunk(const FieldLayout& L, const float* P, const FieldChunk& 
     auto fwd = [&](const Lin& l, Src a0, Src a1, int act, float* pre, float* out, int ldo) {
         LinFwd p; p.a0 = a0; p.a1 = a1; p.W = P + l.w; p.ldw = l.n_in; p.b = P + l.b; p.pre = pre; p.out = out; p.ldo = ldo; p.M = Pc; p.N = l.n_out;
         if (a0.k + a1.k != l.n_in) { set_error("internal: layer K mismatch (%d+%d vs %d)", a0.k, a1.k, l.n_in); return -3; }
-        return run_fwd(act, p, st);
+        return run_fwd(act, p, st, in.x3);
     };
     for (int i = 0; i < nl; ++i) {
         Src a0 = i == 0 ? x : (i == L.skip ? x : S_(c.act[i - 1], h, h));

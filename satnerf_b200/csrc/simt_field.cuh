@@ -12,7 +12,7 @@ struct LinFwd  { Src a0, a1; const float* W; int ldw; const float* b; float* pre
 struct LinBwdIn { const float* dY; int ldy, N; const float* W; int ldw, k_off, K; const float* pre; float* dX; int ldx, accumulate, M; };
 struct LinBwdW { const float* dY; int ldy, N; Src a0, a1; float* partial; int M, m_per_z; };
 
-struct FieldInputs { Src xyz, aux, temb; int n_points; };
+struct FieldInputs { Src xyz, aux, temb; int n_points; int x3 = 0; };      // x3: forward contractions on the tensor cores with fp16 hi+lo operands (SNB_FP16X3_TC)
 
 // Buffers for one chunk of points, carved from the caller's workspace.
 struct FieldChunk {

@@ -208,12 +208,23 @@ class _Field(nn.Module):
         if sigma_only and aux_ is None:
             aux_ = torch.zeros_like(xyz)                     # (unused by the sigma head; the backward's buffers want a direction)
         needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or (input_t is not None and input_t.requires_grad))
+        prec = self._points_precision()
         if not needs_grad:
-            return capi.field_forward(self._desc, self.flat_params(), xyz, aux_, t_, sigma_only, self.number_of_outputs)
+            return capi.field_forward(self._desc, self.flat_params(), xyz, aux_, t_, sigma_only, self.number_of_outputs, prec)
         if sigma_only and self.variant == "sat-nerf" and t_ is None:
             t_ = torch.zeros(xyz.shape[0], self._desc.t_dims, device=xyz.device)
         t_in = input_t if (input_t is not None and not sigma_only) else None
-        return _PointsFn.apply(self, xyz, aux_, t_, sigma_only, t_in, *self.ordered_params())
+        return _PointsFn.apply(self, xyz, aux_, t_, sigma_only, t_in, prec, *self.ordered_params())
+
+    def _points_precision(self) -> int:
+        """`field.points_precision`: 'tcx3' (default on sm_100: contractions on the tensor cores, fp16 hi+lo operands, fp32-level
+        results) | 'fp32' (FFMA).  The gradients are the fp32 CUDA-core chain either way."""
+        p = getattr(self, "points_precision", None)
+        if p is None:
+            p = "tcx3" if capi.device_supports_tc() else "fp32"
+        if p not in ("tcx3", "fp32"):
+            raise ValueError(f"points_precision {p!r} is not valid (tcx3 | fp32)")
+        return capi.FP16X3_TC if p == "tcx3" else capi.FP32_SIMT
 
 
 class _PointsFn(torch.autograd.Function):
@@ -222,8 +233,8 @@ class _PointsFn(torch.autograd.Function):
     to input_xyz / the directions -- the reference's training never asks for one (rays are data)."""
 
     @staticmethod
-    def forward(ctx, field, xyz, aux, t_emb, sigma_only, t_in, *params):
-        out = capi.field_forward(field._desc, field.flat_params(), xyz, aux, t_emb, sigma_only, field.number_of_outputs)
+    def forward(ctx, field, xyz, aux, t_emb, sigma_only, t_in, prec, *params):
+        out = capi.field_forward(field._desc, field.flat_params(), xyz, aux, t_emb, sigma_only, field.number_of_outputs, prec)
         ctx.field, ctx.sigma_only, ctx.has_t = field, sigma_only, t_in is not None
         ctx.save_for_backward(xyz, aux, out, *([t_emb] if t_emb is not None else []))
         return out
@@ -241,7 +252,7 @@ class _PointsFn(torch.autograd.Function):
             n = p.numel()
             gp.append(g_flat[off:off + n].view(p.shape))
             off += n
-        return (None, None, None, None, None, g_t if ctx.has_t else None, *gp)
+        return (None, None, None, None, None, g_t if ctx.has_t else None, None, *gp)
 
 
 class NeRF(_Field):

@@ -8,6 +8,8 @@ sampling, the MLP, compositing and their gradients run in libsatnerf_b200.so thr
 `args` is the reference's argparse Namespace.  Extra, optional attributes understood here:
   args.precision : 'tc'  (default on sm_100: fp16 operands / fp32 accumulate on tcgen05 tensor cores)
                    'fp32' (fp32 FFMA CUDA-core path, matches the reference to rounding level)
+                   'tcx3' (layer-by-layer path with every wide contraction on the tensor cores at fp16 hi+lo operand precision:
+                           fp32-level results -- for checkpoints whose optical depths push the fp16-operand kernel past 1e-3)
   args.render_outputs : 'full' (default: the reference's result dict)
                    'eval'  (no_grad only) per-ray outputs: rgb_*, depth_* and the weighted images eval_satnerf.py:125-146 builds
                            from the per-sample tensors -- sun_w_*, albedo_w_*, beta_w_*, sky_w_* = sum_i w_i x_i -- computed in-kernel
@@ -32,9 +34,9 @@ def _precision(args) -> int:
     p = getattr(args, "precision", None)
     if p is None:
         p = "tc" if capi.device_supports_tc() else "fp32"
-    if p not in ("tc", "fp32"):
-        raise ValueError(f"precision {p!r} is not valid (tc | fp32)")
-    return capi.FP16_TC if p == "tc" else capi.FP32_SIMT
+    if p not in ("tc", "fp32", "tcx3"):
+        raise ValueError(f"precision {p!r} is not valid (tc | tcx3 | fp32)")
+    return {"tc": capi.FP16_TC, "tcx3": capi.FP16X3_TC, "fp32": capi.FP32_SIMT}[p]
 
 
 def _out_shapes(variant: str, R: int, S: int):

@@ -6,8 +6,9 @@ for everything else — outputs that reach 0 need an absolute floor; 1e-3 is nor
 the max-abs / max-ref measure used elsewhere.  Measured maxima are appended to gpurun_out/parity_report.json.
 
 The 'trained-like' regime (density head sharpened x64 so that rays saturate mid-way) is reported separately: the fp16-operand
-contractions carry ~1e-4 relative error on the trunk features, which the sharp density head multiplies — the fp32 path is
-gated at 1e-3 there and the tensor-core path at the bound written in `test_trained_like_regime`.
+contractions carry ~1e-4 relative error on the trunk features, which the sharp density head multiplies — the fp32 path and
+the hi+lo tensor-core path (precision 'tcx3') are gated at 1e-3 there and the fp16-operand kernel at the bound written in
+`test_trained_like_regime`.
 """
 import json
 import os
@@ -176,6 +177,8 @@ def test_trained_like_golden(name):
     assert float(w.argmax(-1).float().mean()) < 50 and float(w[:, -1].mean()) < 0.5          # rays do saturate mid-way
     _, _, res = run_golden(g, "fp32")
     _compare(f"{name}_fp32", res, g.out)
+    _, _, res = run_golden(g, "tcx3")             # tensor cores, fp16 hi+lo operands: the same strict gate as the fp32 path
+    _compare(f"{name}_tcx3", res, g.out)
     _, _, res = run_golden(g, "tc")
     rows = {k: {"elementwise_excess": elementwise_excess(res[k].cpu(), g.out[k], k), "max_rel": rel_err(res[k].cpu(), g.out[k])} for k in g.out}
     _report(f"{name}_tc", rows)
@@ -196,9 +199,12 @@ def test_trained_like_regime_fullsize():
     want = orc.render_rays(params, args, rays, ts, orc.Draws(draws))
     with torch.no_grad():
         got32 = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
+        args.precision = "tcx3"
+        gotx3 = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
         args.precision = "tc"
         got16 = sb.render_rays(ms, args, rays.cuda(), ts.cuda(), _draws=draws)
     _compare("trained_like_fullsize_fp32", got32, want)
+    _compare("trained_like_fullsize_tcx3", gotx3, want)
     rows = {k: {"elementwise_excess": elementwise_excess(got16[k].cpu(), want[k], k), "max_rel": rel_err(got16[k].cpu(), want[k])} for k in want}
     _report("trained_like_fullsize_tc", rows)
     for k, v in rows.items():

@@ -242,6 +242,44 @@ def test_field_forward_matches_oracle():
     assert sig.shape == (333, 1) and rel_err(sig.cpu(), want[:, 3:4]) < 2e-5
 
 
+@pytest.mark.parametrize("model,h", [("sat-nerf", 512), ("sat-nerf", 256), ("s-nerf", 192), ("nerf", 256), ("sat-nerf", 72)])
+def test_field_forward_tensor_cores_hi_lo(model, h):
+    """<Field>.forward with the contractions on the tensor cores at fp16 hi+lo operand precision (SNB_FP16X3_TC, the default of
+    the per-point API on sm_100) against the float64 oracle, on ragged point counts and widths that are not multiples of the tile.
+    Gates (max-abs / max-ref per output column): FFMA path 3e-6 (measures ~1e-6), hi+lo path 8e-6 (measures 1e-6 at h <= 256 and
+    3.8e-6 at h = 512 -- the same figure with and without the 2^8 weight pre-scale, i.e. it is the tensor core's truncating
+    fp32 accumulation over K / 16 x 3 steps, not the operand split)."""
+    import satnerf_b200 as sb
+    args = make_args(model=model, fc_units=h)
+    torch.manual_seed(25)
+    m = sb.load_model(args)
+    p64 = {k: v.detach().clone().double() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(26)
+    B = 8192 + 77
+    xyz, aux, t = torch.rand(B, 3, generator=g) * 2 - 1, torch.rand(B, 3, generator=g), torch.randn(B, 4, generator=g)
+    if model == "nerf":
+        want = orc.field_nerf(p64, xyz.double(), aux.double())
+    else:
+        want = orc.field_satnerf(p64, xyz.double(), aux.double(), t.double() if model == "sat-nerf" else None, with_beta=model == "sat-nerf")
+    m = m.cuda()
+    kw = {"input_dir": aux.cuda()} if model == "nerf" else {"input_sun_dir": aux.cuda()}
+    if model == "sat-nerf":
+        kw["input_t"] = t.cuda()
+    errs = {}
+    with torch.no_grad():
+        for prec in ("fp32", "tcx3"):
+            m.points_precision = prec
+            got = m(xyz.cuda(), **kw).cpu().double()
+            assert got.shape == want.shape
+            errs[prec] = float(((got - want).abs().amax(0) / want.abs().amax(0).clamp_min(1e-30)).max())
+        m.points_precision = None
+        sig = m(xyz.cuda(), sigma_only=True).cpu().double()
+    print(model, h, errs)
+    assert errs["tcx3"] < 8e-6 and errs["fp32"] < 3e-6, errs
+    e_sig = float((sig[:, 0] - want[:, 3]).abs().max() / want[:, 3].abs().max())
+    assert e_sig < 8e-6, e_sig
+
+
 @pytest.mark.parametrize("model", ["sat-nerf", "s-nerf", "nerf"])
 def test_field_forward_is_differentiable(model):
     """<Field>.forward under autograd (models/satnerf.py:156-208, snerf.py:148-196, nerf.py:184-227): parameter gradients and the
