@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import satnerf_b200 as sb
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 9472
 args = argparse.Namespace(model="sat-nerf", fc_layers=8, fc_units=512, t_embbeding_tau=4, t_embbeding_vocab=30)
 torch.manual_seed(0)
 m = sb.load_model(args).cuda()

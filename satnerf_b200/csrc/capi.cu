@@ -11,7 +11,7 @@ using namespace snb;
 
 namespace {
 
-constexpr int kChunkPoints = 8192;
+constexpr int kChunkPoints = 148 * 64;      // 74 row blocks of 128: one CTA per SM in the hi+lo layer kernel (2 column blocks per layer)
 
 struct PassPlan {
     int rays_per_chunk;
@@ -99,7 +99,7 @@ extern "C" SNB_API int snb_render_forward(const snb_field_desc* f, const snb_pas
         int rc = p->n_rays - r0 < pl.rays_per_chunk ? p->n_rays - r0 : pl.rays_per_chunk;
         if (!io->xyz) SNB_TRY(launch_points(io->rays, p->ray_cols, dir_col, io->z_vals, pl.xyz, r0, rc, S, st));
         FieldInputs in = chunk_inputs(L, p, io, pl.xyz, r0, rc);
-        in.x3 = p->precision == SNB_FP16X3_TC;
+        in.x3 = p->precision == SNB_FP16X3_TC ? (r0 == 0 ? 2 : 1) : 0;
         SNB_TRY(field_forward_chunk(L, io->params, pl.chunk, in, pl.raw + (size_t)r0 * S * C, false, st));
     }
     CompositeArgs a{};
@@ -143,7 +143,7 @@ extern "C" SNB_API int snb_render_backward(const snb_field_desc* f, const snb_pa
         int rc = p->n_rays - r0 < pl.rays_per_chunk ? p->n_rays - r0 : pl.rays_per_chunk;
         if (!io->xyz) SNB_TRY(launch_points(io->rays, p->ray_cols, dir_col, io->z_vals, pl.xyz, r0, rc, S, st));
         FieldInputs in = chunk_inputs(L, p, io, pl.xyz, r0, rc);
-        in.x3 = p->precision == SNB_FP16X3_TC;       // the recompute runs the arithmetic the forward ran
+        in.x3 = p->precision == SNB_FP16X3_TC ? (r0 == 0 ? 2 : 1) : 0;       // the recompute runs the arithmetic the forward ran
         SNB_TRY(field_forward_chunk(L, io->params, pl.chunk, in, pl.raw_chunk, false, st));
         float* gt = (g->g_t_emb && L.t_dims) ? g->g_t_emb + (size_t)r0 * L.t_dims : nullptr;
         SNB_TRY(field_backward_chunk(L, io->params, g->g_params, pl.chunk, in, pl.d_head + (size_t)r0 * S * C, gt, S, st));
@@ -218,7 +218,7 @@ extern "C" SNB_API int snb_field_forward(const snb_field_desc* f, const float* p
         in.xyz = Src{xyz + (size_t)p0 * 3, 3, 3, 1};
         in.aux = aux_dir ? Src{aux_dir + (size_t)p0 * 3, 3, 3, 1} : Src{nullptr, 0, 0, 1};
         in.temb = (L.t_dims && t_emb) ? Src{t_emb + (size_t)p0 * L.t_dims, L.t_dims, L.t_dims, 1} : Src{nullptr, 0, 0, 1};
-        in.x3 = precision == SNB_FP16X3_TC;
+        in.x3 = precision == SNB_FP16X3_TC ? (p0 == 0 ? 2 : 1) : 0;
         SNB_TRY(field_forward_chunk(L, params, c, in, out + (size_t)p0 * C, sigma_only != 0, (cudaStream_t)stream));
     }
     return 0;

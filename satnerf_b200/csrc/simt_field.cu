@@ -226,99 +226,144 @@ __global__ void __launch_bounds__(NT) linear_bwd_w_kernel(LinBwdW p) {
 constexpr int NARROW_MAX_N = 4, NARROW_MAX_K = 1024;
 template <int ACT>
 __global__ void __launch_bounds__(256) linear_fwd_narrow_kernel(LinFwd p) {
-    __shared__ float Ws[NARROW_MAX_N * NARROW_MAX_K];
+    __shared__ __align__(16) float Ws[NARROW_MAX_N * NARROW_MAX_K];
     const int K = p.a0.k + p.a1.k;
-    for (int i = threadIdx.x; i < NARROW_MAX_N * K; i += 256) Ws[i] = i < p.N * K ? p.W[(size_t)(i / K) * p.ldw + (i % K)] : 0.f;
+    for (int n = 0; n < NARROW_MAX_N; ++n)
+        for (int k = threadIdx.x; k < K; k += 256) Ws[n * NARROW_MAX_K + k] = n < p.N ? p.W[(size_t)n * p.ldw + k] : 0.f;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int m = blockIdx.x * 8 + warp; m < p.M; m += gridDim.x * 8) {
-        float acc[NARROW_MAX_N] = {};
-        if (p.a1.k == 0 && p.a0.div == 1) {                       // (every head of the three fields: one plain row-major source)
-            const float* row = p.a0.p + (size_t)m * p.a0.ld;
-#pragma unroll 4
-            for (int k = lane; k < K; k += 32) {
-                const float a = row[k];
+    const bool plain = p.a1.k == 0 && p.a0.div == 1;                              // (every head of the three fields: one row-major source)
+    const bool vec4 = plain && (K & 3) == 0 && (p.a0.ld & 3) == 0 && (((uintptr_t)p.a0.p & 15u) == 0);
+    constexpr int RW = 4;                                                         // rows per warp task: RW independent loads in flight per lane
+    for (int m0 = (blockIdx.x * 8 + warp) * RW; m0 < p.M; m0 += gridDim.x * 8 * RW) {
+        float acc[RW][NARROW_MAX_N] = {};
+        if (vec4) {
+            const float4* row[RW];
 #pragma unroll
-                for (int n = 0; n < NARROW_MAX_N; ++n) acc[n] = fmaf(a, Ws[n * K + k], acc[n]);
+            for (int r = 0; r < RW; ++r) row[r] = reinterpret_cast<const float4*>(p.a0.p + (size_t)(m0 + r < p.M ? m0 + r : m0) * p.a0.ld);
+            for (int k4 = lane; k4 < K / 4; k4 += 32) {
+                float4 a[RW];
+#pragma unroll
+                for (int r = 0; r < RW; ++r) a[r] = row[r][k4];
+#pragma unroll
+                for (int n = 0; n < NARROW_MAX_N; ++n) {
+                    const float4 w = *reinterpret_cast<const float4*>(&Ws[n * NARROW_MAX_K + 4 * k4]);
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) acc[r][n] = fmaf(a[r].x, w.x, fmaf(a[r].y, w.y, fmaf(a[r].z, w.z, fmaf(a[r].w, w.w, acc[r][n]))));
+                }
             }
         } else {
             for (int k = lane; k < K; k += 32) {
-                const float a = src_at(p.a0, p.a1, m, k);
 #pragma unroll
-                for (int n = 0; n < NARROW_MAX_N; ++n) acc[n] = fmaf(a, Ws[n * K + k], acc[n]);
+                for (int r = 0; r < RW; ++r) {
+                    const int m = m0 + r < p.M ? m0 + r : m0;
+                    const float a = plain ? p.a0.p[(size_t)m * p.a0.ld + k] : src_at(p.a0, p.a1, m, k);
+#pragma unroll
+                    for (int n = 0; n < NARROW_MAX_N; ++n) acc[r][n] = fmaf(a, Ws[n * NARROW_MAX_K + k], acc[r][n]);
+                }
             }
         }
 #pragma unroll
-        for (int n = 0; n < NARROW_MAX_N; ++n)
+        for (int r = 0; r < RW; ++r)
 #pragma unroll
-            for (int o = 16; o; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-        if (lane < p.N) {
+            for (int n = 0; n < NARROW_MAX_N; ++n)
+#pragma unroll
+                for (int o = 16; o; o >>= 1) acc[r][n] += __shfl_xor_sync(0xffffffffu, acc[r][n], o);
+        // lane 4 r + n writes output n of row m0 + r
+        if (lane < RW * NARROW_MAX_N) {
+            const int r = lane >> 2, n = lane & 3, m = m0 + r;
             float y = 0.f;
 #pragma unroll
-            for (int n = 0; n < NARROW_MAX_N; ++n) if (n == lane) y = acc[n];
-            y += p.b[lane];
-            if (p.pre) p.pre[(size_t)m * p.N + lane] = y;
-            p.out[(size_t)m * p.ldo + lane] = act_fwd<ACT>(y);
+            for (int rr = 0; rr < RW; ++rr)
+#pragma unroll
+                for (int nn = 0; nn < NARROW_MAX_N; ++nn) if (rr * NARROW_MAX_N + nn == lane) y = acc[rr][nn];
+            if (m < p.M && n < p.N) {
+                y += p.b[n];
+                if (p.pre) p.pre[(size_t)m * p.N + n] = y;
+                p.out[(size_t)m * p.ldo + n] = act_fwd<ACT>(y);
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // SNB_FP16X3_TC: the same Y = act(cat(A0,A1) W^T + b) on the tensor cores at (almost) fp32 operand precision.
-// Every fp32 operand is split on the fly into fp16 hi + lo (x = hi + lo to 2^-22 |x|, or 2^-25 absolute below the fp16 normal
-// range) and the contraction is issued as three tcgen05 MMAs per K-step -- A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulation
-// in TMEM (the lo x lo term is 2^-22 of the product and dropped).  One CTA = 128 rows x `nt` <= 256 columns.  K runs over the
-// two sources one after the other (each padded to whole 64-wide slabs, so the loads of the wide source stay aligned whatever
-// the width of the narrow one).  Per slab the 256 threads read the fp32 operands from global memory -- one warp instruction =
-// one 256-byte row segment, two floats per lane -- split them and write the four 128B-swizzled fp16 tiles of a 2-stage ring;
-// one thread issues the 12 MMAs, and the next slab is converted while they run.  The epilogue transposes the accumulator
-// through shared memory (32 x 32 blocks per warp) so that rows leave as 128-byte stores.
+// Every fp32 operand is split into fp16 hi + lo (x = hi + lo to 2^-22 |x|, or 2^-25 absolute below the fp16 normal range) and
+// the contraction is issued as three tcgen05 MMAs per K-step -- A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulation in TMEM
+// (the lo x lo term is 2^-22 of the product and dropped).  One CTA = 128 rows x `nt` <= 256 columns.  K runs over the two
+// sources one after the other (each padded to whole 64-wide slabs, so the loads of the wide source stay aligned whatever the
+// width of the narrow one).
+//   weights: split ONCE per pass by x3_pack_kernel into ready-made 128B-swizzled hi / lo tiles (scaled by 2^8) in the caller's
+//            workspace; a producer warp brings them in with two bulk copies per slab (2-stage ring, mbarrier transaction counts);
+//   activations: split on the fly -- 16 warps read the fp32 rows (one warp instruction = one 256-byte row segment, two floats
+//            per lane; 8 rows per thread and slab), the loads running two slabs ahead of the split in registers;
+//   an issuer warp issues the 12 MMAs of a slab once the 16 converter warps have arrived on the slab's mbarrier and the weight
+//   tiles have landed; nobody meets at a CTA-wide barrier inside the K loop, and the next slab is prepared while the MMAs run.
+// The epilogue transposes the accumulator through shared memory (32 x 32 blocks per warp) so that rows leave as 128-byte stores.
 // For deep optical depths (trained scenes) the plain fp16-operand kernel reaches 1e-2 on the weights; this path
-// stays at the fp32 level.
+// stays at the fp32 level (the tensor core's truncating accumulation leaves ~4e-6 at K = 512).
 // ------------------------------------------------------------------------------------------------
 using namespace ptx;
 constexpr int X3_NT = 256;                      // columns per CTA at most (UMMA N)
 constexpr int X3_STAGE = 2 * 16384 + 2 * X3_NT * 128;      // A_hi | A_lo | W_hi | W_lo
-constexpr int X3_THREADS = 512;                // 16 warps: the split / store stream is latency-bound with fewer
-constexpr int X3_RPT = 64 * 32 / X3_THREADS;     // rows of a 64-row batch per thread
-
-constexpr float X3_WSCALE = 256.f;             // weights enter as 256 w (exact), the accumulator leaves as acc / 256: SIREN-scale weights
+constexpr int X3_THREADS = 512;                 // 16 converter / epilogue warps (the split stream is latency-bound with fewer) + producer warp + issuer warp
+constexpr float X3_WSCALE = 256.f;              // weights enter as 256 w (exact), the accumulator leaves as acc / 256: SIREN-scale weights
                                                 // (|w| ~ 4e-3 at h = 512) keep a NORMAL fp16 lo part; |w| < 255 is required (inf otherwise)
 
 __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void x3_split(float x0, float x1, uint32_t* hi, uint32_t* lo) {
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    *hi = *reinterpret_cast<const uint32_t*>(&hh); *lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
 
-// Work of one CTA = a stream of BATCHES: 64 rows x 64 columns of fp32 (one warp instruction = one 256-byte row segment, two floats
-// per lane; X3_RPT rows per thread).  Slab `it` = 2 batches of A rows + ceil(nt / 64) batches of W rows.  Three batches are in flight
-// in registers while a fourth is split and stored (48 KB of loads outstanding per SM, which covers the L2 latency).
-struct X3Cursor {            // (slab, batch-in-slab) of the next batch, advanced without divisions
-    int it = 0, b = 0;
-    __device__ __forceinline__ void next(int bps) { if (++b == bps) { b = 0; ++it; } }
-};
+static size_t x3_layer_bytes(int N, int k0, int k1) { return (size_t)(ceil_div(k0, 64) + ceil_div(k1, 64)) * 2 * ((N + 15) & ~15) * 128; }
 
-__device__ __forceinline__ void x3_load(const LinFwd& p, int m0, int n0, int s0, int n_slabs, const X3Cursor& c, float2 (&v)[X3_RPT]) {
-    if (c.it >= n_slabs) return;
+// W (N x [k_a0 | k_a1], row-major, leading dimension ldw) -> per slab: hi tile | lo tile, each n16 rows x 128 B, 128B-swizzled K-major
+__global__ void __launch_bounds__(256) x3_pack_kernel(const float* __restrict__ W, int ldw, int N, int n16, int k_a0, int k_a1, unsigned char* __restrict__ dst) {
+    const int s0 = (k_a0 + 63) / 64, s = blockIdx.x, lane = threadIdx.x & 31, r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (r >= n16) return;
+    const bool second = s >= s0;
+    const int k = (second ? s - s0 : s) * 64 + 2 * lane, k_end = second ? k_a1 : k_a0;
+    const float* row = W + (size_t)r * ldw + (second ? k_a0 : 0);
+    const float x0 = (r < N && k < k_end) ? row[k] * X3_WSCALE : 0.f, x1 = (r < N && k + 1 < k_end) ? row[k + 1] * X3_WSCALE : 0.f;
+    uint32_t hi, lo; x3_split(x0, x1, &hi, &lo);
+    unsigned char* t = dst + (size_t)s * 2 * n16 * 128 + (size_t)r * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+    *reinterpret_cast<uint32_t*>(t) = hi;
+    *reinterpret_cast<uint32_t*>(t + (size_t)n16 * 128) = lo;
+}
+
+// slab `it` of the CTA's A tile: this thread's 8 rows (warp + 16 j), columns 2 lane, 2 lane + 1 of the slab
+constexpr int X3_ROWS = 128 * 32 / X3_THREADS;
+__device__ __forceinline__ void x3_load(const LinFwd& p, int m0, int s0, int n_slabs, int it, float2 (&v)[X3_ROWS]) {
+    if (it >= n_slabs) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool second = c.it >= s0;
-    const float* ap = second ? p.a1.p : p.a0.p;
-    const int a_ld = second ? p.a1.ld : p.a0.ld, a_div = second ? p.a1.div : p.a0.div, k_end = second ? p.a1.k : p.a0.k;
-    const int k = (second ? c.it - s0 : c.it) * 64 + 2 * lane;
-    const float* base; int ld, div, row0, row_end;
-    if (c.b < 2) { base = ap; ld = a_ld; div = a_div; row0 = m0 + 64 * c.b + warp; row_end = p.M; }
-    else { base = p.W + (second ? p.a0.k : 0); ld = p.ldw; div = 1; row0 = n0 + 64 * (c.b - 2) + warp; row_end = p.N; }
+    const bool second = it >= s0;
+    const float* base = second ? p.a1.p : p.a0.p;
+    const int ld = second ? p.a1.ld : p.a0.ld, div = second ? p.a1.div : p.a0.div, k_end = second ? p.a1.k : p.a0.k;
+    const int k = (second ? it - s0 : it) * 64 + 2 * lane;
+    const int row0 = m0 + warp;
     const bool in2 = k + 1 < k_end, in1 = k < k_end;
-    if (div == 1 && (ld & 1) == 0 && (((uintptr_t)base & 7u) == 0) && in2) {            // the wide sources: 8-byte loads, rows ld apart
-        const float* q = base + (size_t)row0 * ld + k;
 #pragma unroll
-        for (int j = 0; j < X3_RPT; ++j) {
-            v[j] = make_float2(0.f, 0.f);
-            if (row0 + (X3_THREADS / 32) * j < row_end) v[j] = *reinterpret_cast<const float2*>(q + (size_t)((X3_THREADS / 32) * j) * ld);
+    for (int j = 0; j < X3_ROWS; ++j) v[j] = make_float2(0.f, 0.f);
+    if (div == 1 && (ld & 1) == 0 && (((uintptr_t)base & 7u) == 0)) {            // the wide sources: 8-byte loads, rows ld apart
+        if (in2) {
+            const float* q = base + (size_t)row0 * ld + k;
+            const size_t step = (size_t)(X3_THREADS / 32) * ld;
+#pragma unroll
+            for (int j = 0; j < X3_ROWS; ++j)
+                if (row0 + (X3_THREADS / 32) * j < p.M) v[j] = *reinterpret_cast<const float2*>(q + j * step);
+        } else if (in1) {
+#pragma unroll
+            for (int j = 0; j < X3_ROWS; ++j)
+                if (row0 + (X3_THREADS / 32) * j < p.M) v[j].x = base[(size_t)(row0 + (X3_THREADS / 32) * j) * ld + k];
         }
-    } else {
+    } else if (in1) {
 #pragma unroll
-        for (int j = 0; j < X3_RPT; ++j) {
+        for (int j = 0; j < X3_ROWS; ++j) {
             const int r = row0 + (X3_THREADS / 32) * j;
-            v[j] = make_float2(0.f, 0.f);
-            if (r < row_end && in1) {
+            if (r < p.M) {
                 const float* q = base + (size_t)(div == 1 ? r : r / div) * ld + k;
                 v[j].x = q[0];
                 if (in2) v[j].y = q[1];
@@ -328,53 +373,51 @@ __device__ __forceinline__ void x3_load(const LinFwd& p, int m0, int n0, int s0,
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(X3_THREADS, 1) linear_fwd_x3_kernel(LinFwd p, int nt_tile) {
+__global__ void __launch_bounds__(X3_THREADS + 64, 1) linear_fwd_x3_kernel(LinFwd p, int nt_tile, const unsigned char* __restrict__ wpk, int n16) {
     extern __shared__ unsigned char x3_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)x3_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * X3_STAGE);       // [0,1]: stage consumed by its MMAs; [2]: accumulator complete
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+    // mbarriers: [0,1] stage consumed by its MMAs; [2] accumulator complete; [3,4] weight tiles landed; [5,6] A tiles written (16 warps)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * X3_STAGE);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
     const int s0 = (p.a0.k + 63) / 64, s1 = (p.a1.k + 63) / 64, n_slabs = s0 + s1;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * nt_tile;
     int nv = p.N - n0; if (nv > nt_tile) nv = nt_tile;                           // valid columns of this CTA
     const int nt = (nv + 15) & ~15;                                              // UMMA N: multiple of 16
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_barrier_init(); }
+    if (t == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        mbar_init(&bars[5], X3_THREADS / 32); mbar_init(&bars[6], X3_THREADS / 32);
+        fence_barrier_init();
+    }
     if (warp == 0) tmem_alloc(tmem_ptr, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t idesc = umma_idesc_f16((uint32_t)nt);
-    const int bps = 2 + (nt + 63) / 64;
     const uint32_t sbase = smem_u32(base);
-    // this thread's rows of a batch are warp + 16 j: (row & 7) == (warp & 7), so the swizzle term of its tile offsets is a constant
-    const uint32_t lane_off = (uint32_t)warp * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
 
-    auto process = [&](const X3Cursor& c, float2 (&v)[X3_RPT]) {
-        if (c.it >= n_slabs) return;
-        const int it = c.it, b = c.b, st = it & 1;
-        const uint32_t stage = sbase + (uint32_t)st * X3_STAGE;
-        if (b == 0 && it >= 2) mbar_wait(&bars[st], (uint32_t)((it >> 1) - 1) & 1u, 31);   // the MMAs that read this stage two slabs ago are done
-        const bool is_a = b < 2;
-        const uint32_t hi_t = stage + (is_a ? 0u : 32768u) + (uint32_t)(is_a ? b : b - 2) * 8192u + lane_off;
-        const uint32_t lo_d = is_a ? 16384u : (uint32_t)X3_NT * 128u;                       // lo tile - hi tile
-        const int rows_left = (is_a ? 128 : nt) - 64 * (is_a ? b : b - 2) - warp;          // rows warp + 16 j of this batch below the tile's end
-        const float scale = is_a ? 1.f : X3_WSCALE;
-#pragma unroll
-        for (int j = 0; j < X3_RPT; ++j) {
-            if ((X3_THREADS / 32) * j < rows_left) {
-                const float x0 = v[j].x * scale, x1 = v[j].y * scale;
-                const __half2 hh = __floats2half2_rn(x0, x1);
-                const float2 hf = __half22float2(hh);
-                const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                sts_b32(hi_t + (uint32_t)j * (X3_THREADS / 32 * 128u), *reinterpret_cast<const uint32_t*>(&hh));
-                sts_b32(hi_t + lo_d + (uint32_t)j * (X3_THREADS / 32 * 128u), *reinterpret_cast<const uint32_t*>(&ll));
+    if (warp == X3_THREADS / 32) {
+        // ---- producer: the slab's weight tiles (hi, lo) as two bulk copies as soon as the stage's previous MMAs are done ----
+        if (lane == 0) {
+            for (int it = 0; it < n_slabs; ++it) {
+                const int st = it & 1;
+                if (it >= 2) mbar_wait(&bars[st], (uint32_t)((it >> 1) - 1) & 1u, 33);
+                unsigned char* sW_hi = base + st * X3_STAGE + 32768, *sW_lo = sW_hi + X3_NT * 128;
+                const unsigned char* src = wpk + (size_t)it * 2 * n16 * 128 + (size_t)n0 * 128;
+                mbar_arrive_expect_tx(&bars[3 + st], 2u * (uint32_t)nt * 128u);
+                bulk_g2s(sW_hi, src, (uint32_t)nt * 128u, &bars[3 + st]);
+                bulk_g2s(sW_lo, src + (size_t)n16 * 128, (uint32_t)nt * 128u, &bars[3 + st]);
             }
         }
-        if (b == bps - 1) {
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (t == 0) {
+    } else if (warp == X3_THREADS / 32 + 1) {
+        // ---- issuer: 12 MMAs per slab once its A tiles are written and its weight tiles have landed ----
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16((uint32_t)nt);
+            for (int it = 0; it < n_slabs; ++it) {
+                const int st = it & 1;
+                const uint32_t stage = sbase + (uint32_t)st * X3_STAGE, ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&bars[5 + st], ph, 35);
+                mbar_wait(&bars[3 + st], ph, 34);
                 tc_fence_after();
                 const bool second = it >= s0;
                 const int k_left = (second ? p.a1.k : p.a0.k) - (second ? it - s0 : it) * 64;
@@ -389,43 +432,62 @@ __global__ void __launch_bounds__(X3_THREADS, 1) linear_fwd_x3_kernel(LinFwd p, 
                 if (it == n_slabs - 1) umma_commit(&bars[2]);
             }
         }
-    };
-    {
-        float2 v0[X3_RPT], v1[X3_RPT], v2[X3_RPT];
-        X3Cursor lc, pc;                                     // load cursor runs three batches ahead of the process cursor
-        x3_load(p, m0, n0, s0, n_slabs, lc, v0); lc.next(bps);
-        x3_load(p, m0, n0, s0, n_slabs, lc, v1); lc.next(bps);
-        x3_load(p, m0, n0, s0, n_slabs, lc, v2); lc.next(bps);
-        while (pc.it < n_slabs) {
-            process(pc, v0); pc.next(bps); x3_load(p, m0, n0, s0, n_slabs, lc, v0); lc.next(bps);
-            process(pc, v1); pc.next(bps); x3_load(p, m0, n0, s0, n_slabs, lc, v1); lc.next(bps);
-            process(pc, v2); pc.next(bps); x3_load(p, m0, n0, s0, n_slabs, lc, v2); lc.next(bps);
+    } else {
+        // this thread's rows of a slab are warp + 16 j: (row & 7) == (warp & 7), so the swizzle term of its tile offsets is a constant
+        const uint32_t lane_off = (uint32_t)warp * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)warp & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+        auto process = [&](int it, float2 (&v)[X3_ROWS]) {
+            if (it >= n_slabs) return;
+            const int st = it & 1;
+            if (it >= 2) mbar_wait(&bars[st], (uint32_t)((it >> 1) - 1) & 1u, 31);   // the MMAs that read this stage two slabs ago are done
+            const uint32_t hi_t = sbase + (uint32_t)st * X3_STAGE + lane_off;
+#pragma unroll
+            for (int j = 0; j < X3_ROWS; ++j) {
+                uint32_t hi, lo; x3_split(v[j].x, v[j].y, &hi, &lo);
+                sts_b32(hi_t + (uint32_t)j * (X3_THREADS / 32 * 128u), hi);
+                sts_b32(hi_t + 16384u + (uint32_t)j * (X3_THREADS / 32 * 128u), lo);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[5 + st]);
+        };
+        {
+            float2 v0[X3_ROWS], v1[X3_ROWS];                     // loads run two slabs (64 KB per SM) ahead of the split
+            x3_load(p, m0, s0, n_slabs, 0, v0);
+            x3_load(p, m0, s0, n_slabs, 1, v1);
+            for (int it = 0; it < n_slabs; it += 2) {
+                process(it, v0);     x3_load(p, m0, s0, n_slabs, it + 2, v0);
+                process(it + 1, v1); x3_load(p, m0, s0, n_slabs, it + 3, v1);
+            }
         }
-    }
-    mbar_wait(&bars[2], 0u, 32);
-    tc_fence_after();
-    // epilogue: warp w reads TMEM lanes 32 (w % 4) ..; the warps of a lane quadrant take the 32-column blocks in turn.  Each
-    // block goes through a 32 x 33 shared-memory scratch (the ring is free now) so that one store instruction = one row segment.
-    {
-        float* scratch = reinterpret_cast<float*>(base) + warp * (32 * 33);
+        mbar_wait(&bars[2], 0u, 32);
+        tc_fence_after();
+        // epilogue: warp w reads TMEM lanes 32 (w % 4) ..; the warps of a lane quadrant take the 32-column blocks in turn.  Each
+        // block goes through a 32 x 33 shared-memory scratch (the ring is free now) so that one store instruction = one row segment.
+        const uint32_t scratch = sbase + (uint32_t)warp * (32 * 33 * 4);
         const int quad = warp & 3;
+        int rows = p.M - (m0 + quad * 32); if (rows > 32) rows = 32;
         for (int c0 = (warp >> 2) * 32; c0 < nt; c0 += (X3_THREADS / 128) * 32) {
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = v[i];
+            for (int i = 0; i < 32; ++i) sts_b32(scratch + (uint32_t)(lane * 33 + i) * 4u, __float_as_uint(v[i]));
             __syncwarp();
-            const int n = n0 + c0 + lane;
-            const bool col_ok = c0 + lane < nv;
-            const float bias = col_ok ? p.b[n] : 0.f;
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                const int m = m0 + quad * 32 + r;
-                if (m < p.M && col_ok) {
-                    const float y = fmaf(scratch[r * 33 + lane], 1.f / X3_WSCALE, bias);
-                    if (p.pre) p.pre[(size_t)m * p.N + n] = y;
-                    p.out[(size_t)m * p.ldo + n] = act_fwd<ACT>(y);
+            if (c0 + lane < nv) {
+                const int n = n0 + c0 + lane;
+                const float bias = p.b[n];
+                float* out = p.out + (size_t)(m0 + quad * 32) * p.ldo + n;
+                float* pre = p.pre ? p.pre + (size_t)(m0 + quad * 32) * p.N + n : nullptr;
+                const size_t ldo = (size_t)p.ldo, ldp = (size_t)p.N;
+                const uint32_t sc = scratch + (uint32_t)lane * 4u;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    if (r < rows) {
+                        float a; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(sc + (uint32_t)r * 132u));
+                        const float y = fmaf(a, 1.f / X3_WSCALE, bias);
+                        if (pre) pre[r * ldp] = y;
+                        out[r * ldo] = act_fwd<ACT>(y);
+                    }
                 }
             }
             __syncwarp();
@@ -436,22 +498,29 @@ __global__ void __launch_bounds__(X3_THREADS, 1) linear_fwd_x3_kernel(LinFwd p, 
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// wpk: this layer's packed weights (x3_layer_bytes); pack_now: (re)build them first (first chunk of a pass)
 template <int ACT>
-static int launch_x3(const LinFwd& p, cudaStream_t st) {
+static int launch_x3(const LinFwd& p, cudaStream_t st, unsigned char* wpk, bool pack_now) {
     const size_t smem = 2 * (size_t)X3_STAGE + 1024 + 64;
     static bool attr_set = false;
     if (!attr_set) { SNB_CUDA(cudaFuncSetAttribute(linear_fwd_x3_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    const int n16 = (p.N + 15) & ~15;
+    if (pack_now) {
+        dim3 g(ceil_div(p.a0.k, 64) + ceil_div(p.a1.k, 64), ceil_div(n16, 8));
+        x3_pack_kernel<<<g, 256, 0, st>>>(p.W, p.ldw, p.N, n16, p.a0.k, p.a1.k, wpk);
+        SNB_CHECK_LAUNCH();
+    }
     // 256-column tiles unless that leaves most SMs without a CTA (the h/2-wide head layers of one chunk)
     const int nt_tile = (p.N > 128 && ceil_div(p.M, 128) * ceil_div(p.N, X3_NT) < 100) ? 128 : X3_NT;
     dim3 g(ceil_div(p.M, 128), ceil_div(p.N, nt_tile));
-    linear_fwd_x3_kernel<ACT><<<g, X3_THREADS, smem, st>>>(p, nt_tile);
+    linear_fwd_x3_kernel<ACT><<<g, X3_THREADS + 64, smem, st>>>(p, nt_tile, wpk, n16);
     SNB_CHECK_LAUNCH();
     return 0;
 }
 
 template <int ACT>
 static int launch_narrow(const LinFwd& p, cudaStream_t st) {
-    int blocks = ceil_div(p.M, 8); if (blocks > 148 * 4) blocks = 148 * 4;
+    int blocks = ceil_div(p.M, 32); if (blocks > 148 * 4) blocks = 148 * 4; if (blocks < 1) blocks = 1;
     linear_fwd_narrow_kernel<ACT><<<blocks, 256, 0, st>>>(p);
     SNB_CHECK_LAUNCH();
     return 0;
@@ -460,7 +529,8 @@ static int launch_narrow(const LinFwd& p, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static int run_fwd(int act, const LinFwd& p, cudaStream_t st, int x3 = 0) {
+// x3: 0 = FFMA; 1 / 2 = SNB_FP16X3_TC with the packed weights at *wpk already built / to be built now (*wpk advances layer by layer)
+static int run_fwd(int act, const LinFwd& p, cudaStream_t st, int x3 = 0, unsigned char** wpk = nullptr) {
     if (p.M == 0) return 0;
     if (p.N <= NARROW_MAX_N && p.a0.k + p.a1.k <= NARROW_MAX_K && p.a0.k + p.a1.k >= 64) {
         switch (act) {
@@ -471,13 +541,14 @@ static int run_fwd(int act, const LinFwd& p, cudaStream_t st, int x3 = 0) {
             default: break;
         }
     }
-    if (x3 && p.N >= 32 && p.a0.k + p.a1.k >= 16) {          // (short contractions -- K = 3 inputs -- stay on the FFMA kernel)
+    if (x3 && wpk && *wpk && p.N >= 32 && p.a0.k + p.a1.k >= 16 && (act == ACT_NONE || act == ACT_SIN || act == ACT_SIN30 || act == ACT_RELU)) {
+        unsigned char* w = *wpk;                              // (short contractions -- K = 3 inputs -- stay on the FFMA kernel)
+        *wpk += x3_layer_bytes(p.N, p.a0.k, p.a1.k);
         switch (act) {
-            case ACT_NONE: return launch_x3<ACT_NONE>(p, st);
-            case ACT_SIN: return launch_x3<ACT_SIN>(p, st);
-            case ACT_SIN30: return launch_x3<ACT_SIN30>(p, st);
-            case ACT_RELU: return launch_x3<ACT_RELU>(p, st);
-            default: break;
+            case ACT_NONE: return launch_x3<ACT_NONE>(p, st, w, x3 == 2);
+            case ACT_SIN: return launch_x3<ACT_SIN>(p, st, w, x3 == 2);
+            case ACT_SIN30: return launch_x3<ACT_SIN30>(p, st, w, x3 == 2);
+            default: return launch_x3<ACT_RELU>(p, st, w, x3 == 2);
         }
     }
     dim3 g(ceil_div(p.M, BM), ceil_div(p.N, BN));
@@ -536,6 +607,15 @@ static inline Src none() { return S_(nullptr, 0, 0, 1); }
 size_t FieldChunk::plan(Arena& ar, const FieldLayout& L, int Pc, int Rc, bool keep) {
     const int h = L.width, h2 = h / 2, nl = L.n_layers;
     size_t before = ar.off;
+    {   // SNB_FP16X3_TC: packed hi / lo weight tiles of every wide layer (bound: one extra slab per layer for the narrow source)
+        size_t wb = 0;
+        auto add = [&](const Lin& l) { if (l.n_out >= 32 && l.n_in >= 16) wb += x3_layer_bytes(l.n_out, l.n_in, 64); };
+        for (int i = 0; i < nl; ++i) add(L.trunk[i]);
+        add(L.feats); add(L.rgb0);
+        if (L.variant != SNB_NERF) { for (int j = 0; j < 3; ++j) add(L.sun[j]); add(L.sky0); }
+        if (L.variant == SNB_SATNERF) add(L.beta0);
+        x3_w = ar.take<unsigned char>(wb);
+    }
     enc = L.in_xyz != 3 ? ar.take<float>((size_t)Pc * L.in_xyz) : nullptr;
     enc_dir = L.in_dir ? ar.take<float>((size_t)Rc * L.in_dir) : nullptr;
     float* ping[2] = {nullptr, nullptr};
@@ -575,10 +655,11 @@ int field_forward_chunk(const FieldLayout& L, const float* P, const FieldChunk& 
         SNB_CHECK_LAUNCH();
         x = S_(c.enc, L.in_xyz, L.in_xyz);
     }
+    unsigned char* wpk = c.x3_w;
     auto fwd = [&](const Lin& l, Src a0, Src a1, int act, float* pre, float* out, int ldo) {
         LinFwd p; p.a0 = a0; p.a1 = a1; p.W = P + l.w; p.ldw = l.n_in; p.b = P + l.b; p.pre = pre; p.out = out; p.ldo = ldo; p.M = Pc; p.N = l.n_out;
         if (a0.k + a1.k != l.n_in) { set_error("internal: layer K mismatch (%d+%d vs %d)", a0.k, a1.k, l.n_in); return -3; }
-        return run_fwd(act, p, st, in.x3);
+        return run_fwd(act, p, st, in.x3, &wpk);
     };
     for (int i = 0; i < nl; ++i) {
         Src a0 = i == 0 ? x : (i == L.skip ? x : S_(c.act[i - 1], h, h));

@@ -12,7 +12,8 @@ struct LinFwd  { Src a0, a1; const float* W; int ldw; const float* b; float* pre
 struct LinBwdIn { const float* dY; int ldy, N; const float* W; int ldw, k_off, K; const float* pre; float* dX; int ldx, accumulate, M; };
 struct LinBwdW { const float* dY; int ldy, N; Src a0, a1; float* partial; int M, m_per_z; };
 
-struct FieldInputs { Src xyz, aux, temb; int n_points; int x3 = 0; };      // x3: forward contractions on the tensor cores with fp16 hi+lo operands (SNB_FP16X3_TC)
+struct FieldInputs { Src xyz, aux, temb; int n_points; int x3 = 0; };      // x3: forward contractions on the tensor cores with fp16 hi+lo operands (SNB_FP16X3_TC):
+                                                                           // 2 = build the packed weights in the chunk's x3_w first (first chunk of a pass), 1 = reuse them
 
 // Buffers for one chunk of points, carved from the caller's workspace.
 struct FieldChunk {
@@ -20,6 +21,7 @@ struct FieldChunk {
     float *pre[kMaxTrunk], *act[kMaxTrunk];
     float *feat, *rgb1_pre, *rgb1, *sun_pre[3], *sun_act[3], *sky1_pre, *sky1, *beta1_pre, *beta1;
     float *d_feat, *d_a, *d_b, *d_t, *partial;
+    unsigned char* x3_w;       // SNB_FP16X3_TC: packed hi / lo weight tiles (built by the first chunk of a pass)
     // keep=true allocates one buffer per layer (pre- and post-activation) for the backward pass
     size_t plan(Arena& ar, const FieldLayout& L, int Pc, int Rc, bool keep);
 };

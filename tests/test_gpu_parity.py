@@ -16,8 +16,8 @@ from oracle import render_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-5, "tc": 1e-3}
-GRAD_TOL = {"fp32": 2e-4, "tc": 5e-3}      # tc: measured <= 1.8e-3 of each tensor's max |grad| against the float64 oracle (gpurun_out/parity_report.json)
+TOL = {"fp32": 2e-5, "tcx3": 2e-5, "tc": 1e-3}      # tcx3: tensor cores with fp16 hi+lo operands -- held to the fp32 path's bound
+GRAD_TOL = {"fp32": 2e-4, "tcx3": 2e-4, "tc": 5e-3}      # tc: measured <= 1.8e-3 of each tensor's max |grad| against the float64 oracle (gpurun_out/parity_report.json)
 
 
 def _grad_tol(precision, key):
@@ -40,6 +40,18 @@ def test_forward_fp32_matches_golden(name):
         got = res[k].cpu()
         assert got.shape == ref.shape, k
         assert rel_err(got, ref) < TOL["fp32"], (k, rel_err(got, ref))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_tcx3_matches_golden(name):
+    """SNB_FP16X3_TC against the reference fixtures at the fp32 path's tolerance (all variants, SC pass, coarse + fine)."""
+    g = Golden(name)
+    _, _, res = run_golden(g, "tcx3")
+    assert set(res) == set(g.out)
+    for k, ref in g.out.items():
+        got = res[k].cpu()
+        assert got.shape == ref.shape, k
+        assert rel_err(got, ref) < TOL["tcx3"], (k, rel_err(got, ref))
 
 
 @pytest.mark.parametrize("name", _tc_cases())
@@ -78,7 +90,7 @@ def _grads_fp64(g):
     return {key: (P["t"].grad if key == "t" else P[key.partition(".")[0]][key.partition(".")[2]].grad) for key in g.grads}
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("precision", ["fp32", "tcx3", "tc"])
 @pytest.mark.parametrize("name", [c for c in CASES if "h64" in c])
 def test_gradients_match_golden(name, precision):
     """Parameter gradients against the reference's own (golden, fp32 autograd) gradients.  Where the reference's
