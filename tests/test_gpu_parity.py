@@ -158,7 +158,7 @@ def test_sample_pdf_indices_bit_exact():
     assert torch.equal(z_out.cpu(), want_sorted)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("precision", ["fp32", "tcx3", "tc"])
 def test_matches_oracle_on_fresh_inputs(precision):
     """Seeded inputs that are not fixtures: sat-nerf h=128, 200 rays x 64 samples, oracle on the CPU."""
     import satnerf_b200 as sb
@@ -236,6 +236,40 @@ def test_edge_cases():
     bad = make_args(model="foo")
     with pytest.raises(ValueError):
         sb.render_rays(ms, bad, rays.cuda(), ts.cuda())
+
+
+@pytest.mark.parametrize("model,h,S,R", [("sat-nerf", 192, 64, 149), ("s-nerf", 72, 40, 311), ("nerf", 128, 64, 150), ("sat-nerf", 512, 96, 99)])
+def test_tcx3_ragged_shapes_vs_oracle(model, h, S, R):
+    """SNB_FP16X3_TC at shapes that do not fit its tiles: widths that are not multiples of 64 / 128, ray counts one past a chunk
+    boundary (148 x 64 points per chunk at S = 64), partial last row blocks, the solar-correction pass; empty and single-ray batches.
+    Tolerance: the fp32 path's 2e-5 (max-abs / max-ref per key)."""
+    import satnerf_b200 as sb
+    sc = 0.05 if model == "s-nerf" else 0.0
+    args = make_args(model=model, fc_units=h, n_samples=S, sc_lambda=sc, precision="tcx3")
+    torch.manual_seed(71)
+    ms = {"coarse": sb.load_model(args)}
+    if model == "sat-nerf":
+        ms["t"] = torch.nn.Embedding(30, 4)
+    if model == "nerf":
+        rays = orc.synthetic_blender_rays(R, seed=72)
+        rays = rays[0] if isinstance(rays, tuple) else rays
+        ts = None
+    else:
+        rays, ts = orc.synthetic_sat_rays(R, seed=72)
+        ts = ts if model == "sat-nerf" else None
+    g = torch.Generator().manual_seed(73)
+    draws = [torch.rand(R, S, generator=g), torch.randn(R, S, generator=g)] + ([torch.randn(R, S, generator=g)] if sc else [])
+    params = {k: ({n: v.detach().clone() for n, v in m.state_dict().items()} if k != "t" else m.weight.detach().clone()) for k, m in ms.items()}
+    want = orc.render_rays(params, args, rays, ts, orc.Draws([d.clone() for d in draws]))
+    ms = {k: v.cuda() for k, v in ms.items()}
+    with torch.no_grad():
+        got = sb.render_rays(ms, args, rays.cuda(), None if ts is None else ts.cuda(), _draws=draws)
+        assert set(got) == set(want)
+        for k, ref in want.items():
+            assert rel_err(got[k].cpu(), ref) < TOL["tcx3"], (k, rel_err(got[k].cpu(), ref))
+        for n in (0, 1):
+            out = sb.render_rays(ms, args, rays[:n].cuda(), None if ts is None else ts[:n].cuda())
+            assert out["rgb_coarse"].shape == (n, 3) and torch.isfinite(out["rgb_coarse"]).all()
 
 
 def test_field_forward_matches_oracle():
