@@ -502,8 +502,7 @@ __global__ void __launch_bounds__(X3_THREADS + 64, 1) linear_fwd_x3_kernel(LinFw
 template <int ACT>
 static int launch_x3(const LinFwd& p, cudaStream_t st, unsigned char* wpk, bool pack_now) {
     const size_t smem = 2 * (size_t)X3_STAGE + 1024 + 64;
-    static bool attr_set = false;
-    if (!attr_set) { SNB_CUDA(cudaFuncSetAttribute(linear_fwd_x3_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    SNB_CUDA(cudaFuncSetAttribute(linear_fwd_x3_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     // (per device: not cached)
     const int n16 = (p.N + 15) & ~15;
     if (pack_now) {
         dim3 g(ceil_div(p.a0.k, 64) + ceil_div(p.a1.k, 64), ceil_div(n16, 8));
