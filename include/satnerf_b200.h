@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 4
+#define SNB_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define SNB_API __attribute__((visibility("default")))
@@ -272,6 +272,24 @@ SNB_API int snb_adam_step(float* params, const float* grads, float* exp_avg, flo
 SNB_API int snb_adam_step_sharded(float* const* peer_params, const float* const* peer_grads, int world, int rank,
                           float* exp_avg, float* exp_avg_sq, long long n,
                           double lr, double beta1, double beta2, double eps, double weight_decay, int step, void* stream);
+
+/* The same step for up to 4 flat buffers (fields, embedding table) in ONE launch.  mc_params / mc_grads: multicast (NVLS) addresses of
+ * the symmetric allocations, or NULL: with them the gradient sum is one `multimem.ld_reduce` per 16 bytes (reduced inside the
+ * NVSwitch) and the parameter delivery one `multimem.st`; without them peer loads / stores as in snb_adam_step_sharded.  The
+ * in-switch sum has no specified association order: replicas stay bit-identical (every element is reduced once, by its owner), the
+ * result may differ from the fixed-order sum in the last bit.                                                              */
+typedef struct snb_sharded_buffer {
+    float* const* peer_params;      /* host array of `world` device pointers (valid on this GPU)  */
+    const float* const* peer_grads;
+    float* mc_params;               /* multicast address of the parameter buffers, or NULL        */
+    const float* mc_grads;          /* multicast address of the gradient buffers, or NULL         */
+    float* exp_avg;                 /* this rank's moments (n floats; only its shard is touched)  */
+    float* exp_avg_sq;
+    long long n;                    /* floats in the buffer, a multiple of 4                      */
+    int32_t step;                   /* 1-based count of this update (bias correction)             */
+} snb_sharded_buffer;
+SNB_API int snb_adam_step_sharded_multi(const snb_sharded_buffer* bufs, int n_buffers, int world, int rank,
+                                double lr, double beta1, double beta2, double eps, double weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,7 @@ _SIGNATURES = {
                                 C.c_double, C.c_int, C.c_void_p]),
     "snb_adam_step_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double,
                                         C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]),
+    "snb_adam_step_sharded_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "snb_field_workspace": (C.c_int, [C.POINTER(FieldDesc), C.c_int, C.POINTER(C.c_size_t)]),
     "snb_field_forward": (C.c_int, [C.POINTER(FieldDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -115,7 +116,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if handle.snb_abi_version() != 4:
+        if handle.snb_abi_version() != 5:
             raise RuntimeError("libsatnerf_b200.so ABI version mismatch")
         _lib = handle
     return _lib
@@ -350,6 +351,31 @@ def adam_step_sharded(peer_param_ptrs, peer_grad_ptrs, rank, exp_avg, exp_avg_sq
     with torch.cuda.device(device):
         _check(lib().snb_adam_step_sharded(pp, gp, world, int(rank), C.c_void_p(exp_avg.data_ptr()), C.c_void_p(exp_avg_sq.data_ptr()), int(n),
                                            lr, beta1, beta2, eps, weight_decay, int(step), _stream(device)), "snb_adam_step_sharded")
+
+
+class ShardedBuffer(C.Structure):
+    """snb_sharded_buffer (include/satnerf_b200.h)."""
+    _fields_ = [("peer_params", C.c_void_p), ("peer_grads", C.c_void_p), ("mc_params", C.c_void_p), ("mc_grads", C.c_void_p),
+                ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_longlong), ("step", C.c_int32)]
+
+
+def adam_step_sharded_multi(buffers, rank, lr, beta1, beta2, eps, weight_decay, device):
+    """One launch of the fused reduce + Adam + deliver step over several flat buffers (snb_adam_step_sharded_multi).
+    buffers: list of dicts {param_ptrs, grad_ptrs, mc_params, mc_grads (0 = no multicast), exp_avg, exp_avg_sq, n, step}."""
+    world = len(buffers[0]["param_ptrs"])
+    arr = (ShardedBuffer * len(buffers))()
+    keep = []
+    for i, b in enumerate(buffers):
+        pp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in b["param_ptrs"]])
+        gp = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in b["grad_ptrs"]])
+        keep += [pp, gp]
+        arr[i].peer_params = C.cast(pp, C.c_void_p); arr[i].peer_grads = C.cast(gp, C.c_void_p)
+        arr[i].mc_params = C.c_void_p(int(b.get("mc_params") or 0) or None); arr[i].mc_grads = C.c_void_p(int(b.get("mc_grads") or 0) or None)
+        arr[i].exp_avg = C.c_void_p(b["exp_avg"].data_ptr()); arr[i].exp_avg_sq = C.c_void_p(b["exp_avg_sq"].data_ptr())
+        arr[i].n = int(b["n"]); arr[i].step = int(b["step"])
+    with torch.cuda.device(device):
+        _check(lib().snb_adam_step_sharded_multi(C.cast(arr, C.c_void_p), len(buffers), world, int(rank), lr, beta1, beta2, eps, weight_decay,
+                                                 _stream(device)), "snb_adam_step_sharded_multi")
 
 
 def gather_rows(tables: Dict[str, torch.Tensor], idx: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -119,6 +119,9 @@ class SymmetricBuffer:
         self.hg = symm.rendezvous(self.grads, group)
         self.param_ptrs = [int(x) for x in self.hp.buffer_ptrs]
         self.grad_ptrs = [int(x) for x in self.hg.buffer_ptrs]
+        # multicast (NVLS) addresses of the same allocations: 0 when the fabric / driver offers none
+        self.mc_params = int(getattr(self.hp, "multicast_ptr", 0) or 0)
+        self.mc_grads = int(getattr(self.hg, "multicast_ptr", 0) or 0)
 
     def barrier(self):
         """Device-side barrier among the ranks on the current stream (signal pads of the symmetric allocation)."""

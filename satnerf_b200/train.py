@@ -6,6 +6,7 @@ between backward and the optimizer step."""
 from __future__ import annotations
 
 import copy
+import os
 from collections import defaultdict
 
 import numpy as np
@@ -24,12 +25,13 @@ class FlatAdam(torch.optim.Optimizer):
     fused multi-tensor Adam runs a single large tensor on ~40 CTAs (84 us for 2.6 M parameters against ~12 us here).
     State keys are torch's (`step`, `exp_avg`, `exp_avg_sq`), so optimizer checkpoints interchange with torch.optim.Adam."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, shards=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, shards=None, nvls=True):
         """shards: {id(param): dist.SymmetricBuffer} (dist.make_symmetric) switches to the data-parallel step fused with its
         collective: every rank reduces and updates its shard of each buffer through peer memory and delivers the new parameters to
         all ranks (snb_adam_step_sharded) -- no all-reduce; each rank keeps the Adam moments of its own shard only."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.shards = shards
+        self.nvls = nvls            # reduce / deliver through the NVSwitch multicast mappings when the buffers have them
 
     @property
     def sharded(self) -> bool:
@@ -39,8 +41,9 @@ class FlatAdam(torch.optim.Optimizer):
         rank, _ = sdist.world()
         first = next(iter(self.shards.values()))
         first.barrier()                                  # every rank's gradients are final
-        for group in self.param_groups:
+        for group in self.param_groups:                  # ONE launch per parameter group: all its flat buffers (fields, embedding)
             b1, b2 = group["betas"]
+            bufs, dev = [], None
             for p in group["params"]:
                 sb = self.shards[id(p)]
                 st = self.state[p]
@@ -49,9 +52,12 @@ class FlatAdam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros(sb.n_pad, device=p.device, dtype=torch.float32)
                     st["exp_avg_sq"] = torch.zeros(sb.n_pad, device=p.device, dtype=torch.float32)
                 st["step"] = int(st["step"]) + 1
-                capi.adam_step_sharded(sb.param_ptrs, sb.grad_ptrs, rank, st["exp_avg"], st["exp_avg_sq"], sb.n_pad,
-                                       float(group["lr"]), b1, b2, group["eps"], group["weight_decay"], st["step"], p.device)
+                bufs.append(dict(param_ptrs=sb.param_ptrs, grad_ptrs=sb.grad_ptrs, mc_params=sb.mc_params if self.nvls else 0,
+                                 mc_grads=sb.mc_grads if self.nvls else 0, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"], n=sb.n_pad, step=st["step"]))
+                dev = p.device
                 torch.autograd.graph.increment_version(p)
+            for i in range(0, len(bufs), 4):
+                capi.adam_step_sharded_multi(bufs[i:i + 4], rank, float(group["lr"]), b1, b2, group["eps"], group["weight_decay"], dev)
         first.barrier()                                  # every rank's parameters have been delivered (and nobody reads our gradients any more)
 
     @torch.no_grad()
@@ -151,7 +157,8 @@ class NeRFSystem:
                 groups = []
                 for m in self.models.values():
                     groups += [m.flat_parameter()] if hasattr(m, "flat_parameter") else list(m.parameters())
-            self.optimizer = FlatAdam(groups, lr=self.args.lr, weight_decay=0, shards=shards)      # one library launch per flat buffer
+            self.optimizer = FlatAdam(groups, lr=self.args.lr, weight_decay=0, shards=shards,
+                                      nvls=bool(getattr(self.args, "sharded_nvls", os.environ.get("SNB_SHARDED_NVLS", "1") != "0")))      # one library launch per step
         else:
             self.optimizer = torch.optim.Adam(groups, lr=self.args.lr, weight_decay=0)
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=1, gamma=0.9)   # stepped per epoch
@@ -331,7 +338,9 @@ def bench_training_step(args, dev, rank, world, n_rays, warm, steps, flush, dept
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     what = "DeviceRaySampler batch + render forward + loss seeded in the compositing backward + backward + " + (
-        "gradient reduction, Adam and parameter delivery fused over NVLink peer memory (snb_adam_step_sharded)" if getattr(system.optimizer, "sharded", False)
+        ("gradient reduction, Adam and parameter delivery fused in one kernel over symmetric memory (snb_adam_step_sharded_multi: " +
+         ("in-switch reduction + multicast delivery, multimem.ld_reduce / multimem.st)" if (system.optimizer.nvls and all(sb.mc_grads and sb.mc_params for sb in system.optimizer.shards.values()))
+          else "NVLink peer loads / stores)")) if getattr(system.optimizer, "sharded", False)
         else "one flat-gradient all-reduce + Adam")
     if depth_batch:
         what += " (colour batch + depth-supervision batch, both coarse + fine)"

@@ -96,13 +96,15 @@ def _worker_sharded(rank, world, port, q):
         rays, ts = synthetic_sat_rays(3 * R, seed=17)
         g = torch.Generator().manual_seed(18)
         rgbs = torch.rand(3 * R, 3, generator=g)
-        finals = []
-        for sharded in (True, False):
-            a = make_args(fc_units=128, precision="tc", lr=5e-4, batch_size=R, sharded_adam=sharded)
+        finals, has_mc = [], None
+        for sharded, nvls in ((True, True), (True, False), (False, False)):
+            a = make_args(fc_units=128, precision="tc", lr=5e-4, batch_size=R, sharded_adam=sharded, sharded_nvls=nvls)
             torch.manual_seed(5)                            # same initialisation and noise on both runs
             system = trn.NeRFSystem(a, dev, train_len=3 * R)
             system.configure_optimizers()
             assert system.optimizer.sharded == sharded
+            if sharded and nvls:
+                has_mc = all(sb.mc_params and sb.mc_grads for sb in system.optimizer.shards.values())
             for it in range(3):
                 lo, hi = sdist.shard_bounds(R, rank, world)
                 sl = slice(it * R + lo, it * R + hi)
@@ -111,17 +113,16 @@ def _worker_sharded(rank, world, port, q):
                 system.optimization_step(batch)
             torch.cuda.synchronize()
             finals.append((system.models["coarse"].flat_params().clone(), system.models["t"].weight.detach().clone()))
-        (pa, ta), (pb, tb) = finals
-        ok, msg = True, ""
-        # fused reduce + Adam + deliver step == all-reduce + Adam: the same sum of two ranks' gradients, the same update arithmetic
-        e1 = float((pa - pb).abs().max()); e2 = float((ta - tb).abs().max())
-        if e1 > 1e-7 or e2 > 1e-7:
-            ok, msg = False, f"sharded vs all-reduce: params {e1}, embedding {e2}"
-        ref = pa.clone(); dist.broadcast(ref, 0)
-        if not torch.equal(ref, pa):
-            ok, msg = False, "replicas differ after the sharded step"
-        if float((pa - finals[0][0]).abs().max()) != 0:
-            ok = False
+        ok, msg = True, f"multicast mappings: {has_mc}"
+        pb, tb = finals[2]
+        for name, (pa, ta) in (("multimem", finals[0]), ("peer", finals[1])):
+            # fused reduce + Adam + deliver step == all-reduce + Adam: the same sum of two ranks' gradients, the same update arithmetic
+            e1 = float((pa - pb).abs().max()); e2 = float((ta - tb).abs().max())
+            if e1 > 1e-7 or e2 > 1e-7:
+                ok, msg = False, f"sharded ({name}) vs all-reduce: params {e1}, embedding {e2}"
+            ref = pa.clone(); dist.broadcast(ref, 0)
+            if not torch.equal(ref, pa):
+                ok, msg = False, f"replicas differ after the sharded step ({name})"
         q.put((rank, ok, msg))
     finally:
         dist.destroy_process_group()
@@ -129,9 +130,10 @@ def _worker_sharded(rank, world, port, q):
 
 @pytest.mark.timeout(300)
 def test_sharded_adam_step_equals_all_reduce_plus_adam():
-    """The data-parallel step fused with its collective (snb_adam_step_sharded over symmetric memory: peer loads of the gradient
-    shards, Adam, peer stores of the parameters) against all-reduce + snb_adam_step over three steps: <= 1e-7 on parameters of
-    O(0.1) (two ranks: the same two-term sums), replicas bit-identical."""
+    """The data-parallel step fused with its collective (snb_adam_step_sharded_multi over symmetric memory, one launch for the field
+    and the embedding) against all-reduce + snb_adam_step over three steps, in both variants -- in-switch reduction / multicast
+    delivery (`multimem.ld_reduce` / `multimem.st`, when the allocations have multicast mappings) and peer loads / stores:
+    <= 1e-7 on parameters of O(0.1) (two ranks: the same two-term sums), replicas bit-identical."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -144,6 +146,7 @@ def test_sharded_adam_step_equals_all_reduce_plus_adam():
     res = [q.get(timeout=240) for _ in procs]
     for p in procs:
         p.join(timeout=30)
+    print(res)
     assert sorted(r[:2] for r in res) == [(0, True), (1, True)], res
 
 

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(capi.exported_symbols())
-    assert lib.snb_abi_version() == 4
+    assert lib.snb_abi_version() == 5
 
 
 def test_dev_library_exports_its_header():
