@@ -146,3 +146,49 @@ def test_device_ray_sampler_has_dataloader_semantics():
     batches = list(combined_loader({"color": sm, "depth": depth}))
     assert len(batches) == 4 and all(set(b) == {"color", "depth"} for b in batches)
     assert "depths" in batches[0]["depth"] and batches[2]["depth"]["rays"].shape[0] == 256
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The drop-in boundary is a C ABI: every ctypes.Structure of satnerf_b200/capi.py must have the size and the field offsets a C
+    compiler gives the struct of include/satnerf_b200.h it mirrors (a probe program is compiled with gcc against the header)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from satnerf_b200 import capi
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"snb_field_desc": capi.FieldDesc, "snb_pass_desc": capi.PassDesc, "snb_loss_desc": capi.LossDesc, "snb_render_io": capi.RenderIO,
+             "snb_render_grads": capi.RenderGrads, "snb_rpc_model": capi.RpcModel, "snb_sharded_buffer": capi.ShardedBuffer}
+    header = open(os.path.join(ROOT, "include", "satnerf_b200.h")).read()
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "satnerf_b200.h"', "int main(void) {"]
+    want = {}
+    for cname, cls in pairs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S)
+        assert body, cname
+        body_txt = re.sub(r"/\*.*?\*/", "", body.group(1), flags=re.S)
+        fields = []
+        for decl in body_txt.split(";"):                          # `type a, b[20], *c`
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = [re.sub(r"\[.*?\]", "", n).strip().lstrip("*").strip() for n in re.sub(r"^.*?([\w\*\[\]]+(?:\s*,\s*[\w\*\[\]]+)*)$", r"\1", decl).split(",")]
+            fields += [n for n in names if n]
+        py_fields = [f[0].rstrip("_") for f in cls._fields_]
+        assert [f.rstrip("_") for f in fields] == py_fields, (cname, fields, py_fields)
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f, pf in zip(fields, cls._fields_):
+            lines.append(f'  printf("{cname} {pf[0]} %zu\\n", offsetof({cname}, {f}));')
+        want[cname] = cls
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, text=True).stdout
+    for ln in out.splitlines():
+        cname, what, val = ln.split()
+        cls = want[cname]
+        if what == "size":
+            assert C.sizeof(cls) == int(val), (cname, C.sizeof(cls), val)
+        else:
+            assert getattr(cls, what).offset == int(val), (cname, what, getattr(cls, what).offset, val)
