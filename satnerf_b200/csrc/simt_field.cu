@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) linear_fwd_narrow_kernel(LinFwd p) {
 // (the lo x lo term is 2^-22 of the product and dropped).  One CTA = 128 rows x `nt` <= 256 columns.  K runs over the two
 // sources one after the other (each padded to whole 64-wide slabs, so the loads of the wide source stay aligned whatever the
 // width of the narrow one).
-//   weights: split ONCE per pass by x3_pack_kernel into ready-made 128B-swizzled hi / lo tiles (scaled by 2^8) in the caller's
+//   weights: split ONCE per pass by x3_pack_kernel into ready-made 128B-swizzled hi / lo tiles (scaled per row by 2^e) in the caller's
 //            workspace; a producer warp brings them in with two bulk copies per slab (2-stage ring, mbarrier transaction counts);
 //   activations: split on the fly -- 16 warps read the fp32 rows (one warp instruction = one 256-byte row segment, two floats
 //            per lane; 8 rows per thread and slab), the loads running two slabs ahead of the split in registers;
@@ -308,8 +308,9 @@ using namespace ptx;
 constexpr int X3_NT = 256;                      // columns per CTA at most (UMMA N)
 constexpr int X3_STAGE = 2 * 16384 + 2 * X3_NT * 128;      // A_hi | A_lo | W_hi | W_lo
 constexpr int X3_THREADS = 512;                 // 16 converter / epilogue warps (the split stream is latency-bound with fewer) + producer warp + issuer warp
-constexpr float X3_WSCALE = 256.f;              // weights enter as 256 w (exact), the accumulator leaves as acc / 256: SIREN-scale weights
-                                                // (|w| ~ 4e-3 at h = 512) keep a NORMAL fp16 lo part; |w| < 255 is required (inf otherwise)
+// Weight rows are pre-scaled by a power of two chosen per output row (2^e with max_k |2^e W[n][k]| in [2048, 4096): exact, no
+// fp16 overflow whatever the weights' magnitude, and SIREN-scale weights (|w| ~ 4e-3 at h = 512) keep a NORMAL fp16 lo part); the
+// epilogue multiplies column n of the accumulator by 2^-e (a float per column stored behind the layer's tiles).
 
 __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void x3_split(float x0, float x1, uint32_t* hi, uint32_t* lo) {
@@ -344,20 +345,35 @@ template <int ACT> __device__ __forceinline__ float x3_act(float y) {
     return act_fwd<ACT>(y);
 }
 
-static size_t x3_layer_bytes(int N, int k0, int k1) { return (size_t)(ceil_div(k0, 64) + ceil_div(k1, 64)) * 2 * ((N + 15) & ~15) * 128; }
+static size_t x3_tile_bytes(int N, int k0, int k1) { return (size_t)(ceil_div(k0, 64) + ceil_div(k1, 64)) * 2 * ((N + 15) & ~15) * 128; }
+static size_t x3_layer_bytes(int N, int k0, int k1) { return x3_tile_bytes(N, k0, k1) + (((size_t)((N + 15) & ~15) * 4 + 1023) & ~(size_t)1023); }   // + 2^-e per row
 
-// W (N x [k_a0 | k_a1], row-major, leading dimension ldw) -> per slab: hi tile | lo tile, each n16 rows x 128 B, 128B-swizzled K-major
-__global__ void __launch_bounds__(256) x3_pack_kernel(const float* __restrict__ W, int ldw, int N, int n16, int k_a0, int k_a1, unsigned char* __restrict__ dst) {
-    const int s0 = (k_a0 + 63) / 64, s = blockIdx.x, lane = threadIdx.x & 31, r = blockIdx.y * 8 + (threadIdx.x >> 5);
+// W (N x [k_a0 | k_a1], row-major, leading dimension ldw) -> per slab: hi tile | lo tile, each n16 rows x 128 B, 128B-swizzled K-major;
+// behind the tiles: inv_scale[n16] = 2^-e of every row.  One warp per row: row maximum first, then the slabs.
+__global__ void __launch_bounds__(256) x3_pack_kernel(const float* __restrict__ W, int ldw, int N, int n16, int k_a0, int k_a1, unsigned char* __restrict__ dst,
+                                                      float* __restrict__ inv_scale) {
+    const int s0 = (k_a0 + 63) / 64, n_slabs = s0 + (k_a1 + 63) / 64, lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n16) return;
-    const bool second = s >= s0;
-    const int k = (second ? s - s0 : s) * 64 + 2 * lane, k_end = second ? k_a1 : k_a0;
-    const float* row = W + (size_t)r * ldw + (second ? k_a0 : 0);
-    const float x0 = (r < N && k < k_end) ? row[k] * X3_WSCALE : 0.f, x1 = (r < N && k + 1 < k_end) ? row[k + 1] * X3_WSCALE : 0.f;
-    uint32_t hi, lo; x3_split(x0, x1, &hi, &lo);
-    unsigned char* t = dst + (size_t)s * 2 * n16 * 128 + (size_t)r * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
-    *reinterpret_cast<uint32_t*>(t) = hi;
-    *reinterpret_cast<uint32_t*>(t + (size_t)n16 * 128) = lo;
+    const float* row = W + (size_t)r * ldw;
+    float mx = 0.f;
+    if (r < N) for (int k = lane; k < k_a0 + k_a1; k += 32) mx = fmaxf(mx, fabsf(row[k]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // 2^e with 2^e mx in [2048, 4096) (mx = 0, inf or nan: e = 0)
+    int e = 0;
+    if (mx > 0.f && mx < 3.0e38f) { int ex; frexpf(mx, &ex); e = 12 - ex; e = e < -100 ? -100 : (e > 100 ? 100 : e); }
+    const float scale = ldexpf(1.f, e);
+    if (lane == 0) inv_scale[r] = ldexpf(1.f, -e);
+    for (int s = 0; s < n_slabs; ++s) {
+        const bool second = s >= s0;
+        const int k = (second ? s - s0 : s) * 64 + 2 * lane, k_end = second ? k_a1 : k_a0;
+        const float* q = row + (second ? k_a0 : 0);
+        const float x0 = (r < N && k < k_end) ? q[k] * scale : 0.f, x1 = (r < N && k + 1 < k_end) ? q[k + 1] * scale : 0.f;
+        uint32_t hi, lo; x3_split(x0, x1, &hi, &lo);
+        unsigned char* t = dst + (size_t)s * 2 * n16 * 128 + (size_t)r * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2);
+        *reinterpret_cast<uint32_t*>(t) = hi;
+        *reinterpret_cast<uint32_t*>(t + (size_t)n16 * 128) = lo;
+    }
 }
 
 // slab `it` of the CTA's A tile: this thread's 8 rows (warp + 16 j), columns 2 lane, 2 lane + 1 of the slab
@@ -399,7 +415,7 @@ __device__ __forceinline__ void x3_load(const LinFwd& p, int m0, int s0, int n_s
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(X3_THREADS + 64, 1) linear_fwd_x3_kernel(LinFwd p, int nt_tile, const unsigned char* __restrict__ wpk, int n16) {
+__global__ void __launch_bounds__(X3_THREADS + 64, 1) linear_fwd_x3_kernel(LinFwd p, int nt_tile, const unsigned char* __restrict__ wpk, const float* __restrict__ inv_scale, int n16) {
     extern __shared__ unsigned char x3_raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)x3_raw + 1023) & ~(uintptr_t)1023);
     // mbarriers: [0,1] stage consumed by its MMAs; [2] accumulator complete; [3,4] weight tiles landed; [5,6] A tiles written (16 warps)
@@ -501,7 +517,7 @@ __global__ void __launch_bounds__(X3_THREADS + 64, 1) linear_fwd_x3_kernel(LinFw
             __syncwarp();
             if (c0 + lane < nv) {
                 const int n = n0 + c0 + lane;
-                const float bias = p.b[n];
+                const float bias = p.b[n], inv = inv_scale[n];
                 float* out = p.out + (size_t)(m0 + quad * 32) * p.ldo + n;
                 float* pre = p.pre ? p.pre + (size_t)(m0 + quad * 32) * p.N + n : nullptr;
                 const size_t ldo = (size_t)p.ldo, ldp = (size_t)p.N;
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(X3_THREADS + 64, 1) linear_fwd_x3_kernel(LinFw
                 for (int r = 0; r < 32; ++r) {
                     if (r < rows) {
                         float a; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a) : "r"(sc + (uint32_t)r * 132u));
-                        const float y = fmaf(a, 1.f / X3_WSCALE, bias);
+                        const float y = fmaf(a, inv, bias);
                         if (pre) pre[r * ldp] = y;
                         out[r * ldo] = x3_act<ACT>(y);
                     }
@@ -530,15 +546,15 @@ static int launch_x3(const LinFwd& p, cudaStream_t st, unsigned char* wpk, bool 
     const size_t smem = 2 * (size_t)X3_STAGE + 1024 + 64;
     SNB_CUDA(cudaFuncSetAttribute(linear_fwd_x3_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     // (per device: not cached)
     const int n16 = (p.N + 15) & ~15;
+    float* inv_scale = reinterpret_cast<float*>(wpk + x3_tile_bytes(p.N, p.a0.k, p.a1.k));
     if (pack_now) {
-        dim3 g(ceil_div(p.a0.k, 64) + ceil_div(p.a1.k, 64), ceil_div(n16, 8));
-        x3_pack_kernel<<<g, 256, 0, st>>>(p.W, p.ldw, p.N, n16, p.a0.k, p.a1.k, wpk);
+        x3_pack_kernel<<<ceil_div(n16, 8), 256, 0, st>>>(p.W, p.ldw, p.N, n16, p.a0.k, p.a1.k, wpk, inv_scale);
         SNB_CHECK_LAUNCH();
     }
     // 256-column tiles unless that leaves most SMs without a CTA (the h/2-wide head layers of one chunk)
     const int nt_tile = (p.N > 128 && ceil_div(p.M, 128) * ceil_div(p.N, X3_NT) < 100) ? 128 : X3_NT;
     dim3 g(ceil_div(p.M, 128), ceil_div(p.N, nt_tile));
-    linear_fwd_x3_kernel<ACT><<<g, X3_THREADS + 64, smem, st>>>(p, nt_tile, wpk, n16);
+    linear_fwd_x3_kernel<ACT><<<g, X3_THREADS + 64, smem, st>>>(p, nt_tile, wpk, inv_scale, n16);
     SNB_CHECK_LAUNCH();
     return 0;
 }

@@ -293,7 +293,7 @@ def test_field_forward_tensor_cores_hi_lo(model, h):
     """<Field>.forward with the contractions on the tensor cores at fp16 hi+lo operand precision (SNB_FP16X3_TC, the default of
     the per-point API on sm_100) against the float64 oracle, on ragged point counts and widths that are not multiples of the tile.
     Gates (max-abs / max-ref per output column): FFMA path 3e-6 (measures ~1e-6), hi+lo path 8e-6 (measures 1e-6 at h <= 256 and
-    3.8e-6 at h = 512 -- the same figure with and without the 2^8 weight pre-scale, i.e. it is the tensor core's truncating
+    3.8e-6 at h = 512 -- the same figure with and without the power-of-two weight pre-scale, i.e. it is the tensor core's truncating
     fp32 accumulation over K / 16 x 3 steps, not the operand split)."""
     import satnerf_b200 as sb
     args = make_args(model=model, fc_units=h)
