@@ -326,6 +326,33 @@ def test_field_forward_tensor_cores_hi_lo(model, h):
     assert e_sig < 8e-6, e_sig
 
 
+def test_tcx3_weight_rows_beyond_the_fp16_range():
+    """The hi+lo path scales every weight row by its own power of two before the fp16 split: rows 300x (beyond 65504 / 256: a fixed
+    2^8 pre-scale overflowed to inf there) and 1e-6x the default scale must give finite results that track the FFMA path (the sines
+    amplify the 4e-6 base difference by the row scale: bound 1e-2 of each column's range)."""
+    import satnerf_b200 as sb
+    args = make_args(fc_units=256)
+    torch.manual_seed(41)
+    m = sb.load_model(args)
+    with torch.no_grad():
+        m.feats_from_xyz.weight[:40].mul_(300.0 * 256.0 / 16.0)        # |w| up to ~ 300: 256 w > 65504
+        m.fc_net[6].weight[7].mul_(1e-6)
+    g = torch.Generator().manual_seed(42)
+    B = 4099
+    xyz, sun, t = torch.rand(B, 3, generator=g) * 2 - 1, torch.rand(B, 3, generator=g), torch.randn(B, 4, generator=g)
+    m = m.cuda()
+    assert float(m.feats_from_xyz.weight.abs().max()) * 256.0 > 65504.0
+    outs = {}
+    with torch.no_grad():
+        for prec in ("fp32", "tcx3"):
+            m.points_precision = prec
+            outs[prec] = m(xyz.cuda(), input_sun_dir=sun.cuda(), input_t=t.cuda()).cpu().double()
+    assert torch.isfinite(outs["tcx3"]).all()
+    err = float(((outs["tcx3"] - outs["fp32"]).abs().amax(0) / outs["fp32"].abs().amax(0).clamp_min(1e-30)).max())
+    print("tcx3 vs FFMA with 300x rows:", err)
+    assert err < 1e-2, err
+
+
 @pytest.mark.parametrize("model", ["sat-nerf", "s-nerf", "nerf"])
 def test_field_forward_is_differentiable(model):
     """<Field>.forward under autograd (models/satnerf.py:156-208, snerf.py:148-196, nerf.py:184-227): parameter gradients and the
