@@ -5,6 +5,7 @@ import argparse
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -192,3 +193,40 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
             assert C.sizeof(cls) == int(val), (cname, C.sizeof(cls), val)
         else:
             assert getattr(cls, what).offset == int(val), (cname, what, getattr(cls, what).offset, val)
+
+
+def test_x3_sine_constants_give_fp32_level_accuracy():
+    """The epilogue sine of the hi+lo tensor-core path (x3_sin, csrc/simt_field.cu) restated in numpy float32 with the constants
+    READ FROM THE SOURCE: magic-number rint(y / pi), three-term Cody-Waite reduction, odd degree-11 polynomial, sign from the
+    parity of k.  Max abs error against float64 < 2e-7 for |y| <= 8000 (libm's float sine: 0.7e-7), and the three reduction
+    constants must sum to pi."""
+    src = open(os.path.join(ROOT, "satnerf_b200", "csrc", "simt_field.cu")).read()
+    body = src[src.index("__device__ __forceinline__ float x3_sin(float y)"):]
+    body = body[:body.index("template <int ACT> __device__ __forceinline__ float x3_act")]
+    num = r"(-?\d+\.\d*(?:e-?\d+)?)f"
+    inv_pi, magic = (np.float32(x) for x in re.search(r"fmaf\(y, %s, %s\)" % (num, num), body).groups())
+    pis = [np.float32(x) for x in re.findall(r"r = fmaf\(k, %s," % num, body)]
+    q = re.search(r"fmaf\(%s, r2, %s\)" % (num, num), body).groups() + tuple(re.findall(r"q = fmaf\(q, r2, %s\)" % num, body))
+    coef = [np.float32(x) for x in q]                      # c11, c9, c7, c5, c3
+    assert len(pis) == 3 and len(coef) == 5 and magic == np.float32(12582912.0)
+    assert abs(-sum(float(p) for p in pis) - np.pi) < 1e-13
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+    rng = np.random.default_rng(3)
+    for lim in (4.0, 60.0, 8000.0):
+        y = rng.uniform(-lim, lim, 400000).astype(np.float32)
+        t = fma(y, inv_pi, np.full_like(y, magic))
+        k = (t - magic).astype(np.float32)
+        r = y
+        for p in pis:
+            r = fma(k, p, r)
+        r2 = (r * r).astype(np.float32)
+        acc = (np.full_like(y, coef[0]).astype(np.float64) * r2 + np.float64(coef[1])).astype(np.float32)
+        for c in coef[2:]:
+            acc = (acc.astype(np.float64) * r2 + np.float64(c)).astype(np.float32)
+        s = ((r * r2).astype(np.float32).astype(np.float64) * acc + r).astype(np.float32)
+        s = np.where((t.view(np.int32) & 1).astype(bool), -s, s)
+        err = float(np.abs(s.astype(np.float64) - np.sin(y.astype(np.float64))).max())
+        assert err < 2e-7, (lim, err)
